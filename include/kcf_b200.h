@@ -1,0 +1,168 @@
+/*
+ * kcf_b200.h — C ABI of libkcfgpu.so, the B200 (sm_100a) implementation of kcftools'
+ * `getVariations` hot path.  Plain C types only; no C++/torch types, no callbacks.
+ *
+ * What it replaces in the reference (sivasubramanics/kcftools v0.4.0; paths under
+ * src/main/java/nl/wur/bis/kcftools/): the thread-pool fan-out and per-window scan in
+ * Plugins/GetVariants.java:126-159 (processWindow :202-261), together with everything
+ * that scan calls: Data/KMC.java (database open :56-189, getCount :292-326),
+ * Data/Kmer.java, Data/Signature.java, Data/Fasta.java:90-167 and the substring
+ * extraction of Data/FastaIndex.java:122-182.  The CLI, window generation, GTF parsing
+ * and KCF emission stay on the host side (INTEGRATION.md shows the JNI / FFM binding).
+ *
+ * Conventions
+ *   - every function returns KCF_OK (0) or a negative kcf_status; the message for the
+ *     last failure on a context is kcf_last_error(ctx).  Where the reference calls
+ *     Logger.error (print + System.exit(1), Utils/Logger.java:29-31) this library
+ *     returns an error code instead; the Java shim maps non-zero to Logger.error.
+ *   - the caller owns every input and output buffer; the library copies what it needs
+ *     before returning and keeps no caller pointer.  Handles are opaque and are freed
+ *     only by the matching close/destroy call.
+ *   - there is NO CPU fallback: without a CUDA device, or for a database outside the
+ *     supported envelope, the call fails.
+ *   - one context drives one GPU (one process or thread per GPU); a context serialises
+ *     its own stream.  Different contexts may be used concurrently.
+ */
+#ifndef KCF_B200_H
+#define KCF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum kcf_status {
+    KCF_OK = 0,
+    KCF_ERR_CUDA = -1,          /* CUDA runtime failure or no device */
+    KCF_ERR_IO = -2,            /* cannot read .kmc_pre / .kmc_suf */
+    KCF_ERR_DB_FORMAT = -3,     /* not a KMC 0x200 database (KMC.java:139-141) or inconsistent sizes / LUT */
+    KCF_ERR_UNSUPPORTED = -4,   /* valid database outside the envelope (k > 32, (k-P) % 4 != 0, counter > 4 B, ...) */
+    KCF_ERR_ARG = -5,           /* bad argument (null handle, min_count < 1 as GetVariants.java:383-385, ...) */
+    KCF_ERR_RANGE = -6,         /* window segment outside its sequence (FastaIndex.java:132-135) or no segment (GetVariants.java:213-216) */
+    KCF_ERR_FASTA = -7,         /* read past the mapped sequence bytes, e.g. no trailing newline (FastaIndex.java:175-177) */
+    KCF_ERR_WEIGHTS = -8,       /* wi + wt + wr != 1.0 when a score had to be computed (Data.java:101-103) */
+    KCF_ERR_NOMEM = -9,         /* device or host allocation failed */
+    KCF_ERR_DB_ORDER = -10      /* records of one (bin, prefix) range not strictly ascending: the reference's binary search is undefined */
+} kcf_status;
+
+typedef struct kcf_ctx kcf_ctx;   /* one GPU + its stream + the resident reference sequences */
+typedef struct kcf_db kcf_db;     /* one KMC database resident in HBM (replaces the KMC object, Data/KMC.java) */
+typedef struct kcf_plan kcf_plan; /* a window list resident on the device, reusable across databases */
+
+/* One output row = one window (what processWindow delivers through Window.addTotalKmers / setEffLength /
+ * addData, GetVariants.java:254-258).  48 bytes, natural alignment. */
+typedef struct kcf_result_t {
+    int32_t total_kmers;     /* TOTAL_KMERS column */
+    int32_t eff_len;         /* EFFLEN, Fasta.getEffectiveATGCCount (Fasta.java:140-167) */
+    int32_t obs;             /* OB */
+    int32_t variations;      /* VA */
+    int32_t inner;           /* ID */
+    int32_t left;            /* LD */
+    int32_t right;           /* RD */
+    int32_t _pad;
+    int64_t kmer_count_sum;  /* Σ count over observed k-mers; KD = sum / obs (Data.java:87) */
+    double score;            /* SC, Data.computeScore (Data.java:95-107); Java recomputes it from the integers */
+} kcf_result_t;
+
+/* A window is the concatenation of n_segs segments starting at segs[first_seg]
+ * (fixed / sliding window: 1 segment, Window.java:224-226; gene / transcript: the merged exon loci in
+ * concatenation order, GTF.java:223-248). */
+typedef struct kcf_window_t {
+    uint32_t first_seg;
+    uint32_t n_segs;
+} kcf_window_t;
+
+typedef struct kcf_segment_t {
+    int32_t seq_id;   /* id returned by kcf_ref_add */
+    int32_t start0;   /* 0-based start on the sequence */
+    int32_t len;      /* number of bases (> 0) */
+} kcf_segment_t;
+
+typedef struct kcf_db_info_t {
+    int32_t kmer_length;        /* KMC.getKmerLength() */
+    int32_t lut_prefix_length;  /* KMC.getPrefixLength() */
+    int32_t signature_length;
+    int32_t counter_size;
+    int32_t both_strands;       /* KMC.isBothStrands(): 1 when the stored flag byte is 0 */
+    int32_t min_count;
+    int32_t max_count;
+    int32_t n_bins;
+    int64_t total_kmers;        /* records in .kmc_suf */
+    int64_t resident_kmers;     /* records a reference getCount() can return (inserted in the HBM table) */
+    int64_t unreachable_kmers;  /* records no reference lookup can ever reach (wrong bin / non-canonical / before LUT[0]) */
+    int64_t stash_kmers;        /* resident records living in the overflow stash */
+    int64_t table_bytes;        /* HBM bytes of the lookup structure */
+    int64_t n_buckets;          /* 32-byte buckets */
+    double load_seconds;        /* wall time of the open call */
+} kcf_db_info_t;
+
+/* ---- context ------------------------------------------------------------------------- */
+/* device: CUDA ordinal (LOCAL_RANK in a one-process-per-GPU job). */
+int kcf_init(int device, kcf_ctx **out);
+void kcf_shutdown(kcf_ctx *ctx);
+const char *kcf_last_error(kcf_ctx *ctx); /* ctx may be NULL: message of the last failed kcf_init */
+/* The CUDA stream (cudaStream_t) every call on this context is ordered on; lets a caller time the
+ * kernels with events on the launching stream. */
+void *kcf_stream(kcf_ctx *ctx);
+/* Pinned host memory for callers that want asynchronous full-rate copies (optional). */
+int kcf_host_alloc(kcf_ctx *ctx, uint64_t n_bytes, void **out);
+void kcf_host_free(kcf_ctx *ctx, void *p);
+
+/* ---- database: replaces `new KMC(prefix, inMemory)` (KMC.java:56-78) ------------------- */
+/* placement: 0 = whole database resident on this context's GPU (replicated across contexts);
+ *            1 = this context keeps only the slice rank/world of the mixed-key space
+ *                (prefix partition; see kcf_db_open_part). */
+int kcf_db_open(kcf_ctx *ctx, const char *kmc_prefix, int placement, kcf_db **out);
+/* Same, from the byte images of the two files (what the reference mmaps, KMC.java:112, 173-189). */
+int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_len, const uint8_t *suf, uint64_t suf_len,
+                    int placement, kcf_db **out);
+int kcf_db_info(kcf_db *db, kcf_db_info_t *out);
+void kcf_db_close(kcf_db *db);
+/* Load-factor target for subsequently opened databases (0 < lf <= 0.9; default 0.5). */
+int kcf_set_load_factor(kcf_ctx *ctx, double lf);
+
+/* KMC.getCount for a batch of k-mers given as ASCII (n * k bytes, upper or lower case ACGT), canonicalised
+ * per the database's both_strands flag like GetVariants.java:222-223.  counts_out[i] is the Java int.
+ * Exists for parity tests of the lookup structure. */
+int kcf_db_count(kcf_ctx *ctx, kcf_db *db, const char *kmers_ascii, uint64_t n, int32_t *counts_out);
+
+/* ---- reference sequences: replaces the per-sequence mmap of FastaIndex (FastaIndex.java:26-77) */
+/* bytes = the raw file bytes of one sequence from its .faidx offset to the next sequence's offset (or EOF),
+ * newlines included; line_bases / line_width / seq_len are the .faidx columns. */
+int kcf_ref_add(kcf_ctx *ctx, const uint8_t *fasta_seq_bytes, uint64_t n_bytes, uint32_t line_bases,
+                uint32_t line_width, uint64_t seq_len, int *seq_id_out);
+int kcf_ref_clear(kcf_ctx *ctx);
+
+/* ---- screening: replaces GetVariants.java:126-159 ---------------------------------------- */
+/* One call screens all windows against the database and fills out[n_wins].
+ * w = {wi, wt, wr} = {--wi, --wt, --wr} in the order of getWeights() (GetVariants.java:388-390). */
+int kcf_screen(kcf_ctx *ctx, kcf_db *db, const kcf_window_t *wins, uint64_t n_wins, const kcf_segment_t *segs,
+               uint64_t n_segs, int32_t min_count, const double w[3], kcf_result_t *out);
+
+/* The same in three steps, for callers that screen one window list against many databases (cohorts)
+ * or want the device-resident part timed alone. */
+int kcf_plan_create(kcf_ctx *ctx, int32_t kmer_length, const kcf_window_t *wins, uint64_t n_wins,
+                    const kcf_segment_t *segs, uint64_t n_segs, kcf_plan **out);
+int kcf_plan_run(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t min_count, const double w[3]); /* asynchronous on kcf_stream */
+int kcf_plan_fetch(kcf_ctx *ctx, kcf_plan *plan, kcf_result_t *out);                              /* D2H + synchronise */
+void kcf_plan_destroy(kcf_plan *plan);
+/* Σ total_kmers of the last run and the number of kernels launched by it. */
+int kcf_plan_stats(kcf_plan *plan, uint64_t *n_tiles, uint64_t *n_positions, uint32_t *kernels_per_run);
+/* Per-valid-k-mer counts of one window of the last run (debug / parity; runs a separate pass). */
+int kcf_window_counts(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, uint64_t window, int32_t *counts_out, uint64_t cap,
+                      uint64_t *n_out);
+
+/* ---- measurement helpers ------------------------------------------------------------------ */
+/* Random 32-byte-sector gather bandwidth of this GPU (the random-access roofline of SURVEY §8(d)):
+ * n_loads independent 32-B loads from uniformly random sector addresses of a buffer of n_bytes. */
+int kcf_measure_random_sector_gbps(kcf_ctx *ctx, uint64_t n_bytes, uint64_t n_loads, int repeats, double *gbps_out);
+/* Milliseconds of the screening kernel in the last kcf_plan_run when profiling is on. */
+int kcf_set_profiling(kcf_ctx *ctx, int on);
+int kcf_last_kernel_ms(kcf_ctx *ctx, float *screen_ms, float *finalize_ms);
+const char *kcf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KCF_B200_H */

@@ -1,0 +1,499 @@
+// kcf_db.cu — K1: KMC 0x200 database ingest and re-layout into the HBM-resident table.
+//
+// Replaces `new KMC(prefix, inMemory)` (KMC.java:56-189).  The file layout is parsed exactly as
+// readPrefixFile does (KMC.java:107-168); the records of .kmc_suf are streamed through pinned
+// staging buffers and re-keyed on the device.  A record is inserted only if a reference lookup
+// could return it, i.e. if it sits in the (bin, prefix) range that getCount (KMC.java:292-326)
+// would search for that very k-mer: its signature (Kmer.java:105-118, Signature.java:23-37) must
+// map to the bin that holds it and, for a both-strands database, it must be its own canonical
+// form (Kmer.java:72-79).  That proof is done once per record here, so the screening kernel needs
+// neither signatures nor the per-bin LUTs.
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include "kcf_internal.cuh"
+#include "kcf_lookup.cuh"
+
+
+// ---- Signature.java:23-95 on the device: one thread per m-mer -----------------------------------
+__device__ __forceinline__ bool sig_allowed(uint32_t s, int L)
+{
+    if ((s & 0x3F) == 0x3F) return false; // TTT suffix
+    if ((s & 0x3F) == 0x3B) return false; // TGT suffix
+    if ((s & 0x3C) == 0x3C) return false; // TG* suffix
+    for (int j = 0; j < L - 3; ++j) {
+        if ((s & 0xF) == 0) return false; // AA inside
+        s >>= 2;
+    }
+    if (s == 0) return false;    // AAA prefix
+    if (s == 0x04) return false; // ACA prefix
+    if ((s & 0xF) == 0) return false; // *AA prefix
+    return true;
+}
+
+__global__ void kcf_norm_kernel(int L, uint32_t *__restrict__ norm)
+{
+    uint32_t special = 1u << (2 * L);
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= special) return;
+    uint32_t rev = 0, t = i;
+    for (int j = 0; j < L; ++j) {
+        rev = (rev << 2) | ((~t) & 3u);
+        t >>= 2;
+    }
+    uint32_t a = sig_allowed(i, L) ? i : special;
+    uint32_t b = sig_allowed(rev, L) ? rev : special;
+    norm[i] = min(a, b);
+}
+
+// LUT must be non-decreasing and bounded by total (else the reference reads garbage ranges)
+__global__ void kcf_lut_check_kernel(const uint64_t *__restrict__ lut, uint64_t n, uint64_t total, uint32_t *flags)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t v = lut[i];
+    bool bad = v > total;
+    if (i + 1 < n && lut[i + 1] < v) bad = true;
+    if (bad) atomicOr(&flags[FLAG_LUT_BAD], 1u);
+}
+
+struct KcfIngestParams {
+    const uint8_t *rec;      // staged records of this chunk
+    uint64_t rec0;           // global index of the first staged record
+    uint64_t n_rec;
+    uint8_t prev[16];        // record rec0-1 (valid when rec0 > 0)
+    const uint64_t *lut;
+    uint64_t lut_len;
+    const uint32_t *sigmap;
+    const uint32_t *norm;
+    uint32_t P, L, nsb, cs, rec_size;
+    uint64_t *table;
+    KcfStashEntry *ovf;      // overflow list
+    uint64_t ovf_cap;
+    unsigned long long *counters; // [0] inserted, [1] unreachable, [2] overflow
+    uint32_t *flags;
+};
+
+__global__ void __launch_bounds__(256) kcf_ingest_kernel(KcfIngestParams p, KcfTableGeom g)
+{
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.n_rec) return;
+    const uint64_t i = p.rec0 + t;
+    // (bin, prefix) range holding record i: last idx with lut[idx] <= i
+    uint64_t lo = 0, hi = p.lut_len;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (p.lut[mid] <= i) lo = mid + 1;
+        else hi = mid;
+    }
+    if (lo == 0) {
+        atomicAdd(&p.counters[1], 1ULL);
+        return;
+    }
+    const uint64_t idx = lo - 1;
+    const uint32_t bin = (uint32_t)(idx >> (2 * p.P));
+    const uint64_t prefix = idx & ((1ULL << (2 * p.P)) - 1);
+    const uint8_t *r = p.rec + t * p.rec_size;
+    uint64_t suffix = 0;
+    for (uint32_t j = 0; j < p.nsb; ++j) suffix = (suffix << 8) | r[j]; // big-endian suffix bytes (Kmer.java:166)
+    uint32_t count = 0;
+    for (uint32_t j = 0; j < p.cs; ++j) count |= (uint32_t)r[p.nsb + j] << (8 * j); // KMC.java:395-401
+    // strict ascending order inside the range, which the reference's binary search presumes
+    if (i > p.lut[idx]) {
+        const uint8_t *q = (t > 0) ? (r - p.rec_size) : p.prev;
+        uint64_t ps = 0;
+        for (uint32_t j = 0; j < p.nsb; ++j) ps = (ps << 8) | q[j];
+        if (ps >= suffix) atomicOr(&p.flags[FLAG_ORDER_BAD], 1u);
+    }
+    const uint32_t sbits = 8 * p.nsb;
+    const uint64_t kmer = (p.P > 0 ? (prefix << sbits) : 0ULL) | suffix;
+    bool reachable = true;
+    if (g.both_strands) {
+        uint64_t rc = kcf_revcomp(kmer, g.kshift);
+        if (kmer > rc) reachable = false; // a query is canonicalised first (GetVariants.java:222)
+    }
+    if (reachable) {
+        // signature = min norm over the k-L+1 m-mers, first base most significant (Kmer.java:105-118)
+        const uint32_t mmask = (1u << (2 * p.L)) - 1u;
+        uint32_t sig = 0xFFFFFFFFu;
+        for (int j = 0; j <= (int)g.k - (int)p.L; ++j) {
+            uint32_t m = (uint32_t)(kmer >> (2 * (g.k - p.L - j))) & mmask;
+            sig = min(sig, p.norm[m]);
+        }
+        if (p.sigmap[sig] != bin) reachable = false; // KMC.java:300
+    }
+    if (!reachable) {
+        atomicAdd(&p.counters[1], 1ULL);
+        return;
+    }
+    const uint64_t h = kcf_mix(kmer, g);
+    const uint64_t home = kcf_home_bucket(h, g);
+    const uint64_t rem = h & g.rmask;
+    for (uint32_t d = 0; d <= KCF_MAX_DISP; ++d) {
+        uint64_t b = home + d;
+        if (b >= g.n_buckets) b -= g.n_buckets;
+        const uint64_t entry = ((((uint64_t)(8u | d) << g.rbits) | rem) << g.cbits) | count;
+        unsigned long long *slot = (unsigned long long *)(p.table + 4 * b);
+        for (int s = 0; s < KCF_SLOTS_PER_BUCKET; ++s) {
+            if (slot[s] == 0ULL && atomicCAS(&slot[s], 0ULL, (unsigned long long)entry) == 0ULL) {
+                atomicAdd(&p.counters[0], 1ULL);
+                return;
+            }
+        }
+    }
+    unsigned long long pos = atomicAdd(&p.counters[2], 1ULL);
+    if (pos < p.ovf_cap) {
+        p.ovf[pos].key = kmer;
+        p.ovf[pos].meta = (1ULL << 63) | count;
+    }
+}
+
+__global__ void kcf_stash_build_kernel(const KcfStashEntry *__restrict__ ovf, uint64_t n, KcfStashEntry *stash, KcfTableGeom g)
+{
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    KcfStashEntry e = ovf[t];
+    uint64_t i = (kcf_mix(e.key, g) * 0x9E3779B97F4A7C15ULL) >> 20;
+    for (uint64_t k = 0;; ++k) {
+        KcfStashEntry *s = &stash[(i + k) & g.stash_mask];
+        if (atomicCAS((unsigned long long *)&s->meta, 0ULL, (unsigned long long)e.meta) == 0ULL) {
+            s->key = e.key; // keys are distinct; nobody reads them before the build kernel ends
+            return;
+        }
+    }
+}
+
+// ---- KMC.getCount for a batch of ASCII k-mers (parity helper) ----------------------------------
+__global__ void kcf_count_kernel(const char *__restrict__ ascii, uint64_t n, const uint64_t *__restrict__ table,
+                                 const KcfStashEntry *__restrict__ stash, KcfTableGeom g, int32_t *__restrict__ out)
+{
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const char *s = ascii + t * g.k;
+    uint64_t v = 0;
+    bool ok = true;
+    for (uint32_t j = 0; j < g.k; ++j) {
+        uint32_t b = (uint8_t)s[j];
+        uint32_t u = b & 0xDFu;
+        ok &= (u == 'A') | (u == 'C') | (u == 'G') | (u == 'T');
+        v = (v << 2) | (((b >> 1) & 3u) ^ ((b >> 2) & 1u));
+    }
+    if (!ok) {
+        out[t] = 0;
+        return;
+    }
+    if (g.both_strands) {
+        uint64_t rc = kcf_revcomp(v, g.kshift);
+        if (rc < v) v = rc;
+    }
+    out[t] = (int32_t)kcf_lookup(table, stash, g, v);
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+static uint32_t rd_u32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static uint64_t rd_u64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
+
+static int floor_log2_u64(uint64_t v)
+{
+    int r = -1;
+    while (v) { v >>= 1; ++r; }
+    return r;
+}
+
+extern "C" int kcf_set_load_factor(kcf_ctx *ctx, double lf)
+{
+    if (!ctx) return KCF_ERR_ARG;
+    if (!(lf > 0.0) || lf > 0.9) return kcf_fail(ctx, KCF_ERR_ARG, "load factor must be in (0, 0.9]");
+    ctx->load_factor = lf;
+    return KCF_OK;
+}
+
+extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_len, const uint8_t *suf, uint64_t suf_len,
+                               int placement, kcf_db **out)
+{
+    if (!ctx || !pre || !suf || !out) return KCF_ERR_ARG;
+    *out = nullptr;
+    if (placement != 0) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "placement %d: use kcf_db_open_part for a partitioned database", placement);
+    auto t0 = std::chrono::steady_clock::now();
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    // --- KMC.java:107-168 readPrefixFile ---
+    if (pre_len < 16) return kcf_fail(ctx, KCF_ERR_DB_FORMAT, ".kmc_pre too short");
+    const uint64_t file_size = pre_len;
+    const uint32_t header_offset = rd_u32(pre + file_size - 8);
+    if ((uint64_t)header_offset + 8 + 4 > file_size || header_offset < 68)
+        return kcf_fail(ctx, KCF_ERR_DB_FORMAT, "bad header offset %u", header_offset);
+    const uint8_t *h = pre + (file_size - header_offset - 8);
+    kcf_db_info_t info{};
+    info.kmer_length = (int32_t)rd_u32(h + 0);
+    /* mode */
+    info.counter_size = (int32_t)rd_u32(h + 8);
+    info.lut_prefix_length = (int32_t)rd_u32(h + 12);
+    info.signature_length = (int32_t)rd_u32(h + 16);
+    info.min_count = (int32_t)rd_u32(h + 20);
+    info.max_count = (int32_t)rd_u32(h + 24);
+    info.total_kmers = (int64_t)rd_u64(h + 28);
+    info.both_strands = (h[36] == 0) ? 1 : 0; // KMC.java:133
+    const uint32_t version = rd_u32(h + 64);
+    if (version != 0x200) return kcf_fail(ctx, KCF_ERR_DB_FORMAT, "KMC version is not 0x200 (found 0x%x)", version);
+    const int k = info.kmer_length, P = info.lut_prefix_length, L = info.signature_length, cs = info.counter_size;
+    if (k < 1 || P < 0 || P > k || L < 1 || cs < 0 || info.total_kmers < 0)
+        return kcf_fail(ctx, KCF_ERR_DB_FORMAT, "inconsistent header (k=%d P=%d L=%d counter=%d)", k, P, L, cs);
+    if (k > 32) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "k=%d > 32 is not supported by this build", k);
+    if ((k - P) % 4 != 0) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "(k - lut_prefix_length) %% 4 != 0 (k=%d P=%d)", k, P);
+    if (cs > 4) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "counter_size %d > 4", cs);
+    if (L < 3 || L > 12 || L > k) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "signature length %d", L);
+    if (P > 15) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "lut_prefix_length %d > 15", P);
+    const uint64_t sig_map_size = (1ULL << (2 * L)) + 1;
+    if (sig_map_size * 4 + header_offset + 8 + 4 > file_size) return kcf_fail(ctx, KCF_ERR_DB_FORMAT, "signature map does not fit the file");
+    const uint64_t sig_map_start = file_size - header_offset - 8 - sig_map_size * 4;
+    const uint64_t lut_size = 1ULL << (2 * P);
+    const uint64_t single_lut_bytes = lut_size * 8;
+    const uint64_t n_bins = (sig_map_start >= 12) ? (sig_map_start - 8 - 4) / single_lut_bytes : 0; // KMC.java:156
+    const uint64_t lut_len = n_bins * lut_size;
+    info.n_bins = (int32_t)n_bins;
+    const uint32_t nsb = (uint32_t)(k - P) / 4, rec_size = nsb + (uint32_t)cs; // KMC.java:61
+    const uint64_t N = (uint64_t)info.total_kmers;
+    if (suf_len < 4 + N * rec_size) return kcf_fail(ctx, KCF_ERR_DB_FORMAT, ".kmc_suf holds fewer than total_kmers records");
+    // signature map entries must name existing bins, else the reference indexes outside prefixArray
+    for (uint64_t i = 0; i < sig_map_size; ++i)
+        if (rd_u32(pre + sig_map_start + 4 * i) >= (n_bins ? n_bins : 1) && N > 0)
+            return kcf_fail(ctx, KCF_ERR_DB_FORMAT, "signature map entry %llu names bin %u of %llu", (unsigned long long)i,
+                            rd_u32(pre + sig_map_start + 4 * i), (unsigned long long)n_bins);
+
+    // --- table geometry ---
+    const uint32_t cbits = 8u * (uint32_t)cs;
+    const int kk2 = 2 * k;
+    uint64_t nb = (uint64_t)((double)N / (KCF_SLOTS_PER_BUCKET * ctx->load_factor)) + 1;
+    const int min_log = kk2 + 1 + KCF_DISP_BITS + 1 + (int)cbits - 64; // so that 1 + disp + rem + count fit 64 bits
+    if (min_log > 31) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "k=%d with %d-byte counters needs a wide-slot table (not in this build)", k, cs);
+    nb = std::max<uint64_t>(nb, 64);
+    if (min_log > 0) nb = std::max<uint64_t>(nb, 1ULL << min_log);
+    if (kk2 < 63) nb = std::min<uint64_t>(nb, 1ULL << kk2); // never more buckets than distinct keys
+    nb = std::max<uint64_t>(nb, 1);
+    KcfTableGeom g{};
+    g.n_buckets = nb;
+    g.k = (uint32_t)k;
+    g.kshift = 64 - kk2;
+    g.kmask = kk2 == 64 ? ~0ULL : ((1ULL << kk2) - 1);
+    int fl = floor_log2_u64(nb);
+    int rbits = kk2 - fl + (((nb & (nb - 1)) != 0) ? 1 : 0);
+    if (rbits < 1) rbits = 1;
+    if (rbits > kk2) rbits = kk2;
+    if (1 + KCF_DISP_BITS + rbits + (int)cbits > 64)
+        return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "slot does not fit: rem %d + count %u bits", rbits, cbits);
+    g.rbits = (uint32_t)rbits;
+    g.rmask = rbits == 64 ? ~0ULL : ((1ULL << rbits) - 1);
+    g.cbits = cbits;
+    g.cmask = cbits == 0 ? 0 : ((1ULL << cbits) - 1);
+    g.both_strands = (uint32_t)info.both_strands;
+    g.s1 = (uint32_t)std::max(1, k);
+    g.s2 = (uint32_t)std::max(1, k - 3);
+    g.stash_mask = 0;
+
+    kcf_db *db = new kcf_db();
+    db->ctx = ctx;
+    uint64_t *d_lut = nullptr;
+    uint32_t *d_sigmap = nullptr, *d_norm = nullptr;
+    uint8_t *d_stage[2] = {nullptr, nullptr};
+    uint8_t *h_stage[2] = {nullptr, nullptr};
+    KcfStashEntry *d_ovf = nullptr;
+    unsigned long long *d_counters = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int rc = KCF_OK;
+    const uint64_t chunk_rec = std::max<uint64_t>(1, (64ULL << 20) / std::max<uint32_t>(rec_size, 1));
+    const uint64_t chunk_bytes = chunk_rec * std::max<uint32_t>(rec_size, 1);
+    const uint64_t ovf_cap = N / 64 + 4096;
+    unsigned long long counters[3] = {0, 0, 0};
+    uint32_t flags[FLAG_COUNT] = {0};
+
+#define DB_CUDA(call)                                                                                         \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess) {                                                                             \
+            rc = kcf_fail(ctx, e__ == cudaErrorMemoryAllocation ? KCF_ERR_NOMEM : KCF_ERR_CUDA, "%s: %s (%s:%d)", \
+                          #call, cudaGetErrorString(e__), __FILE__, __LINE__);                               \
+            goto done;                                                                                        \
+        }                                                                                                     \
+    } while (0)
+
+    DB_CUDA(cudaMalloc(&db->table, nb * 32));
+    DB_CUDA(cudaMemsetAsync(db->table, 0, nb * 32, ctx->stream));
+    DB_CUDA(cudaMalloc(&d_lut, std::max<uint64_t>(lut_len, 1) * 8));
+    DB_CUDA(cudaMalloc(&d_sigmap, sig_map_size * 4));
+    DB_CUDA(cudaMalloc(&d_norm, (1ULL << (2 * L)) * 4));
+    DB_CUDA(cudaMalloc(&d_counters, 3 * sizeof(unsigned long long)));
+    DB_CUDA(cudaMemsetAsync(d_counters, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    DB_CUDA(cudaMemsetAsync(ctx->d_flags, 0, FLAG_COUNT * sizeof(uint32_t), ctx->stream));
+    DB_CUDA(cudaMalloc(&d_ovf, ovf_cap * sizeof(KcfStashEntry)));
+    if (lut_len) DB_CUDA(cudaMemcpyAsync(d_lut, pre + 4, lut_len * 8, cudaMemcpyHostToDevice, ctx->stream)); // KMC.java:153,159-163
+    DB_CUDA(cudaMemcpyAsync(d_sigmap, pre + sig_map_start, sig_map_size * 4, cudaMemcpyHostToDevice, ctx->stream)); // :145-151
+    {
+        uint32_t special = 1u << (2 * L);
+        kcf_norm_kernel<<<(special + 255) / 256, 256, 0, ctx->stream>>>(L, d_norm);
+        if (lut_len) kcf_lut_check_kernel<<<(unsigned)((lut_len + 255) / 256), 256, 0, ctx->stream>>>(d_lut, lut_len, N, ctx->d_flags);
+        DB_CUDA(cudaGetLastError());
+    }
+    for (int j = 0; j < 2; ++j) {
+        DB_CUDA(cudaMalloc(&d_stage[j], chunk_bytes));
+        DB_CUDA(cudaHostAlloc(&h_stage[j], chunk_bytes, cudaHostAllocDefault));
+        DB_CUDA(cudaEventCreateWithFlags(&ev[j], cudaEventDisableTiming));
+    }
+    {
+        const uint8_t *recs = suf + 4; // KMC.java:94 — skip the KMCS marker
+        int j = 0;
+        for (uint64_t r0 = 0; r0 < N; r0 += chunk_rec, j ^= 1) {
+            uint64_t n = std::min<uint64_t>(chunk_rec, N - r0);
+            DB_CUDA(cudaEventSynchronize(ev[j])); // staging buffer j free again
+            memcpy(h_stage[j], recs + r0 * rec_size, n * rec_size);
+            DB_CUDA(cudaMemcpyAsync(d_stage[j], h_stage[j], n * rec_size, cudaMemcpyHostToDevice, ctx->stream));
+            KcfIngestParams p{};
+            p.rec = d_stage[j];
+            p.rec0 = r0;
+            p.n_rec = n;
+            memset(p.prev, 0, sizeof p.prev);
+            if (r0 > 0) memcpy(p.prev, recs + (r0 - 1) * rec_size, std::min<uint32_t>(rec_size, 16));
+            p.lut = d_lut;
+            p.lut_len = lut_len;
+            p.sigmap = d_sigmap;
+            p.norm = d_norm;
+            p.P = (uint32_t)P;
+            p.L = (uint32_t)L;
+            p.nsb = nsb;
+            p.cs = (uint32_t)cs;
+            p.rec_size = rec_size;
+            p.table = db->table;
+            p.ovf = d_ovf;
+            p.ovf_cap = ovf_cap;
+            p.counters = d_counters;
+            p.flags = ctx->d_flags;
+            kcf_ingest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(p, g);
+            DB_CUDA(cudaGetLastError());
+            DB_CUDA(cudaEventRecord(ev[j], ctx->stream));
+        }
+    }
+    DB_CUDA(cudaMemcpyAsync(counters, d_counters, sizeof counters, cudaMemcpyDeviceToHost, ctx->stream));
+    DB_CUDA(cudaMemcpyAsync(flags, ctx->d_flags, sizeof flags, cudaMemcpyDeviceToHost, ctx->stream));
+    DB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (flags[FLAG_LUT_BAD]) { rc = kcf_fail(ctx, KCF_ERR_DB_FORMAT, "prefix LUT is not monotone or exceeds total_kmers"); goto done; }
+    if (flags[FLAG_ORDER_BAD]) { rc = kcf_fail(ctx, KCF_ERR_DB_ORDER, "records inside a (bin, prefix) range are not strictly ascending"); goto done; }
+    if (counters[2] > ovf_cap) { rc = kcf_fail(ctx, KCF_ERR_NOMEM, "hash overflow list exhausted (%llu entries); lower the load factor", counters[2]); goto done; }
+    if (counters[2] > 0) {
+        uint64_t cap = 64;
+        while (cap < 2 * counters[2]) cap <<= 1;
+        g.stash_mask = cap - 1;
+        DB_CUDA(cudaMalloc(&db->stash, cap * sizeof(KcfStashEntry)));
+        DB_CUDA(cudaMemsetAsync(db->stash, 0, cap * sizeof(KcfStashEntry), ctx->stream));
+        kcf_stash_build_kernel<<<(unsigned)((counters[2] + 255) / 256), 256, 0, ctx->stream>>>(d_ovf, counters[2], db->stash, g);
+        DB_CUDA(cudaGetLastError());
+        DB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    info.resident_kmers = (int64_t)(counters[0] + counters[2]);
+    info.unreachable_kmers = (int64_t)counters[1];
+    info.stash_kmers = (int64_t)counters[2];
+    info.n_buckets = (int64_t)nb;
+    info.table_bytes = (int64_t)(nb * 32 + (db->stash ? (g.stash_mask + 1) * sizeof(KcfStashEntry) : 0));
+    info.load_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    db->info = info;
+    db->geom = g;
+
+done:
+    for (int j = 0; j < 2; ++j) {
+        if (d_stage[j]) cudaFree(d_stage[j]);
+        if (h_stage[j]) cudaFreeHost(h_stage[j]);
+        if (ev[j]) cudaEventDestroy(ev[j]);
+    }
+    if (d_lut) cudaFree(d_lut);
+    if (d_sigmap) cudaFree(d_sigmap);
+    if (d_norm) cudaFree(d_norm);
+    if (d_ovf) cudaFree(d_ovf);
+    if (d_counters) cudaFree(d_counters);
+    if (rc != KCF_OK) {
+        if (db->table) cudaFree(db->table);
+        if (db->stash) cudaFree(db->stash);
+        delete db;
+        return rc;
+    }
+    *out = db;
+    return KCF_OK;
+#undef DB_CUDA
+}
+
+namespace {
+struct Mapped {
+    const uint8_t *p = nullptr;
+    size_t n = 0;
+    int fd = -1;
+    bool open(const std::string &path)
+    {
+        fd = ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0) return false;
+        n = (size_t)st.st_size;
+        if (n == 0) return false;
+        void *m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) return false;
+        p = (const uint8_t *)m;
+        return true;
+    }
+    ~Mapped()
+    {
+        if (p) munmap((void *)p, n);
+        if (fd >= 0) ::close(fd);
+    }
+};
+} // namespace
+
+extern "C" int kcf_db_open(kcf_ctx *ctx, const char *kmc_prefix, int placement, kcf_db **out)
+{
+    if (!ctx || !kmc_prefix || !out) return KCF_ERR_ARG;
+    *out = nullptr;
+    Mapped pre, suf;
+    std::string base(kmc_prefix);
+    if (!pre.open(base + ".kmc_pre")) return kcf_fail(ctx, KCF_ERR_IO, "Error reading prefix file %s.kmc_pre", kmc_prefix); // KMC.java:165-167
+    if (!suf.open(base + ".kmc_suf")) return kcf_fail(ctx, KCF_ERR_IO, "Error reading suffix buffers from file %s.kmc_suf", kmc_prefix); // :186-188
+    return kcf_db_open_mem(ctx, pre.p, pre.n, suf.p, suf.n, placement, out);
+}
+
+extern "C" int kcf_db_info(kcf_db *db, kcf_db_info_t *out)
+{
+    if (!db || !out) return KCF_ERR_ARG;
+    *out = db->info;
+    return KCF_OK;
+}
+
+extern "C" void kcf_db_close(kcf_db *db)
+{
+    if (!db) return;
+    cudaSetDevice(db->ctx->device);
+    if (db->table) cudaFree(db->table);
+    if (db->stash) cudaFree(db->stash);
+    delete db;
+}
+
+extern "C" int kcf_db_count(kcf_ctx *ctx, kcf_db *db, const char *kmers_ascii, uint64_t n, int32_t *counts_out)
+{
+    if (!ctx || !db || (!kmers_ascii && n) || (!counts_out && n)) return KCF_ERR_ARG;
+    if (n == 0) return KCF_OK;
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    char *d_in = nullptr;
+    int32_t *d_out = nullptr;
+    const uint64_t k = db->geom.k;
+    KCF_CUDA(ctx, cudaMalloc(&d_in, n * k));
+    cudaError_t e = cudaMalloc(&d_out, n * 4);
+    if (e != cudaSuccess) { cudaFree(d_in); return kcf_fail(ctx, KCF_ERR_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    cudaMemcpyAsync(d_in, kmers_ascii, n * k, cudaMemcpyHostToDevice, ctx->stream);
+    kcf_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_in, n, db->table, db->stash, db->geom, d_out);
+    cudaMemcpyAsync(counts_out, d_out, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return kcf_fail(ctx, KCF_ERR_CUDA, "kcf_db_count: %s", cudaGetErrorString(e));
+    return KCF_OK;
+}

@@ -1,0 +1,630 @@
+// kcf_screen.cu — K3 (rolling canonical k-mers + table probe), K4 (gap monoid reduction) and
+// K5 (score): the replacement for GetVariants.processWindow (GetVariants.java:202-261) and what it
+// calls per k-mer (Fasta.getKmersList Fasta.java:90-127, new Kmer(k, bothStrands) Kmer.java:57-79,
+// KMC.getCount KMC.java:292-326), for all windows in one launch.
+//
+// Work unit = a tile of KCF_TILE consecutive positions of one window (a window is the concatenation
+// of its segments, GTF.java:240-244 / Window.java:224-226).  A CTA stages the tile's 2-bit bases and
+// validity bits plus a 32-base halo in shared memory, every thread then owns 8 consecutive k-mer end
+// positions: it rolls the forward / reverse-complement words, issues its 8 independent 32-byte bucket
+// loads, folds the hit pattern into a gap monoid, and the CTA reduces the 256 partial monoids in
+// order with warp shuffles.  No per-k-mer data ever goes back to HBM.
+#include <algorithm>
+#include <cstring>
+#include "kcf_internal.cuh"
+#include "kcf_lookup.cuh"
+
+
+struct KcfScreenParams {
+    const KcfSeqDev *seqs;
+    const kcf_window_t *wins;
+    const kcf_segment_t *segs;
+    const uint32_t *seg_off;
+    const uint32_t *win_len;
+    const uint64_t *tile_first;
+    uint64_t n_wins;
+    uint64_t tile_begin, tile_end;
+    const uint64_t *table;
+    const KcfStashEntry *stash;
+    KcfGap *tile_sum;
+    unsigned long long *tile_counter;
+    int32_t min_count;
+    int32_t *counts_out;   // optional: per position count of the tiles processed (-1 = no k-mer ends here)
+    uint64_t counts_tile0; // tile whose position 0 maps to counts_out[0]
+};
+
+// GetVariants.java:267-273 getDistance
+__device__ __forceinline__ uint32_t kcf_gap_distance(uint32_t gap, uint32_t k)
+{
+    int32_t d = (int32_t)gap - ((int32_t)k - 1);
+    if (d <= 0) d = abs(d + 1);
+    return (uint32_t)d;
+}
+
+// in-order concatenation of two summaries
+__device__ __forceinline__ KcfGap kcf_gap_combine(const KcfGap &a, const KcfGap &b, uint32_t k)
+{
+    if (b.n == 0) return a;
+    if (a.n == 0) return b;
+    KcfGap r;
+    r.n = a.n + b.n;
+    r.obs = a.obs + b.obs;
+    r.sum = a.sum + b.sum;
+    r.starts = a.starts + b.starts;
+    r.vin = a.vin + b.vin;
+    r.inner = a.inner + b.inner;
+    r.has = a.has | b.has;
+    if (a.has && b.has) {
+        uint32_t g = a.trail + b.lead; // a miss run closed by hits on both sides (GetVariants.java:227-238)
+        if (g > 0) {
+            r.vin += 1;
+            r.inner += kcf_gap_distance(g, k);
+        }
+        r.lead = a.lead;
+        r.trail = b.trail;
+    } else if (a.has) {
+        r.lead = a.lead;
+        r.trail = a.trail + b.n;
+    } else if (b.has) {
+        r.lead = a.n + b.lead;
+        r.trail = b.trail;
+    } else {
+        r.lead = r.n;
+        r.trail = r.n;
+    }
+    return r;
+}
+
+__device__ __forceinline__ KcfGap kcf_gap_shfl_down(const KcfGap &a, int delta)
+{
+    KcfGap r;
+    r.n = __shfl_down_sync(0xffffffffu, a.n, delta);
+    r.obs = __shfl_down_sync(0xffffffffu, a.obs, delta);
+    r.lead = __shfl_down_sync(0xffffffffu, a.lead, delta);
+    r.trail = __shfl_down_sync(0xffffffffu, a.trail, delta);
+    r.vin = __shfl_down_sync(0xffffffffu, a.vin, delta);
+    r.inner = __shfl_down_sync(0xffffffffu, a.inner, delta);
+    r.has = __shfl_down_sync(0xffffffffu, a.has, delta);
+    r.starts = __shfl_down_sync(0xffffffffu, a.starts, delta);
+    r.sum = __shfl_down_sync(0xffffffffu, a.sum, delta);
+    return r;
+}
+
+#define S_CODE_WORDS ((KCF_TILE + KCF_HALO) / 16 + 4)
+#define S_VALID_WORDS ((KCF_TILE + KCF_HALO) / 32 + 2)
+
+__global__ void __launch_bounds__(KCF_THREADS, 2) kcf_screen_kernel(KcfScreenParams p, KcfTableGeom g)
+{
+    __shared__ uint32_t s_codes[S_CODE_WORDS];
+    __shared__ uint32_t s_valid[S_VALID_WORDS];
+    __shared__ KcfGap s_warp[KCF_THREADS / 32];
+    __shared__ uint64_t s_tile;
+    __shared__ uint32_t s_win;
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t k = g.k;
+    const uint64_t km1 = (k == 32) ? 0xFFFFFFFFULL : ((1ULL << k) - 1ULL);
+
+    for (;;) {
+        __syncthreads(); // shared buffers of the previous tile are no longer read
+        if (tid == 0) {
+            uint64_t t = p.tile_begin + atomicAdd(p.tile_counter, 1ULL);
+            s_tile = t;
+            if (t < p.tile_end) {
+                // window owning tile t: last w with tile_first[w] <= t
+                uint64_t lo = 0, hi = p.n_wins;
+                while (lo < hi) {
+                    uint64_t mid = (lo + hi) >> 1;
+                    if (p.tile_first[mid] <= t) lo = mid + 1;
+                    else hi = mid;
+                }
+                s_win = (uint32_t)(lo - 1);
+            }
+        }
+        __syncthreads();
+        const uint64_t tile = s_tile;
+        if (tile >= p.tile_end) break;
+        const uint32_t w = s_win;
+        const kcf_window_t win = p.wins[w];
+        const uint32_t wlen = p.win_len[w];
+        const int64_t o = (int64_t)(tile - p.tile_first[w]) * KCF_TILE; // window position of the tile's first k-mer end
+
+        // ---- stage bases [o - HALO, o + TILE) of the window: 8 positions per thread step ----
+        for (uint32_t u = tid; u < (KCF_TILE + KCF_HALO) / 8; u += KCF_THREADS) {
+            const int64_t pos0 = o - KCF_HALO + 8 * (int64_t)u;
+            uint32_t c16 = 0, v8 = 0;
+            if (pos0 + 8 > 0 && pos0 < (int64_t)wlen) {
+                if (win.n_segs == 1 && pos0 >= 0 && pos0 + 8 <= (int64_t)wlen) {
+                    // fixed / sliding window, fully inside: two funnel shifts over the packed words
+                    const kcf_segment_t sg = p.segs[win.first_seg];
+                    const KcfSeqDev sq = p.seqs[sg.seq_id];
+                    const uint32_t sp = (uint32_t)(sg.start0 + pos0);
+                    const uint32_t wi = sp >> 4, vi = sp >> 5;
+                    c16 = __funnelshift_r(__ldg(sq.codes + wi), __ldg(sq.codes + wi + 1), (sp & 15u) * 2u) & 0xFFFFu;
+                    v8 = __funnelshift_r(__ldg(sq.valid + vi), __ldg(sq.valid + vi + 1), sp & 31u) & 0xFFu;
+                } else {
+                    // window edges and multi-segment (gene / transcript) windows: base by base
+                    uint32_t s = 0;
+                    bool have = false;
+                    for (int j = 0; j < 8; ++j) {
+                        const int64_t pos = pos0 + j;
+                        if (pos < 0 || pos >= (int64_t)wlen) continue;
+                        if (!have) {
+                            uint32_t lo = 0, hi = win.n_segs; // last segment with seg_off <= pos
+                            while (lo < hi) {
+                                uint32_t mid = (lo + hi) >> 1;
+                                if (p.seg_off[win.first_seg + mid] <= (uint32_t)pos) lo = mid + 1;
+                                else hi = mid;
+                            }
+                            s = lo - 1;
+                            have = true;
+                        }
+                        while (s + 1 < win.n_segs && p.seg_off[win.first_seg + s + 1] <= (uint32_t)pos) ++s;
+                        const kcf_segment_t sg = p.segs[win.first_seg + s];
+                        const KcfSeqDev sq = p.seqs[sg.seq_id];
+                        const uint32_t sp = (uint32_t)sg.start0 + ((uint32_t)pos - p.seg_off[win.first_seg + s]);
+                        const uint32_t c = (__ldg(sq.codes + (sp >> 4)) >> ((sp & 15u) * 2u)) & 3u;
+                        const uint32_t v = (__ldg(sq.valid + (sp >> 5)) >> (sp & 31u)) & 1u;
+                        c16 |= c << (2 * j);
+                        v8 |= v << j;
+                    }
+                }
+            }
+            reinterpret_cast<uint16_t *>(s_codes)[u] = (uint16_t)c16;
+            reinterpret_cast<uint8_t *>(s_valid)[u] = (uint8_t)v8;
+        }
+        __syncthreads();
+
+        // ---- this thread's 40-base buffer: local bases [8 tid, 8 tid + 40); k-mer i ends at buffer base 32 + i ----
+        uint64_t blo, bhi, V;
+        {
+            const uint32_t wq = tid >> 1;
+            const uint32_t w0 = s_codes[wq], w1 = s_codes[wq + 1], w2 = s_codes[wq + 2];
+            const uint64_t t01 = ((uint64_t)w1 << 32) | w0;
+            if (tid & 1) {
+                blo = (t01 >> 16) | ((uint64_t)w2 << 48);
+                bhi = w2 >> 16;
+            } else {
+                blo = t01;
+                bhi = w2 & 0xFFFFu;
+            }
+            const uint32_t vq = tid >> 2;
+            const uint64_t v01 = ((uint64_t)s_valid[vq + 1] << 32) | s_valid[vq];
+            V = v01 >> (8 * (tid & 3));
+        }
+        const uint32_t sh0 = 2 * (33 - k); // 2..60
+        uint64_t X = ((blo >> sh0) | (bhi << (64 - sh0))) & g.kmask; // k-mer 0, base j in bits 2j
+        uint64_t fw = kcf_pair_reverse(X, g.kshift);                   // first base most significant (Kmer.java:232-252)
+        bool ok_prev = ((V >> (32 - k)) & km1) == km1;                 // k-mer ending one position before this thread's first
+
+        uint64_t key[KCF_PER_THREAD], hh[KCF_PER_THREAD];
+        uint64_t s0[KCF_PER_THREAD], s1[KCF_PER_THREAD], s2[KCF_PER_THREAD], s3[KCF_PER_THREAD];
+        uint32_t okmask = 0, startmask = 0;
+#pragma unroll
+        for (int i = 0; i < KCF_PER_THREAD; ++i) {
+            if (i > 0) {
+                const uint64_t c = (bhi >> (2 * i)) & 3ULL;
+                X = (X >> 2) | (c << (2 * (k - 1)));
+                fw = ((fw << 2) | c) & g.kmask;
+            }
+            const bool ok = ((V >> (33 + i - k)) & km1) == km1; // Fasta.java:99-104: any non-ACGT restarts the stretch
+            const uint64_t rc = (~X) & g.kmask;                 // reverse complement value (Kmer.java:300-338)
+            // canonical = unsigned-smaller word, tie keeps forward (Kmer.java:72-79, 406-414)
+            const uint64_t kk = (g.both_strands && rc < fw) ? rc : fw;
+            key[i] = kk;
+            hh[i] = kcf_mix(kk, g);
+            okmask |= (uint32_t)ok << i;
+            startmask |= (uint32_t)(ok && !ok_prev) << i;
+            ok_prev = ok;
+            s0[i] = s1[i] = s2[i] = s3[i] = 0;
+            if (ok) kcf_ld_bucket(p.table + 4 * kcf_home_bucket(hh[i], g), s0[i], s1[i], s2[i], s3[i]);
+        }
+
+        // ---- fold the 8 results into this thread's gap summary (GetVariants.java:220-245) ----
+        KcfGap a;
+        a.n = a.obs = a.lead = a.trail = a.vin = a.inner = a.has = 0;
+        a.starts = __popc(startmask);
+        a.sum = 0;
+        uint32_t gap = 0;
+#pragma unroll
+        for (int i = 0; i < KCF_PER_THREAD; ++i) {
+            const bool ok = (okmask >> i) & 1u;
+            uint32_t cnt = 0;
+            if (ok) {
+                const uint64_t tag = ((uint64_t)8u << g.rbits) | (hh[i] & g.rmask);
+                bool full;
+                if (!kcf_match4(s0[i], s1[i], s2[i], s3[i], tag, g, cnt, full)) {
+                    cnt = 0;
+                    if (full) cnt = kcf_lookup_tail(p.table, p.stash, g, key[i], hh[i], kcf_home_bucket(hh[i], g));
+                }
+                a.n += 1;
+                if ((int32_t)cnt >= p.min_count) { // Java int compare (GetVariants.java:224)
+                    a.obs += 1;
+                    a.sum += cnt;
+                    if (!a.has) {
+                        a.lead = gap;
+                        a.has = 1;
+                    } else if (gap > 0) {
+                        a.vin += 1;
+                        a.inner += kcf_gap_distance(gap, k);
+                    }
+                    gap = 0;
+                } else {
+                    gap += 1;
+                }
+            }
+            if (p.counts_out) {
+                const uint64_t pos = (tile - p.counts_tile0) * KCF_TILE + 8 * tid + i;
+                p.counts_out[pos] = ok ? (int32_t)cnt : -1;
+            }
+        }
+        a.trail = gap;
+        if (!a.has) a.lead = a.n;
+
+        // ---- ordered reduction: 32 lanes by shuffle, 8 warps through shared memory ----
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            KcfGap b = kcf_gap_shfl_down(a, d);
+            if ((tid & 31) + d < 32) a = kcf_gap_combine(a, b, k);
+        }
+        if ((tid & 31) == 0) s_warp[tid >> 5] = a;
+        __syncthreads();
+        if (tid == 0) {
+            KcfGap r = s_warp[0];
+            for (int i = 1; i < KCF_THREADS / 32; ++i) r = kcf_gap_combine(r, s_warp[i], k);
+            p.tile_sum[tile] = r;
+        }
+    }
+}
+
+// K4 tail + K5: combine a window's tiles in order and emit the KCF integers and the score
+// (GetVariants.java:247-258, Data.java:70-107).  No FMA contraction: explicit _rn intrinsics.
+__global__ void kcf_finalize_kernel(const KcfGap *__restrict__ tile_sum, const uint64_t *__restrict__ tile_first, uint64_t n_wins,
+                                    uint32_t k, double wi, double wt, double wr, kcf_result_t *__restrict__ out, uint32_t *flags)
+{
+    uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_wins) return;
+    KcfGap r;
+    r.n = r.obs = r.lead = r.trail = r.vin = r.inner = r.has = r.starts = 0;
+    r.sum = 0;
+    for (uint64_t t = tile_first[w]; t < tile_first[w + 1]; ++t) r = kcf_gap_combine(r, tile_sum[t], k);
+    kcf_result_t o;
+    o.total_kmers = (int32_t)r.n;
+    o.eff_len = (int32_t)(r.n + (k - 1) * r.starts); // Fasta.java:140-167: stretches of >= k valid bases
+    o.obs = (int32_t)r.obs;
+    o.kmer_count_sum = (int64_t)r.sum;
+    o._pad = 0;
+    if (r.has) {
+        o.left = (int32_t)r.lead;
+        o.right = (int32_t)r.trail;
+        o.inner = (int32_t)r.inner;
+        o.variations = (int32_t)(r.vin + (r.lead > 0) + (r.trail > 0));
+    } else { // no hit at all: one trailing gap (GetVariants.java:247-251)
+        o.left = 0;
+        o.right = (int32_t)r.n;
+        o.inner = 0;
+        o.variations = r.n > 0 ? 1 : 0;
+    }
+    double score = 0.0;
+    if (!(o.obs == 0 || o.total_kmers == 0 || o.eff_len == 0)) { // Data.java:96-98
+        atomicOr(&flags[FLAG_SCORE_USED], 1u);
+        const double eff = (double)o.eff_len;
+        const double ta = __dmul_rn(wr, __ddiv_rn((double)o.obs, (double)o.total_kmers));
+        const double tb = __dmul_rn(wi, __dsub_rn(1.0, __ddiv_rn((double)o.inner, eff)));
+        const double tc = __dmul_rn(wt, __dsub_rn(1.0, __ddiv_rn((double)(o.left + o.right), eff)));
+        score = __dmul_rn(__dadd_rn(__dadd_rn(ta, tb), tc), 100.0); // Data.java:104-106
+    }
+    o.score = score;
+    out[w] = o;
+}
+
+// ---- random 32-byte sector gather microbenchmark (the random-access roofline of SURVEY §8(d)) ----
+__global__ void __launch_bounds__(256) kcf_random_sector_kernel(const uint64_t *__restrict__ buf, uint64_t n_sectors, uint64_t per_thread,
+                                                                uint64_t seed, uint64_t *sink)
+{
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t x = (t + 1) * 0x9E3779B97F4A7C15ULL ^ seed;
+    uint64_t acc = 0;
+    for (uint64_t it = 0; it < per_thread; it += 8) {
+        uint64_t a[8], b[8], c[8], d[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            x ^= x >> 29;
+            x *= 0xBF58476D1CE4E5B9ULL;
+            x ^= x >> 32;
+            uint64_t s = __umul64hi(x, n_sectors);
+            kcf_ld_bucket(buf + 4 * s, a[j], b[j], c[j], d[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += a[j] ^ b[j] ^ c[j] ^ d[j];
+    }
+    if (acc == 0x1234567ULL) *sink = acc; // keeps the loads alive
+}
+
+extern "C" int kcf_measure_random_sector_gbps(kcf_ctx *ctx, uint64_t n_bytes, uint64_t n_loads, int repeats, double *gbps_out)
+{
+    if (!ctx || !gbps_out || n_bytes < 4096 || n_loads == 0) return KCF_ERR_ARG;
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint64_t *buf = nullptr, *sink = nullptr;
+    const uint64_t n_sectors = n_bytes / 32;
+    KCF_CUDA(ctx, cudaMalloc(&buf, n_sectors * 32));
+    cudaError_t e = cudaMalloc(&sink, 8);
+    if (e != cudaSuccess) { cudaFree(buf); return kcf_fail(ctx, KCF_ERR_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    cudaMemsetAsync(buf, 1, n_sectors * 32, ctx->stream);
+    const uint64_t per_thread = 64;
+    const uint64_t threads = (n_loads + per_thread - 1) / per_thread;
+    const unsigned grid = (unsigned)((threads + 255) / 256);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    double best = 0;
+    for (int r = 0; r < std::max(repeats, 1) + 1; ++r) {
+        cudaEventRecord(a, ctx->stream);
+        kcf_random_sector_kernel<<<grid, 256, 0, ctx->stream>>>(buf, n_sectors, per_thread, 0x51ED27ULL * (r + 1), sink);
+        cudaEventRecord(b, ctx->stream);
+        e = cudaEventSynchronize(b);
+        if (e != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        double gbps = (double)grid * 256.0 * per_thread * 32.0 / (ms * 1e-3) / 1e9;
+        if (r > 0 && gbps > best) best = gbps; // first launch is the warm-up
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(buf);
+    cudaFree(sink);
+    if (e != cudaSuccess) return kcf_fail(ctx, KCF_ERR_CUDA, "random sector kernel: %s", cudaGetErrorString(e));
+    *gbps_out = best;
+    return KCF_OK;
+}
+
+// ---- host side: plans ---------------------------------------------------------------------------
+static int kcf_sync_seqs(kcf_ctx *ctx)
+{
+    if (!ctx->seqs_dirty && ctx->d_seqs) return KCF_OK;
+    const size_t n = std::max<size_t>(ctx->seqs.size(), 1);
+    if (ctx->d_seqs_cap < n) {
+        if (ctx->d_seqs) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(ctx->d_seqs);
+            ctx->d_seqs = nullptr;
+        }
+        KCF_CUDA(ctx, cudaMalloc(&ctx->d_seqs, n * sizeof(KcfSeqDev)));
+        ctx->d_seqs_cap = n;
+    }
+    std::vector<KcfSeqDev> h(n);
+    for (size_t i = 0; i < ctx->seqs.size(); ++i) {
+        h[i].codes = ctx->seqs[i].codes;
+        h[i].valid = ctx->seqs[i].valid;
+        h[i].len = (uint32_t)ctx->seqs[i].len;
+        h[i]._pad = 0;
+    }
+    KCF_CUDA(ctx, cudaMemcpyAsync(ctx->d_seqs, h.data(), n * sizeof(KcfSeqDev), cudaMemcpyHostToDevice, ctx->stream));
+    KCF_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // h goes out of scope
+    ctx->seqs_dirty = false;
+    return KCF_OK;
+}
+
+extern "C" void kcf_plan_destroy(kcf_plan *plan)
+{
+    if (!plan) return;
+    cudaSetDevice(plan->ctx->device);
+    cudaStreamSynchronize(plan->ctx->stream);
+    cudaFree(plan->d_wins);
+    cudaFree(plan->d_segs);
+    cudaFree(plan->d_seg_off);
+    cudaFree(plan->d_win_len);
+    cudaFree(plan->d_tile_first);
+    cudaFree(plan->d_tile_sum);
+    cudaFree(plan->d_out);
+    delete plan;
+}
+
+extern "C" int kcf_plan_create(kcf_ctx *ctx, int32_t kmer_length, const kcf_window_t *wins, uint64_t n_wins,
+                               const kcf_segment_t *segs, uint64_t n_segs, kcf_plan **out)
+{
+    if (!ctx || !out || (!wins && n_wins) || (!segs && n_segs)) return KCF_ERR_ARG;
+    *out = nullptr;
+    if (kmer_length < 3 || kmer_length > 32) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "k=%d outside 3..32", kmer_length);
+    if (n_wins >= (1ULL << 32) || n_segs >= (1ULL << 32)) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "too many windows / segments");
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<uint32_t> seg_off(std::max<uint64_t>(n_segs, 1), 0);
+    std::vector<uint32_t> win_len(std::max<uint64_t>(n_wins, 1), 0);
+    std::vector<uint64_t> tile_first(n_wins + 1, 0);
+    uint64_t tiles = 0, positions = 0;
+    for (uint64_t w = 0; w < n_wins; ++w) {
+        const kcf_window_t &win = wins[w];
+        if (win.n_segs == 0) // fasta == null (GetVariants.java:213-216)
+            return kcf_fail(ctx, KCF_ERR_RANGE, "Fasta object is null for window %llu (no segment)", (unsigned long long)w);
+        if ((uint64_t)win.first_seg + win.n_segs > n_segs) return kcf_fail(ctx, KCF_ERR_ARG, "window %llu: segment range outside segs[]", (unsigned long long)w);
+        uint64_t len = 0;
+        for (uint32_t s = 0; s < win.n_segs; ++s) {
+            const kcf_segment_t &sg = segs[win.first_seg + s];
+            if (sg.seq_id < 0 || (size_t)sg.seq_id >= ctx->seqs.size())
+                return kcf_fail(ctx, KCF_ERR_RANGE, "Sequence not found in index: id %d (window %llu)", sg.seq_id, (unsigned long long)w);
+            const KcfSeqHost &sq = ctx->seqs[sg.seq_id];
+            const int64_t start = sg.start0, end = (int64_t)sg.start0 + sg.len;
+            if (start < 0 || end > (int64_t)sq.len || start >= end) // FastaIndex.java:132-135
+                return kcf_fail(ctx, KCF_ERR_RANGE, "Invalid range: %lld-%lld for sequence: id %d", (long long)start, (long long)end, sg.seq_id);
+            // FastaIndex.java:169,175-177: after the last chunk the buffer position still moves past the line terminator
+            const uint64_t last = (uint64_t)((end - 1) / sq.line_bases) * sq.line_width + (uint64_t)((end - 1) % sq.line_bases);
+            if (last + 1 + (sq.line_width - sq.line_bases) > sq.n_bytes)
+                return kcf_fail(ctx, KCF_ERR_FASTA, "Error reading sequence: id %d range %lld-%lld runs past the mapped bytes (missing trailing newline?)",
+                                sg.seq_id, (long long)start, (long long)end);
+            seg_off[win.first_seg + s] = (uint32_t)len;
+            len += (uint64_t)sg.len;
+        }
+        if (len >= (1ULL << 31)) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "window %llu longer than 2^31 bases", (unsigned long long)w);
+        win_len[w] = (uint32_t)len;
+        tile_first[w] = tiles;
+        tiles += (len + KCF_TILE - 1) / KCF_TILE;
+        positions += len;
+    }
+    tile_first[n_wins] = tiles;
+    kcf_plan *plan = new kcf_plan();
+    plan->ctx = ctx;
+    plan->k = kmer_length;
+    plan->n_wins = n_wins;
+    plan->n_segs = n_segs;
+    plan->n_tiles = tiles;
+    plan->n_positions = positions;
+    int rc = KCF_OK;
+#define PL_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess && rc == KCF_OK)                                                         \
+            rc = kcf_fail(ctx, e__ == cudaErrorMemoryAllocation ? KCF_ERR_NOMEM : KCF_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+    PL_CUDA(cudaMalloc(&plan->d_wins, std::max<uint64_t>(n_wins, 1) * sizeof(kcf_window_t)));
+    PL_CUDA(cudaMalloc(&plan->d_segs, std::max<uint64_t>(n_segs, 1) * sizeof(kcf_segment_t)));
+    PL_CUDA(cudaMalloc(&plan->d_seg_off, std::max<uint64_t>(n_segs, 1) * 4));
+    PL_CUDA(cudaMalloc(&plan->d_win_len, std::max<uint64_t>(n_wins, 1) * 4));
+    PL_CUDA(cudaMalloc(&plan->d_tile_first, (n_wins + 1) * 8));
+    PL_CUDA(cudaMalloc(&plan->d_tile_sum, std::max<uint64_t>(tiles, 1) * sizeof(KcfGap) + 8)); // +8: the tile counter lives at the end
+    PL_CUDA(cudaMalloc(&plan->d_out, std::max<uint64_t>(n_wins, 1) * sizeof(kcf_result_t)));
+    if (rc == KCF_OK && n_wins) {
+        PL_CUDA(cudaMemcpyAsync(plan->d_wins, wins, n_wins * sizeof(kcf_window_t), cudaMemcpyHostToDevice, ctx->stream));
+        PL_CUDA(cudaMemcpyAsync(plan->d_segs, segs, n_segs * sizeof(kcf_segment_t), cudaMemcpyHostToDevice, ctx->stream));
+        PL_CUDA(cudaMemcpyAsync(plan->d_seg_off, seg_off.data(), n_segs * 4, cudaMemcpyHostToDevice, ctx->stream));
+        PL_CUDA(cudaMemcpyAsync(plan->d_win_len, win_len.data(), n_wins * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (rc == KCF_OK) PL_CUDA(cudaMemcpyAsync(plan->d_tile_first, tile_first.data(), (n_wins + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (rc == KCF_OK) PL_CUDA(cudaStreamSynchronize(ctx->stream)); // host vectors go out of scope; caller may free wins/segs
+#undef PL_CUDA
+    if (rc != KCF_OK) {
+        kcf_plan_destroy(plan);
+        return rc;
+    }
+    plan->h_tile_first.swap(tile_first);
+    plan->h_win_len.swap(win_len);
+    *out = plan;
+    return KCF_OK;
+}
+
+static int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t min_count, uint64_t tile_begin, uint64_t tile_end,
+                             int32_t *d_counts)
+{
+    int rc = kcf_sync_seqs(ctx);
+    if (rc != KCF_OK) return rc;
+    unsigned long long *d_counter = reinterpret_cast<unsigned long long *>(
+        reinterpret_cast<uint8_t *>(plan->d_tile_sum) + std::max<uint64_t>(plan->n_tiles, 1) * sizeof(KcfGap));
+    KCF_CUDA(ctx, cudaMemsetAsync(d_counter, 0, 8, ctx->stream));
+    KcfScreenParams p{};
+    p.seqs = ctx->d_seqs;
+    p.wins = plan->d_wins;
+    p.segs = plan->d_segs;
+    p.seg_off = plan->d_seg_off;
+    p.win_len = plan->d_win_len;
+    p.tile_first = plan->d_tile_first;
+    p.n_wins = plan->n_wins;
+    p.tile_begin = tile_begin;
+    p.tile_end = tile_end;
+    p.table = db->table;
+    p.stash = db->stash;
+    p.tile_sum = plan->d_tile_sum;
+    p.tile_counter = d_counter;
+    p.min_count = min_count;
+    p.counts_out = d_counts;
+    p.counts_tile0 = tile_begin;
+    int per_sm = 0;
+    KCF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kcf_screen_kernel, KCF_THREADS, 0));
+    const uint64_t n = tile_end - tile_begin;
+    const unsigned grid = (unsigned)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * std::max(per_sm, 1));
+    if (grid) kcf_screen_kernel<<<grid, KCF_THREADS, 0, ctx->stream>>>(p, db->geom);
+    KCF_CUDA(ctx, cudaGetLastError());
+    return KCF_OK;
+}
+
+extern "C" int kcf_plan_run(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t min_count, const double w[3])
+{
+    if (!ctx || !db || !plan || !w || plan->ctx != ctx || db->ctx != ctx) return KCF_ERR_ARG;
+    if (min_count < 1) return kcf_fail(ctx, KCF_ERR_ARG, "Minimum kmer count should be at least 1"); // GetVariants.java:383-385
+    if (plan->k != db->info.kmer_length) return kcf_fail(ctx, KCF_ERR_ARG, "plan built for k=%d, database has k=%d", plan->k, db->info.kmer_length);
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    KCF_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, FLAG_COUNT * sizeof(uint32_t), ctx->stream));
+    if (ctx->profiling) cudaEventRecord(ctx->ev[0], ctx->stream);
+    int rc = kcf_launch_screen(ctx, db, plan, min_count, 0, plan->n_tiles, nullptr);
+    if (rc != KCF_OK) return rc;
+    if (ctx->profiling) cudaEventRecord(ctx->ev[1], ctx->stream);
+    if (plan->n_wins) {
+        kcf_finalize_kernel<<<(unsigned)((plan->n_wins + 127) / 128), 128, 0, ctx->stream>>>(
+            plan->d_tile_sum, plan->d_tile_first, plan->n_wins, (uint32_t)plan->k, w[0], w[1], w[2], plan->d_out, ctx->d_flags);
+        KCF_CUDA(ctx, cudaGetLastError());
+    }
+    if (ctx->profiling) {
+        cudaEventRecord(ctx->ev[2], ctx->stream);
+        ctx->ev_valid = true;
+    }
+    plan->weights[0] = w[0];
+    plan->weights[1] = w[1];
+    plan->weights[2] = w[2];
+    plan->ran = true;
+    return KCF_OK;
+}
+
+extern "C" int kcf_plan_fetch(kcf_ctx *ctx, kcf_plan *plan, kcf_result_t *out)
+{
+    if (!ctx || !plan || plan->ctx != ctx || (!out && plan->n_wins)) return KCF_ERR_ARG;
+    if (!plan->ran) return kcf_fail(ctx, KCF_ERR_ARG, "kcf_plan_fetch before kcf_plan_run");
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint32_t flags[FLAG_COUNT] = {0};
+    if (plan->n_wins) KCF_CUDA(ctx, cudaMemcpyAsync(out, plan->d_out, plan->n_wins * sizeof(kcf_result_t), cudaMemcpyDeviceToHost, ctx->stream));
+    KCF_CUDA(ctx, cudaMemcpyAsync(flags, ctx->d_flags, sizeof flags, cudaMemcpyDeviceToHost, ctx->stream));
+    KCF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // Data.java:101-103 — evaluated only for windows that reach the formula, left to right in double
+    if (flags[FLAG_SCORE_USED] && plan->weights[0] + plan->weights[1] + plan->weights[2] != 1.0)
+        return kcf_fail(ctx, KCF_ERR_WEIGHTS, "Weights should sum to 1.0");
+    return KCF_OK;
+}
+
+extern "C" int kcf_plan_stats(kcf_plan *plan, uint64_t *n_tiles, uint64_t *n_positions, uint32_t *kernels_per_run)
+{
+    if (!plan) return KCF_ERR_ARG;
+    if (n_tiles) *n_tiles = plan->n_tiles;
+    if (n_positions) *n_positions = plan->n_positions;
+    if (kernels_per_run) *kernels_per_run = plan->n_wins ? 2u : 0u;
+    return KCF_OK;
+}
+
+extern "C" int kcf_screen(kcf_ctx *ctx, kcf_db *db, const kcf_window_t *wins, uint64_t n_wins, const kcf_segment_t *segs,
+                          uint64_t n_segs, int32_t min_count, const double w[3], kcf_result_t *out)
+{
+    if (!ctx || !db) return KCF_ERR_ARG;
+    if (min_count < 1) return kcf_fail(ctx, KCF_ERR_ARG, "Minimum kmer count should be at least 1");
+    kcf_plan *plan = nullptr;
+    int rc = kcf_plan_create(ctx, db->info.kmer_length, wins, n_wins, segs, n_segs, &plan);
+    if (rc != KCF_OK) return rc;
+    rc = kcf_plan_run(ctx, db, plan, min_count, w);
+    if (rc == KCF_OK) rc = kcf_plan_fetch(ctx, plan, out);
+    kcf_plan_destroy(plan);
+    return rc;
+}
+
+extern "C" int kcf_window_counts(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, uint64_t window, int32_t *counts_out, uint64_t cap,
+                                 uint64_t *n_out)
+{
+    if (!ctx || !db || !plan || !n_out || plan->ctx != ctx || window >= plan->n_wins) return KCF_ERR_ARG;
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t t0 = plan->h_tile_first[window], t1 = plan->h_tile_first[window + 1];
+    const uint64_t npos = (t1 - t0) * KCF_TILE;
+    int32_t *d = nullptr;
+    KCF_CUDA(ctx, cudaMalloc(&d, std::max<uint64_t>(npos, 1) * 4));
+    int rc = kcf_launch_screen(ctx, db, plan, 1, t0, t1, d);
+    std::vector<int32_t> h(npos);
+    if (rc == KCF_OK) {
+        cudaMemcpyAsync(h.data(), d, npos * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = kcf_fail(ctx, KCF_ERR_CUDA, "kcf_window_counts: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    if (rc != KCF_OK) return rc;
+    uint64_t n = 0;
+    const uint64_t wlen = plan->h_win_len[window];
+    for (uint64_t i = 0; i < wlen && i < npos; ++i)
+        if (h[i] != -1) { // -1 marks "no k-mer ends here" (ambiguous only for a 4-byte counter of 0xFFFFFFFF)
+            if (n < cap && counts_out) counts_out[n] = h[i];
+            ++n;
+        }
+    *n_out = n;
+    return KCF_OK;
+}

@@ -1,0 +1,57 @@
+"""CPU tests of the boundary: the library loads and exports every symbol include/kcf_b200.h declares.
+No compute call is made (there is no GPU here); kcf_init must fail loudly instead of falling back."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from kcftools_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "kcf_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(kcf_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_symbols_all_exported_and_bound():
+    names = _declared()
+    assert len(names) >= 20
+    lib = _lib.load()
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/kcf_b200.h but not exported by libkcfgpu.so"
+        assert n in _lib.SYMBOLS, f"{n} has no ctypes prototype in kcftools_b200/_lib.py"
+    assert set(_lib.SYMBOLS) == set(names)
+
+
+def test_struct_sizes_match_header():
+    assert _lib.RESULT_DTYPE.itemsize == 48
+    assert _lib.RESULT_DTYPE.fields["kmer_count_sum"][1] == 32 and _lib.RESULT_DTYPE.fields["score"][1] == 40
+    assert _lib.WINDOW_DTYPE.itemsize == 8 and _lib.SEGMENT_DTYPE.itemsize == 12
+    assert C.sizeof(_lib.DbInfo) == 88
+
+
+def test_version_string():
+    assert b"sm_100a" in _lib.load().kcf_version()
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from kcftools_b200.api import Context, KcfError
+    with pytest.raises(KcfError) as e:
+        Context(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "kcftools_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                src = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle" not in src.lower() or f == "README.md", f"{f} mentions the oracle"

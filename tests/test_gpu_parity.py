@@ -1,0 +1,242 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle on the same seeded inputs.
+Bar: integer columns bit-exact, score within 1e-9 relative (north_star)."""
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from tools import synth
+from common import Scenario, assert_results_equal, windows_from_lists
+from kcftools_b200.api import KMC, KcfError, fixed_windows
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_screen(sc, wins, segs, min_count=1, w=(0.3, 0.3, 0.4), threads=8):
+    odb = ob.OracleKMC(sc.kmc.pre, sc.kmc.suf)
+    rc, want = odb.screen(sc.seqs(), wins, segs, min_count=min_count, w=w, threads=threads)
+    return rc, want
+
+
+@pytest.fixture(scope="module")
+def sc_main():
+    return Scenario(seq_lens=(300_000, 123_457, 40), seed=1, n_bins=64)
+
+
+def test_db_info_and_counts(ctx, sc_main):
+    sc = sc_main
+    db = KMC(ctx, pre=sc.kmc.pre, suf=sc.kmc.suf)
+    assert db.getKmerLength() == 31 and db.getPrefixLength() == 7 and db.isBothStrands()
+    assert db.info.total_kmers == sc.kmc.total
+    assert db.info.resident_kmers == sc.kmc.total and db.info.unreachable_kmers == 0
+    odb = ob.OracleKMC(sc.kmc.pre, sc.kmc.suf)
+    raw, lb, lw, sl = sc.seqs()[0]
+    rc, text = ob.get_sequence(raw, lb, lw, sl, 0, 20000)
+    text = text.decode().upper()
+    kms = [text[i:i + 31] for i in range(0, len(text) - 31) if set(text[i:i + 31]) <= set("ACGT")]
+    got = db.getCounts(kms)
+    want = np.array([odb.count(s) for s in kms], np.int32)
+    assert (got == want).all() and (want > 0).any() and (want == 0).any()
+    # lower case input is upper-cased like Fasta.getKmersList does
+    assert db.getCount(kms[5].lower()) == want[5]
+    db.close()
+
+
+def test_fixed_windows_parity(ctx, sc_main):
+    sc = sc_main
+    sc.add_to(ctx)
+    db = KMC(ctx, pre=sc.kmc.pre, suf=sc.kmc.suf)
+    for (W, step) in [(50_000, 0), (5000, 0), (3000, 1000), (700, 2500)]:
+        wins, segs, *_ = fixed_windows(sc.seq_lens, W, step, 31)
+        rc, want = _oracle_screen(sc, wins, segs)
+        assert rc == 0
+        got = ctx.screen(db, wins, segs)
+        assert_results_equal(got, want)
+        assert want["obs"].sum() > 0 and (want["variations"] > 0).any() and (want["eff_len"] != want["total_kmers"] + 30).any()
+    db.close()
+
+
+def test_per_kmer_counts_of_a_window(ctx, sc_main):
+    sc = sc_main
+    sc.add_to(ctx)
+    db = KMC(ctx, pre=sc.kmc.pre, suf=sc.kmc.suf)
+    wins, segs, starts, ends, sids = fixed_windows(sc.seq_lens, 5000, 0, 31)
+    plan = ctx.plan(31, wins, segs)
+    plan.run(db)
+    plan.fetch()
+    odb = ob.OracleKMC(sc.kmc.pre, sc.kmc.suf)
+    for w in (0, 7, len(starts) - 1):
+        raw, lb, lw, sl = sc.seqs()[sids[w]]
+        rc, text = ob.get_sequence(raw, lb, lw, sl, int(starts[w]), int(ends[w] - starts[w]))
+        rc, res, counts = odb.process_window(text, want_counts=True)
+        got = plan.window_counts(db, w)
+        assert got.size == counts.size and (got == counts).all()
+    plan.close()
+    db.close()
+
+
+def test_min_count_and_weights(ctx, sc_main):
+    sc = sc_main
+    sc.add_to(ctx)
+    db = KMC(ctx, pre=sc.kmc.pre, suf=sc.kmc.suf)
+    wins, segs, *_ = fixed_windows(sc.seq_lens, 10_000, 0, 31)
+    for mc, w in [(1, (0.3, 0.3, 0.4)), (5, (0.5, 0.25, 0.25)), (12, (0.0, 0.0, 1.0)), (300, (0.3, 0.3, 0.4))]:
+        rc, want = _oracle_screen(sc, wins, segs, min_count=mc, w=w)
+        assert rc == 0
+        got = ctx.screen(db, wins, segs, min_count=mc, weights=w)
+        assert_results_equal(got, want)
+    # min_count 300 > max counter (255): no hit anywhere -> variations 1, right = total (Q5)
+    assert (got["obs"] == 0).all() and (got["variations"][got["total_kmers"] > 0] == 1).all()
+    assert (got["right"] == got["total_kmers"]).all() and (got["score"] == 0).all()
+    # weights that do not sum to 1.0 are fatal in the reference once a score is computed
+    with pytest.raises(KcfError) as e:
+        ctx.screen(db, wins, segs, weights=(0.3, 0.3, 0.5))
+    assert e.value.code == -8
+    with pytest.raises(KcfError) as e:
+        ctx.screen(db, wins, segs, min_count=0)
+    assert e.value.code == -5
+    db.close()
+
+
+def test_multi_segment_windows(ctx, sc_main):
+    """gene / transcript style windows: concatenated loci, k-mers span the junctions (GTF.java:240-244)."""
+    sc = sc_main
+    sc.add_to(ctx)
+    db = KMC(ctx, pre=sc.kmc.pre, suf=sc.kmc.suf)
+    rng = np.random.default_rng(5)
+    lists = []
+    for _ in range(300):
+        sid = int(rng.integers(0, 2))
+        n = sc.seq_lens[sid]
+        ns = int(rng.integers(1, 9))
+        pos = int(rng.integers(0, n - 30_000))
+        sl = []
+        for _ in range(ns):
+            ln = int(rng.integers(1, 2500))
+            sl.append((sid, pos, ln))
+            pos += ln + int(rng.integers(0, 800))  # 0 => abutting loci
+        lists.append(sl)
+    lists.append([(0, 0, 10), (1, 5, 12), (0, 100, 9)])       # shorter than k in total: 31 bases, exactly one k-mer
+    lists.append([(0, 0, 5), (0, 5, 5)])                       # 10 bases: no k-mer
+    lists.append([(2, 0, 40)])                                  # the 40-base sequence
+    lists.append([(0, 0, 300_000), (1, 0, 123_457)])           # very long window (many tiles)
+    wins, segs = windows_from_lists(lists)
+    rc, want = _oracle_screen(sc, wins, segs)
+    assert rc == 0
+    got = ctx.screen(db, wins, segs)
+    assert_results_equal(got, want)
+    assert want["total_kmers"][-3] == 0 and want["total_kmers"][-4] <= 1
+    db.close()
+
+
+@pytest.mark.parametrize("k,P,L,cs,both,line", [(32, 8, 9, 2, True, 70), (21, 5, 7, 1, False, 60), (13, 1, 5, 3, True, 33),
+                                                 (5, 1, 3, 1, True, 7), (31, 3, 9, 1, True, 1000), (16, 4, 5, 0, True, 60)])
+def test_other_k_and_layouts(ctx, k, P, L, cs, both, line):
+    sc = Scenario(seq_lens=(30_000, 2_000), k=k, P=P, L=L, n_bins=8, counter_size=cs, both_strands=both, seed=k, line=line,
+                  coverage=8.0 if cs else 1.0)
+    sc.add_to(ctx)
+    db = KMC(ctx, pre=sc.kmc.pre, suf=sc.kmc.suf)
+    assert db.info.unreachable_kmers == 0
+    wins, segs, *_ = fixed_windows(sc.seq_lens, 4000, 0, k)
+    rc, want = _oracle_screen(sc, wins, segs)
+    assert rc == 0
+    got = ctx.screen(db, wins, segs)
+    assert_results_equal(got, want)
+    if cs == 0:
+        assert (got["obs"] == 0).all()  # Q7: counter_size 0 => nothing is ever observed
+    db.close()
+
+
+def test_high_load_factor_uses_displacement_and_stash(ctx, sc_main):
+    sc = sc_main
+    sc.add_to(ctx)
+    ctx.set_load_factor(0.9)
+    try:
+        db = KMC(ctx, pre=sc.kmc.pre, suf=sc.kmc.suf)
+    finally:
+        ctx.set_load_factor(0.5)
+    assert db.info.resident_kmers == sc.kmc.total
+    wins, segs, *_ = fixed_windows(sc.seq_lens, 20_000, 0, 31)
+    rc, want = _oracle_screen(sc, wins, segs)
+    got = ctx.screen(db, wins, segs)
+    assert_results_equal(got, want)
+    db.close()
+
+
+def test_unreachable_records_are_ignored_like_the_reference(ctx):
+    """records sitting in a bin their signature does not map to can never be returned by KMC.getCount."""
+    sc = Scenario(seq_lens=(20_000,), seed=9, n_bins=16)
+    # rotate the signature map: most records now live in the "wrong" bin for both implementations
+    img = sc.kmc
+    L = img.L
+    nmap = (1 << (2 * L)) + 1
+    pre = img.pre.copy()
+    map_start = pre.size - 68 - 8 - nmap * 4
+    m = pre[map_start:map_start + 4 * nmap].view("<u4").copy()
+    m[::3] = (m[::3] + 1) % 16
+    pre[map_start:map_start + 4 * nmap] = m.view(np.uint8)
+    sc.kmc = synth.KmcImage(pre, img.suf, img.k, img.P, img.L, img.n_bins, img.counter_size, img.total, img.both_strands)
+    sc.add_to(ctx)
+    db = KMC(ctx, pre=sc.kmc.pre, suf=sc.kmc.suf)
+    assert 0 < db.info.unreachable_kmers < img.total
+    wins, segs, *_ = fixed_windows(sc.seq_lens, 2000, 0, 31)
+    rc, want = _oracle_screen(sc, wins, segs)
+    got = ctx.screen(db, wins, segs)
+    assert_results_equal(got, want)
+    db.close()
+
+
+def test_error_codes(ctx, sc_main):
+    sc = sc_main
+    sc.add_to(ctx)
+    db = KMC(ctx, pre=sc.kmc.pre, suf=sc.kmc.suf)
+    # segment outside its sequence (FastaIndex.java:132-135)
+    wins, segs = windows_from_lists([[(0, 299_990, 100)]])
+    with pytest.raises(KcfError) as e:
+        ctx.screen(db, wins, segs)
+    assert e.value.code == -6
+    wins, segs = windows_from_lists([[(5, 0, 100)]])
+    with pytest.raises(KcfError) as e:
+        ctx.screen(db, wins, segs)
+    assert e.value.code == -6
+    # bad version
+    pre = sc.kmc.pre.copy()
+    pre[pre.size - 8 - 4:pre.size - 8] = 0
+    with pytest.raises(KcfError) as e:
+        KMC(ctx, pre=pre, suf=sc.kmc.suf)
+    assert e.value.code == -3
+    # unsorted records
+    suf = sc.kmc.suf.copy()
+    suf[4:11], suf[11:18] = sc.kmc.suf[11:18].copy(), sc.kmc.suf[4:11].copy()
+    with pytest.raises(KcfError) as e:
+        KMC(ctx, pre=sc.kmc.pre, suf=suf)
+    assert e.value.code in (-10,)
+    # missing trailing newline: reading the final bases is fatal in the reference (Q9)
+    g = synth.random_genome(500, 4)
+    rec = synth.fasta_record(g, "x", line=60, trailing_newline=False)
+    ctx.ref_clear()
+    ctx.ref_add(rec[3:], 60, 61, 500)
+    wins, segs = windows_from_lists([[(0, 400, 100)]])
+    with pytest.raises(KcfError) as e:
+        ctx.screen(db, wins, segs)
+    assert e.value.code == -7
+    wins, segs = windows_from_lists([[(0, 300, 100)]])
+    ctx.screen(db, wins, segs)
+    db.close()
+
+
+def test_empty_inputs(ctx, sc_main):
+    sc = sc_main
+    sc.add_to(ctx)
+    db = KMC(ctx, pre=sc.kmc.pre, suf=sc.kmc.suf)
+    wins, segs = windows_from_lists([])
+    assert ctx.screen(db, wins, segs).size == 0
+    db.close()
+    # empty database: everything is a miss
+    import torch
+    z = torch.zeros(0, dtype=torch.int64)
+    img = synth.kmc_image_from_kmers(z, z, z, k=31, P=7, L=9, n_bins=4, counter_size=1)
+    db = KMC(ctx, pre=img.pre, suf=img.suf)
+    wins, segs, *_ = fixed_windows(sc.seq_lens, 50_000, 0, 31)
+    got = ctx.screen(db, wins, segs)
+    assert (got["obs"] == 0).all() and (got["right"] == got["total_kmers"]).all()
+    db.close()
