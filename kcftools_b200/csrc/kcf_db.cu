@@ -308,7 +308,7 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     int rc = KCF_OK;
     const uint64_t chunk_rec = std::max<uint64_t>(1, (64ULL << 20) / std::max<uint32_t>(rec_size, 1));
     const uint64_t chunk_bytes = chunk_rec * std::max<uint32_t>(rec_size, 1);
-    const uint64_t ovf_cap = N / 64 + 4096;
+    const uint64_t ovf_cap = N / 16 + 4096;
     unsigned long long counters[3] = {0, 0, 0};
     uint32_t flags[FLAG_COUNT] = {0};
 

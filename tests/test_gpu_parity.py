@@ -204,12 +204,14 @@ def test_error_codes(ctx, sc_main):
     with pytest.raises(KcfError) as e:
         KMC(ctx, pre=pre, suf=sc.kmc.suf)
     assert e.value.code == -3
-    # unsorted records
-    suf = sc.kmc.suf.copy()
-    suf[4:11], suf[11:18] = sc.kmc.suf[11:18].copy(), sc.kmc.suf[4:11].copy()
+    # unsorted records inside one (bin, prefix) range: the reference's binary search is undefined -> refused
+    sc2 = Scenario(seq_lens=(20_000,), seed=2, n_bins=2, P=3)
+    KMC(ctx, pre=sc2.kmc.pre, suf=sc2.kmc.suf).close()
+    suf = sc2.kmc.suf.copy()
+    suf[4:12], suf[12:20] = sc2.kmc.suf[12:20].copy(), sc2.kmc.suf[4:12].copy()  # 7 suffix bytes + 1 counter byte
     with pytest.raises(KcfError) as e:
-        KMC(ctx, pre=sc.kmc.pre, suf=suf)
-    assert e.value.code in (-10,)
+        KMC(ctx, pre=sc2.kmc.pre, suf=suf)
+    assert e.value.code == -10
     # missing trailing newline: reading the final bases is fatal in the reference (Q9)
     g = synth.random_genome(500, 4)
     rec = synth.fasta_record(g, "x", line=60, trailing_newline=False)

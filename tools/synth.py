@@ -281,7 +281,9 @@ def kmc_image_from_kmers(kmers: torch.Tensor, counts: torch.Tensor, sigs: torch.
         rec[:, j] = ((suffix >> (8 * (nsb - 1 - j))) & 0xFF).to(torch.uint8)
     for j in range(counter_size):
         rec[:, nsb + j] = ((counts >> (8 * j)) & 0xFF).to(torch.uint8)
-    suf = np.concatenate([np.frombuffer(b"KMCS", np.uint8), rec.flatten().cpu().numpy(), np.frombuffer(b"KMCS", np.uint8)])
+    mark = torch.tensor(list(b"KMCS"), dtype=torch.uint8, device=dev)
+    suf = torch.cat([mark, rec.flatten(), mark]).cpu().numpy()  # one device-side assembly, one D2H
+    del rec
     header = struct.pack("<7IQB3x24xI", k, 0, counter_size, P, L, min_count, max_count, N, 0 if both_strands else 1, 0x200)
     assert len(header) == 68
     pre = np.concatenate([
