@@ -153,6 +153,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-windows", type=int, default=0, help="windows in the CPU baseline sample (0 = auto, ~15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lf", type=float, default=0.0, help="table load factor (0 = library default)")
+    ap.add_argument("--m", type=int, default=0, help="minimizer length (0 = automatic)")
     args = ap.parse_args()
 
     import torch
@@ -209,6 +211,10 @@ def main():
     # ------------------------------------------------------------------ our arm (GPU)
     from kcftools_b200.api import Context, KMC
     ctx = Context(local_rank)
+    if args.lf > 0:
+        ctx.set_load_factor(args.lf)
+    if args.m > 0:
+        ctx.set_minimizer_length(args.m)
     stream = torch.cuda.ExternalStream(ctx.stream, device=device)
     t0 = time.time()
     db = KMC(ctx, pre=kmc.pre, suf=kmc.suf)

@@ -93,7 +93,7 @@ typedef struct kcf_db_info_t {
     int64_t unreachable_kmers;  /* records no reference lookup can ever reach (wrong bin / non-canonical / before LUT[0]) */
     int64_t stash_kmers;        /* resident records living in the overflow stash */
     int64_t table_bytes;        /* HBM bytes of the lookup structure */
-    int64_t n_buckets;          /* 32-byte buckets */
+    int64_t n_buckets;          /* 128-byte table lines */
     double load_seconds;        /* wall time of the open call */
 } kcf_db_info_t;
 
@@ -121,6 +121,9 @@ int kcf_db_info(kcf_db *db, kcf_db_info_t *out);
 void kcf_db_close(kcf_db *db);
 /* Load-factor target for subsequently opened databases (0 < lf <= 0.9; default 0.5). */
 int kcf_set_load_factor(kcf_ctx *ctx, double lf);
+/* Minimizer length of the home-line function for subsequently opened databases (1..16; 0 = chosen from the
+ * database size).  A tuning / test knob: results never depend on it. */
+int kcf_set_minimizer_length(kcf_ctx *ctx, int m);
 
 /* KMC.getCount for a batch of k-mers given as ASCII (n * k bytes, upper or lower case ACGT), canonicalised
  * per the database's both_strands flag like GetVariants.java:222-223.  counts_out[i] is the Java int.

@@ -47,6 +47,7 @@ SYMBOLS = {
     "kcf_db_info": (C.c_int, [_P, C.POINTER(DbInfo)]),
     "kcf_db_close": (None, [_P]),
     "kcf_set_load_factor": (C.c_int, [_P, C.c_double]),
+    "kcf_set_minimizer_length": (C.c_int, [_P, C.c_int]),
     "kcf_db_count": (C.c_int, [_P, _P, _P, C.c_uint64, _P]),
     "kcf_ref_add": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_int)]),
     "kcf_ref_clear": (C.c_int, [_P]),

@@ -66,6 +66,10 @@ class Context:
     def set_load_factor(self, lf: float):
         self._check(self._lib.kcf_set_load_factor(self._h, lf))
 
+    def set_minimizer_length(self, m: int):
+        """0 = automatic; a tuning / test knob of the table layout, results never depend on it"""
+        self._check(self._lib.kcf_set_minimizer_length(self._h, m))
+
     def set_profiling(self, on: bool):
         self._check(self._lib.kcf_set_profiling(self._h, int(on)))
 

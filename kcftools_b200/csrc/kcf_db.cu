@@ -73,7 +73,7 @@ struct KcfIngestParams {
     const uint32_t *sigmap;
     const uint32_t *norm;
     uint32_t P, L, nsb, cs, rec_size;
-    uint64_t *table;
+    uint8_t *table;
     KcfStashEntry *ovf;      // overflow list
     uint64_t ovf_cap;
     unsigned long long *counters; // [0] inserted, [1] unreachable, [2] overflow
@@ -132,21 +132,44 @@ __global__ void __launch_bounds__(256) kcf_ingest_kernel(KcfIngestParams p, KcfT
         atomicAdd(&p.counters[1], 1ULL);
         return;
     }
-    const uint64_t h = kcf_mix(kmer, g);
-    const uint64_t home = kcf_home_bucket(h, g);
-    const uint64_t rem = h & g.rmask;
-    for (uint32_t d = 0; d <= KCF_MAX_DISP; ++d) {
-        uint64_t b = home + d;
-        if (b >= g.n_buckets) b -= g.n_buckets;
-        const uint64_t entry = ((((uint64_t)(8u | d) << g.rbits) | rem) << g.cbits) | count;
-        unsigned long long *slot = (unsigned long long *)(p.table + 4 * b);
-        for (int s = 0; s < KCF_SLOTS_PER_BUCKET; ++s) {
-            if (slot[s] == 0ULL && atomicCAS(&slot[s], 0ULL, (unsigned long long)entry) == 0ULL) {
-                atomicAdd(&p.counters[0], 1ULL);
-                return;
+    if (p.cs == 0) { // Q7: a 0-byte counter reads as 0, never a hit; nothing to store
+        atomicAdd(&p.counters[0], 1ULL);
+        return;
+    }
+    const uint32_t home = kcf_home_line(kcf_minimizer_of_key(kmer, g), g);
+    uint32_t *home_w31 = reinterpret_cast<uint32_t *>(p.table + (uint64_t)home * KCF_LINE_BYTES) + 31;
+    if (KCF_KEY_IN_LINES(kmer)) {
+        const uint32_t lo = (uint32_t)kmer, hi = (uint32_t)(kmer >> 32);
+        for (uint32_t d = 0; d <= KCF_MAX_DISP; ++d) {
+            uint8_t *line = p.table + (uint64_t)kcf_line_wrap(home, d, g) * KCF_LINE_BYTES;
+            uint32_t *w = reinterpret_cast<uint32_t *>(line);
+            bool placed = false;
+            for (uint32_t s = 0; s < g.S; ++s) {
+                uint32_t v = ((volatile uint32_t *)w)[s];
+                if (v == KCF_EMPTY_LO) {
+                    v = atomicCAS(&w[s], KCF_EMPTY_LO, lo); // claiming a slot and publishing the low word are one step
+                    if (v == KCF_EMPTY_LO) {
+                        w[g.S + s] = hi;
+                        // count and mask bits are cleared out of the all-ones initial image (atomics: several writers
+                        // share these 32-bit words)
+                        const uint32_t off = 8 * g.S + g.cw * s;
+                        const uint32_t sh = 8 * (off & 3u);
+                        const uint32_t field = g.cw == 4 ? 0xFFFFFFFFu : (((1u << (8 * g.cw)) - 1u) << sh);
+                        atomicAnd(w + (off >> 2), ~field | (count << sh));
+                        atomicAnd(home_w31, ~(1u << (16 + d)));
+                        atomicAdd(&p.counters[0], 1ULL);
+                        placed = true;
+                        break;
+                    }
+                }
+                // a key with the same low word already lives in this line: keep low words unique per line (a probe
+                // then has one candidate at most) and move on to the next line
+                if (v == lo) break;
             }
+            if (placed) return;
         }
     }
+    atomicAnd(home_w31, ~(1u << (16 + KCF_STASH_BIT)));
     unsigned long long pos = atomicAdd(&p.counters[2], 1ULL);
     if (pos < p.ovf_cap) {
         p.ovf[pos].key = kmer;
@@ -159,7 +182,7 @@ __global__ void kcf_stash_build_kernel(const KcfStashEntry *__restrict__ ovf, ui
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     KcfStashEntry e = ovf[t];
-    uint64_t i = (kcf_mix(e.key, g) * 0x9E3779B97F4A7C15ULL) >> 20;
+    uint64_t i = kcf_mix64(e.key);
     for (uint64_t k = 0;; ++k) {
         KcfStashEntry *s = &stash[(i + k) & g.stash_mask];
         if (atomicCAS((unsigned long long *)&s->meta, 0ULL, (unsigned long long)e.meta) == 0ULL) {
@@ -170,7 +193,7 @@ __global__ void kcf_stash_build_kernel(const KcfStashEntry *__restrict__ ovf, ui
 }
 
 // ---- KMC.getCount for a batch of ASCII k-mers (parity helper) ----------------------------------
-__global__ void kcf_count_kernel(const char *__restrict__ ascii, uint64_t n, const uint64_t *__restrict__ table,
+__global__ void kcf_count_kernel(const char *__restrict__ ascii, uint64_t n, const uint8_t *__restrict__ table,
                                  const KcfStashEntry *__restrict__ stash, KcfTableGeom g, int32_t *__restrict__ out)
 {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -211,6 +234,14 @@ extern "C" int kcf_set_load_factor(kcf_ctx *ctx, double lf)
     if (!ctx) return KCF_ERR_ARG;
     if (!(lf > 0.0) || lf > 0.9) return kcf_fail(ctx, KCF_ERR_ARG, "load factor must be in (0, 0.9]");
     ctx->load_factor = lf;
+    return KCF_OK;
+}
+
+extern "C" int kcf_set_minimizer_length(kcf_ctx *ctx, int m)
+{
+    if (!ctx) return KCF_ERR_ARG;
+    if (m < 0 || m > 16) return kcf_fail(ctx, KCF_ERR_ARG, "minimizer length must be 0 (auto) or 1..16");
+    ctx->minimizer_len = m;
     return KCF_OK;
 }
 
@@ -267,33 +298,33 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
                             rd_u32(pre + sig_map_start + 4 * i), (unsigned long long)n_bins);
 
     // --- table geometry ---
-    const uint32_t cbits = 8u * (uint32_t)cs;
     const int kk2 = 2 * k;
-    uint64_t nb = (uint64_t)((double)N / (KCF_SLOTS_PER_BUCKET * ctx->load_factor)) + 1;
-    const int min_log = kk2 + 1 + KCF_DISP_BITS + 1 + (int)cbits - 64; // so that 1 + disp + rem + count fit 64 bits
-    if (min_log > 31) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "k=%d with %d-byte counters needs a wide-slot table (not in this build)", k, cs);
-    nb = std::max<uint64_t>(nb, 64);
-    if (min_log > 0) nb = std::max<uint64_t>(nb, 1ULL << min_log);
-    if (kk2 < 63) nb = std::min<uint64_t>(nb, 1ULL << kk2); // never more buckets than distinct keys
-    nb = std::max<uint64_t>(nb, 1);
     KcfTableGeom g{};
-    g.n_buckets = nb;
     g.k = (uint32_t)k;
     g.kshift = 64 - kk2;
     g.kmask = kk2 == 64 ? ~0ULL : ((1ULL << kk2) - 1);
-    int fl = floor_log2_u64(nb);
-    int rbits = kk2 - fl + (((nb & (nb - 1)) != 0) ? 1 : 0);
-    if (rbits < 1) rbits = 1;
-    if (rbits > kk2) rbits = kk2;
-    if (1 + KCF_DISP_BITS + rbits + (int)cbits > 64)
-        return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "slot does not fit: rem %d + count %u bits", rbits, cbits);
-    g.rbits = (uint32_t)rbits;
-    g.rmask = rbits == 64 ? ~0ULL : ((1ULL << rbits) - 1);
-    g.cbits = cbits;
-    g.cmask = cbits == 0 ? 0 : ((1ULL << cbits) - 1);
+    g.cw = cs <= 1 ? 1u : (cs == 2 ? 2u : 4u);
+    g.S = g.cw == 1 ? 14u : (g.cw == 2 ? 12u : 10u);
     g.both_strands = (uint32_t)info.both_strands;
-    g.s1 = (uint32_t)std::max(1, k);
-    g.s2 = (uint32_t)std::max(1, k - 3);
+    {
+        // minimizer length: long enough that one m-mer value rarely names more than one locus of the
+        // sampled genome (4^m >= 4 N), short enough that consecutive k-mers share it (w = k-m+1)
+        int m = ctx->minimizer_len;
+        if (m <= 0) {
+            m = 8;
+            while (m < 16 && (1ULL << (2 * m)) < 4 * N) ++m;
+        }
+        m = std::min(std::min(m, 16), k);
+        m = std::max(m, 1);
+        if (k - m + 1 > 32) m = k - 31;
+        g.m = (uint32_t)m;
+        g.w = (uint32_t)(k - m + 1);
+        g.mmask = m == 16 ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
+    }
+    uint64_t nb = cs == 0 ? 1 : (uint64_t)((double)N / (g.S * ctx->load_factor)) + 1;
+    nb = std::max<uint64_t>(nb, cs == 0 ? 1 : 64);
+    if (nb >= 0xFFFFFFFFULL) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "%llu records need more than 2^32 table lines; partition the database", (unsigned long long)N);
+    g.n_lines = nb;
     g.stash_mask = 0;
 
     kcf_db *db = new kcf_db();
@@ -308,7 +339,7 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     int rc = KCF_OK;
     const uint64_t chunk_rec = std::max<uint64_t>(1, (64ULL << 20) / std::max<uint32_t>(rec_size, 1));
     const uint64_t chunk_bytes = chunk_rec * std::max<uint32_t>(rec_size, 1);
-    const uint64_t ovf_cap = N / 16 + 4096;
+    uint64_t ovf_cap = N / 16 + 4096;
     unsigned long long counters[3] = {0, 0, 0};
     uint32_t flags[FLAG_COUNT] = {0};
 
@@ -322,8 +353,8 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
         }                                                                                                     \
     } while (0)
 
-    DB_CUDA(cudaMalloc(&db->table, nb * 32));
-    DB_CUDA(cudaMemsetAsync(db->table, 0, nb * 32, ctx->stream));
+    DB_CUDA(cudaMalloc(&db->table, nb * KCF_LINE_BYTES));
+    DB_CUDA(cudaMemsetAsync(db->table, 0xFF, nb * KCF_LINE_BYTES, ctx->stream)); // empty keys, zero counts and masks (stored inverted)
     DB_CUDA(cudaMalloc(&d_lut, std::max<uint64_t>(lut_len, 1) * 8));
     DB_CUDA(cudaMalloc(&d_sigmap, sig_map_size * 4));
     DB_CUDA(cudaMalloc(&d_norm, (1ULL << (2 * L)) * 4));
@@ -344,7 +375,17 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
         DB_CUDA(cudaHostAlloc(&h_stage[j], chunk_bytes, cudaHostAllocDefault));
         DB_CUDA(cudaEventCreateWithFlags(&ev[j], cudaEventDisableTiming));
     }
-    {
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) {
+            // the overflow list was too short (a table whose minimizers collide massively): the device counted
+            // how long it has to be; reset the table and stream the records once more
+            cudaFree(d_ovf);
+            d_ovf = nullptr;
+            ovf_cap = counters[2];
+            DB_CUDA(cudaMalloc(&d_ovf, ovf_cap * sizeof(KcfStashEntry)));
+            DB_CUDA(cudaMemsetAsync(db->table, 0xFF, nb * KCF_LINE_BYTES, ctx->stream));
+            DB_CUDA(cudaMemsetAsync(d_counters, 0, 3 * sizeof(unsigned long long), ctx->stream));
+        }
         const uint8_t *recs = suf + 4; // KMC.java:94 — skip the KMCS marker
         int j = 0;
         for (uint64_t r0 = 0; r0 < N; r0 += chunk_rec, j ^= 1) {
@@ -376,10 +417,11 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
             DB_CUDA(cudaGetLastError());
             DB_CUDA(cudaEventRecord(ev[j], ctx->stream));
         }
+        DB_CUDA(cudaMemcpyAsync(counters, d_counters, sizeof counters, cudaMemcpyDeviceToHost, ctx->stream));
+        DB_CUDA(cudaMemcpyAsync(flags, ctx->d_flags, sizeof flags, cudaMemcpyDeviceToHost, ctx->stream));
+        DB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (counters[2] <= ovf_cap || flags[FLAG_LUT_BAD] || flags[FLAG_ORDER_BAD]) break;
     }
-    DB_CUDA(cudaMemcpyAsync(counters, d_counters, sizeof counters, cudaMemcpyDeviceToHost, ctx->stream));
-    DB_CUDA(cudaMemcpyAsync(flags, ctx->d_flags, sizeof flags, cudaMemcpyDeviceToHost, ctx->stream));
-    DB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (flags[FLAG_LUT_BAD]) { rc = kcf_fail(ctx, KCF_ERR_DB_FORMAT, "prefix LUT is not monotone or exceeds total_kmers"); goto done; }
     if (flags[FLAG_ORDER_BAD]) { rc = kcf_fail(ctx, KCF_ERR_DB_ORDER, "records inside a (bin, prefix) range are not strictly ascending"); goto done; }
     if (counters[2] > ovf_cap) { rc = kcf_fail(ctx, KCF_ERR_NOMEM, "hash overflow list exhausted (%llu entries); lower the load factor", counters[2]); goto done; }
@@ -397,7 +439,7 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     info.unreachable_kmers = (int64_t)counters[1];
     info.stash_kmers = (int64_t)counters[2];
     info.n_buckets = (int64_t)nb;
-    info.table_bytes = (int64_t)(nb * 32 + (db->stash ? (g.stash_mask + 1) * sizeof(KcfStashEntry) : 0));
+    info.table_bytes = (int64_t)(nb * KCF_LINE_BYTES + (db->stash ? (g.stash_mask + 1) * sizeof(KcfStashEntry) : 0));
     info.load_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     db->info = info;
     db->geom = g;

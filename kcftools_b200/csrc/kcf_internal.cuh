@@ -11,34 +11,41 @@
 //
 // The reference finds a k-mer by signature -> bin -> prefix LUT -> binary search over 7-11 byte
 // records (KMC.java:292-326): ~23 table lookups plus ~log2(range) dependent random reads.  Here
-// the records are re-keyed once at load time into an open-addressing table whose unit is one
-// 32-byte DRAM sector:
+// the records are re-keyed once at load time into a table whose unit is one 128-byte line — the
+// granularity at which B200's HBM serves a random access (profiles/README.md) — and whose home
+// line is chosen by the k-mer's MINIMIZER, so that the ~(w+1)/2 consecutive reference k-mers
+// sharing a minimizer probe the same line:
 //
-//   h      = mix(canonical k-mer)            bijection on 2k bits
-//   bucket = floor(h * n_buckets / 4^k)      home bucket
-//   slot   = [1 | disp:3 | rem:r | count:cbits]   64 bits, 4 slots per bucket
+//   o(x)   = mix32(min(x, revcomp(x)))         order hash of an m-mer, strand symmetric
+//   mu(K)  = min o(x) over the w = k-m+1 m-mers of K
+//   home   = floor(mix32(mu ^ c) * n_lines / 2^32)
+//   line   = S key low words | S key high words | S counts | 16-bit mask      (S = 14 for 1-byte counts)
+//            (key = canonical k-mer value, stored in full; low word 0xFFFFFFFF = empty slot)
 //
-// rem = low r bits of h; the h values of one home bucket form an interval shorter than 2^r, so
-// (home bucket, rem) identifies h and therefore the k-mer.  An entry that does not fit its home
-// bucket goes to bucket home+disp (disp <= 7); beyond that to a small stash.  A probe stops at the
-// first bucket with a free slot (there are no deletions).
+// A key lives in line home+d, 0 <= d <= 14, the first one with a free slot when it was inserted
+// (no deletions).  Bit d of the HOME line's mask says "some key homed here lives in home+d", bit 15
+// "some key homed here lives in the stash"; a lookup therefore knows after reading the home line
+// exactly which other lines (if any) can hold its key.  Keys are stored in full: a probe is exact.
 // ------------------------------------------------------------------------------------------
-#define KCF_SLOTS_PER_BUCKET 4
-#define KCF_DISP_BITS 3
-#define KCF_MAX_DISP 7
+#define KCF_LINE_BYTES 128
+#define KCF_MAX_DISP 14
+#define KCF_STASH_BIT 15
+#define KCF_EMPTY_LO 0xFFFFFFFFu // low key word of a free slot
+// keys whose low word equals the marker live in the stash
+#define KCF_KEY_IN_LINES(key) ((uint32_t)(key) != KCF_EMPTY_LO)
 
 struct KcfTableGeom {
-    uint64_t n_buckets;
+    uint64_t n_lines;    // < 2^32 - 1
     uint64_t kmask;      // 2k one-bits
-    uint64_t rmask;      // r one-bits
-    uint64_t cmask;      // cbits one-bits
     uint64_t stash_mask; // stash capacity - 1 (power of two), 0 when the stash is empty
     uint32_t k;
     uint32_t kshift;     // 64 - 2k
-    uint32_t rbits;
-    uint32_t cbits;
+    uint32_t m;          // minimizer length, 1..16, <= k
+    uint32_t w;          // k - m + 1 (1..32)
+    uint32_t mmask;      // 2m one-bits
+    uint32_t S;          // slots per line: 14 / 12 / 10 for count width 1 / 2 / 4
+    uint32_t cw;         // bytes per stored count: 1, 2 or 4 (0-byte counters store nothing)
     uint32_t both_strands;
-    uint32_t s1, s2;     // xor-shift distances of the mixer
 };
 
 struct KcfStashEntry {
@@ -46,23 +53,27 @@ struct KcfStashEntry {
     uint64_t meta;  // bit 63 = occupied, low 32 bits = count
 };
 
-// bijective mixer on 2k-bit values: xorshift / odd multiply rounds, all modulo 2^(2k)
-__host__ __device__ __forceinline__ uint64_t kcf_mix(uint64_t x, const KcfTableGeom &g)
+// bijective 32-bit mixer (multiply / xorshift rounds)
+__host__ __device__ __forceinline__ uint32_t kcf_mix32(uint32_t x)
 {
-    x ^= x >> g.s1;
-    x = (x * 0xff51afd7ed558ccdULL) & g.kmask;
-    x ^= x >> g.s2;
-    x = (x * 0xc4ceb9fe1a85ec53ULL) & g.kmask;
-    x ^= x >> g.s1;
+    x ^= x >> 16;
+    x *= 0x7feb352dU;
+    x ^= x >> 15;
+    x *= 0x846ca68bU;
+    x ^= x >> 16;
     return x;
 }
 
-#ifdef __CUDACC__
-__device__ __forceinline__ uint64_t kcf_home_bucket(uint64_t h, const KcfTableGeom &g)
+// 64-bit mixer used for the stash only
+__host__ __device__ __forceinline__ uint64_t kcf_mix64(uint64_t x)
 {
-    return __umul64hi(h << g.kshift, g.n_buckets);
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
 }
-#endif
 
 // ------------------------------------------------------------------------------------------
 // Reference sequences: 2-bit codes (16 bases per u32, base j of a word in bits 2j..2j+1) and a
@@ -110,6 +121,7 @@ struct kcf_ctx {
     uint8_t *d_raw = nullptr;    // staging for raw FASTA bytes
     size_t d_raw_cap = 0;
     double load_factor = 0.5;
+    int minimizer_len = 0;       // 0 = chosen from the database size
     int sm_count = 148;
     int profiling = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -122,7 +134,7 @@ struct kcf_db {
     kcf_ctx *ctx = nullptr;
     kcf_db_info_t info{};
     KcfTableGeom geom{};
-    uint64_t *table = nullptr;       // n_buckets * 4 slots
+    uint8_t *table = nullptr;        // n_lines * 128 bytes
     KcfStashEntry *stash = nullptr;  // stash_mask + 1 entries
 };
 
@@ -143,10 +155,13 @@ struct kcf_plan {
     double weights[3] = {0, 0, 0};
 };
 
-#define KCF_TILE 2048          // positions per tile (256 threads x 8)
-#define KCF_THREADS 256
+#define KCF_TILE 2048          // positions per tile = the unit of work one warp takes
+#define KCF_SUB 256            // positions per step of a warp (32 lanes x 8)
 #define KCF_PER_THREAD 8
-#define KCF_HALO 32            // bases staged before the tile (>= k-1, word aligned)
+#define KCF_HALO 32            // bases staged before a step (>= k-1, word aligned)
+#define KCF_HCW 40             // home lines staged per chunk of runs
+#define KCF_ECW 56             // continuation lines staged per round
+#define KCF_QC 512             // (k-mer, continuation line) pairs searched per round
 
 // indices into kcf_ctx::d_flags
 enum { FLAG_LUT_BAD = 0, FLAG_ORDER_BAD = 1, FLAG_SCORE_USED = 2, FLAG_COUNT = 8 };

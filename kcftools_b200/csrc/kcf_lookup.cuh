@@ -1,67 +1,95 @@
-// kcf_lookup.cuh — device-side probe of the HBM-resident k-mer table.
-// Replaces KMC.getCount (KMC.java:292-326): one 32-byte sector read in the common case.
+// kcf_lookup.cuh — device-side pieces shared by the database loader and the screening kernel:
+// k-mer bit tricks, the minimizer that picks a k-mer's home line, and the generic (global-memory)
+// probe that replaces KMC.getCount (KMC.java:292-326) outside the tiled fast path.
 #pragma once
 #include "kcf_internal.cuh"
 
-// one whole bucket = one DRAM sector, fetched with a single 256-bit load that bypasses L1
-// allocation (the probes are uniformly random; L1 is kept for the reference bases)
-__device__ __forceinline__ void kcf_ld_bucket(const uint64_t *p, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d)
+// bit-reverse a 64-bit word keeping each 2-bit base code intact: base j moves to pair 31-j
+__device__ __forceinline__ uint64_t kcf_pair_reverse64(uint64_t x)
 {
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
-                 : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
-                 : "l"(p));
+    uint64_t z = __brevll(x);
+    return ((z >> 1) & 0x5555555555555555ULL) | ((z & 0x5555555555555555ULL) << 1);
 }
 
-// reverse complement of a right-aligned 2k-bit k-mer value
+// reverse complement of a right-aligned 2k-bit k-mer value (first base most significant)
 __device__ __forceinline__ uint64_t kcf_revcomp(uint64_t x, uint32_t kshift)
 {
-    uint64_t z = __brevll(~x);
-    z = ((z >> 1) & 0x5555555555555555ULL) | ((z & 0x5555555555555555ULL) << 1);
-    return z >> kshift; // the complemented padding bits fall off the low end
+    return kcf_pair_reverse64(~x) >> kshift; // the complemented padding bits fall off the low end
 }
 
-// base-order reversal of a 2k-bit value packed LSB-first (base j in bits 2j) into the
+// base-order reversal of a 2k-bit value: LSB-first packing (base j in bits 2j) <-> the
 // first-base-most-significant value the reference uses (Kmer.java:232-252)
 __device__ __forceinline__ uint64_t kcf_pair_reverse(uint64_t x, uint32_t kshift)
 {
-    uint64_t z = __brevll(x);
-    z = ((z >> 1) & 0x5555555555555555ULL) | ((z & 0x5555555555555555ULL) << 1);
-    return z >> kshift;
+    return kcf_pair_reverse64(x) >> kshift;
 }
 
-// Match `tag` (valid|disp|rem) against the 4 slots of one bucket.  Returns true on a match and sets
-// count; `full` tells whether the probe sequence must continue.
-__device__ __forceinline__ bool kcf_match4(uint64_t s0, uint64_t s1, uint64_t s2, uint64_t s3, uint64_t tag,
-                                           const KcfTableGeom &g, uint32_t &count, bool &full)
+// Order hash of the m-mer that starts at base j of E (E: up to 32 bases packed LSB-first, R =
+// kcf_pair_reverse64(~E), i.e. the reverse complement of all 32 bases).  Strand symmetric: an m-mer
+// and its reverse complement get the same value.
+__device__ __forceinline__ uint32_t kcf_mmer_order(uint64_t E, uint64_t R, uint32_t j, const KcfTableGeom &g)
 {
-    const uint32_t cb = g.cbits;
-    bool m0 = (s0 >> cb) == tag, m1 = (s1 >> cb) == tag, m2 = (s2 >> cb) == tag, m3 = (s3 >> cb) == tag;
-    uint64_t hit = m0 ? s0 : (m1 ? s1 : (m2 ? s2 : s3));
-    bool any = m0 | m1 | m2 | m3;
-    count = (uint32_t)(hit & g.cmask);
-    full = (s0 != 0) & (s1 != 0) & (s2 != 0) & (s3 != 0);
-    return any;
+    const uint32_t x = (uint32_t)(E >> (2 * j)) & g.mmask;
+    const uint32_t r = (uint32_t)(R >> (2 * (32 - g.m - j))) & g.mmask;
+    return kcf_mix32(min(x, r));
 }
 
-// Continue a probe sequence after the home bucket was full and held no match (rare path).
-static __device__ __noinline__ uint32_t kcf_lookup_tail(const uint64_t *__restrict__ table, const KcfStashEntry *__restrict__ stash,
-                                                 const KcfTableGeom &g, uint64_t key, uint64_t h, uint64_t home)
+__device__ __forceinline__ uint32_t kcf_home_line(uint32_t mu, const KcfTableGeom &g)
 {
-    const uint64_t rem = h & g.rmask;
-    for (uint32_t d = 1; d <= KCF_MAX_DISP; ++d) {
-        uint64_t b = home + d;
-        if (b >= g.n_buckets) b -= g.n_buckets;
-        uint64_t s0, s1, s2, s3;
-        kcf_ld_bucket(table + 4 * b, s0, s1, s2, s3);
-        uint64_t tag = ((((uint64_t)(8u | d)) << g.rbits) | rem);
-        uint32_t c;
-        bool full;
-        if (kcf_match4(s0, s1, s2, s3, tag, g, c, full)) return c;
-        if (!full) return 0;
+    return __umulhi(kcf_mix32(mu ^ 0x9E3779B9u), (uint32_t)g.n_lines);
+}
+
+// minimizer value of a k-mer given as the reference's first-base-most-significant value
+__device__ __forceinline__ uint32_t kcf_minimizer_of_key(uint64_t key, const KcfTableGeom &g)
+{
+    const uint64_t E = kcf_pair_reverse(key, g.kshift);
+    const uint64_t R = kcf_pair_reverse64(~E);
+    uint32_t mu = 0xFFFFFFFFu;
+    for (uint32_t j = 0; j < g.w; ++j) mu = min(mu, kcf_mmer_order(E, R, j, g));
+    return mu;
+}
+
+__device__ __forceinline__ uint32_t kcf_line_wrap(uint32_t home, uint32_t d, const KcfTableGeom &g)
+{
+    uint64_t l = (uint64_t)home + d;
+    if (l >= g.n_lines) l -= g.n_lines;
+    return (uint32_t)l;
+}
+
+// the 16-bit mask of a home line (stored inverted so that the table can be initialised with 0xFF bytes)
+__device__ __forceinline__ uint32_t kcf_mask_from_word31(uint32_t w31) { return (~w31) >> 16; }
+
+// count of slot s of a line image (global or shared memory)
+__device__ __forceinline__ uint32_t kcf_slot_count(const uint8_t *line, uint32_t s, const KcfTableGeom &g)
+{
+    const uint8_t *c = line + 8 * g.S + g.cw * s;
+    if (g.cw == 1) return *c;
+    if (g.cw == 2) return *reinterpret_cast<const uint16_t *>(c);
+    return *reinterpret_cast<const uint32_t *>(c);
+}
+
+// search one line in global memory.  Inside a line the low words of the live keys are distinct (the loader
+// guarantees it), so the first low-word match is the only candidate.
+__device__ __forceinline__ bool kcf_line_find(const uint8_t *line, uint64_t key, const KcfTableGeom &g, uint32_t &count)
+{
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(line);
+    const uint32_t lo = (uint32_t)key, hi = (uint32_t)(key >> 32);
+    for (uint32_t s = 0; s < g.S; ++s) {
+        const uint32_t v = __ldg(w + s);
+        if (v == lo) {
+            if (__ldg(w + g.S + s) != hi) return false;
+            count = kcf_slot_count(line, s, g);
+            return true;
+        }
+        if (v == KCF_EMPTY_LO) return false; // occupied slots form a prefix of the line
     }
+    return false;
+}
+
+static __device__ __noinline__ uint32_t kcf_stash_find(const KcfStashEntry *__restrict__ stash, const KcfTableGeom &g, uint64_t key)
+{
     if (stash == nullptr) return 0;
-    // stash: linear probing over 16-byte entries
-    uint64_t i = (kcf_mix(key, g) * 0x9E3779B97F4A7C15ULL) >> 20;
+    uint64_t i = kcf_mix64(key);
     for (uint64_t n = 0; n <= g.stash_mask; ++n) {
         const KcfStashEntry e = stash[(i + n) & g.stash_mask];
         if (e.meta == 0) return 0;
@@ -70,18 +98,25 @@ static __device__ __noinline__ uint32_t kcf_lookup_tail(const uint64_t *__restri
     return 0;
 }
 
-// Full lookup of one canonical k-mer value (used by the count kernel and the slow paths).
-__device__ __forceinline__ uint32_t kcf_lookup(const uint64_t *__restrict__ table, const KcfStashEntry *__restrict__ stash,
+// Probe the lines named by `mask` bits [dmin, 14] of home line `home`, then the stash if bit 15 is set.
+static __device__ __noinline__ uint32_t kcf_probe_lines(const uint8_t *__restrict__ table, const KcfStashEntry *__restrict__ stash,
+                                                        const KcfTableGeom &g, uint64_t key, uint32_t home, uint32_t mask, uint32_t dmin)
+{
+    if (!KCF_KEY_IN_LINES(key)) dmin = KCF_MAX_DISP + 1; // low word doubles as a slot marker: such keys live in the stash
+    for (uint32_t d = dmin; d <= KCF_MAX_DISP; ++d) {
+        if (!((mask >> d) & 1u)) continue;
+        uint32_t c;
+        if (kcf_line_find(table + (uint64_t)kcf_line_wrap(home, d, g) * KCF_LINE_BYTES, key, g, c)) return c;
+    }
+    if ((mask >> KCF_STASH_BIT) & 1u) return kcf_stash_find(stash, g, key);
+    return 0;
+}
+
+// Full lookup of one canonical k-mer value (count kernel and slow paths).
+__device__ __forceinline__ uint32_t kcf_lookup(const uint8_t *__restrict__ table, const KcfStashEntry *__restrict__ stash,
                                                const KcfTableGeom &g, uint64_t key)
 {
-    uint64_t h = kcf_mix(key, g);
-    uint64_t home = kcf_home_bucket(h, g);
-    uint64_t s0, s1, s2, s3;
-    kcf_ld_bucket(table + 4 * home, s0, s1, s2, s3);
-    uint64_t tag = (((uint64_t)8u << g.rbits) | (h & g.rmask));
-    uint32_t c;
-    bool full;
-    if (kcf_match4(s0, s1, s2, s3, tag, g, c, full)) return c;
-    if (!full) return 0;
-    return kcf_lookup_tail(table, stash, g, key, h, home);
+    const uint32_t home = kcf_home_line(kcf_minimizer_of_key(key, g), g);
+    const uint32_t w31 = __ldg(reinterpret_cast<const uint32_t *>(table + (uint64_t)home * KCF_LINE_BYTES) + 31);
+    return kcf_probe_lines(table, stash, g, key, home, kcf_mask_from_word31(w31), 0);
 }

@@ -24,7 +24,7 @@ struct KcfScreenParams {
     const uint64_t *tile_first;
     uint64_t n_wins;
     uint64_t tile_begin, tile_end;
-    const uint64_t *table;
+    const uint8_t *table;
     const KcfStashEntry *stash;
     KcfGap *tile_sum;
     unsigned long long *tile_counter;
@@ -90,190 +90,452 @@ __device__ __forceinline__ KcfGap kcf_gap_shfl_down(const KcfGap &a, int delta)
     return r;
 }
 
-#define S_CODE_WORDS ((KCF_TILE + KCF_HALO) / 16 + 4)
-#define S_VALID_WORDS ((KCF_TILE + KCF_HALO) / 32 + 2)
+#define S_CODE_WORDS ((KCF_SUB + KCF_HALO) / 16 + 4)
+#define S_VALID_WORDS ((KCF_SUB + KCF_HALO) / 32 + 2)
+#define S_HASH_WORDS ((KCF_SUB + KCF_HALO) + (KCF_SUB + KCF_HALO) / 8) // one pad word per 8: bank-conflict-free windows
 
-__global__ void __launch_bounds__(KCF_THREADS, 2) kcf_screen_kernel(KcfScreenParams p, KcfTableGeom g)
+// Shared memory of one warp (one warp = one CTA: nothing in this kernel synchronises wider than a warp, so the
+// warps of an SM drift apart and one warp's table fetches overlap the others' arithmetic).  `lines` is the staging
+// area the table lines land in: the first KCF_HCW slots take the home lines of a chunk of runs, the last KCF_ECW
+// the continuation lines their masks name.
+struct KcfWarpSmem {
+    uint8_t lines[(KCF_HCW + KCF_ECW) * KCF_LINE_BYTES];
+    unsigned long long key[KCF_SUB]; // canonical k-mer of every position of the step (read back by the pair queue)
+    uint32_t hash[S_HASH_WORDS];
+    uint32_t cnt[KCF_SUB];           // counts found through the pair queue
+    uint32_t queue[KCF_QC];          // (position << 16 | continuation slot)
+    uint32_t fetch[KCF_HCW + KCF_ECW]; // table line staged in each slot
+    uint32_t need[KCF_HCW];          // run -> round in which its continuation lines were claimed
+    uint32_t extbase[KCF_HCW];       // run -> first continuation slot (0xFFFFFFFF: not this round)
+    uint32_t codes[S_CODE_WORDS];
+    uint32_t valid[S_VALID_WORDS];
+    uint32_t ext_count, q_count;
+    uint32_t ext_limit, q_limit; // first staging slot / queue entry of a claim that did not fit this round
+};
+
+__device__ __forceinline__ uint32_t kcf_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Cooperative fetch of n table lines into consecutive staging slots: 8 lanes move one 128-byte line (one coalesced
+// request per line) with 16-byte asynchronous copies that bypass the register file.
+__device__ __forceinline__ void kcf_fetch_lines(uint32_t dst_sa, const uint32_t *ids, uint32_t n, const uint8_t *table, uint32_t lane)
 {
-    __shared__ uint32_t s_codes[S_CODE_WORDS];
-    __shared__ uint32_t s_valid[S_VALID_WORDS];
-    __shared__ KcfGap s_warp[KCF_THREADS / 32];
-    __shared__ uint64_t s_tile;
-    __shared__ uint32_t s_win;
+    for (uint32_t q = lane; q < n * 8; q += 32) {
+        const uint8_t *src = table + (uint64_t)ids[q >> 3] * KCF_LINE_BYTES + (q & 7u) * 16u;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_sa + q * 16u), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void kcf_fetch_wait()
+{
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+}
 
-    const uint32_t tid = threadIdx.x;
+// Search a line staged in shared memory: S key low words, then S high words, then the counts.  Low words of the live
+// keys of a line are distinct, so there is one candidate at most; it is confirmed on the high word.  `rot` staggers the
+// order in which lanes walk the 16-byte chunks (lanes look at different lines: same offsets would share banks).
+template <int S>
+__device__ __forceinline__ bool kcf_smem_find(const uint8_t *line, uint32_t rot, uint64_t key, const KcfTableGeom &g, uint32_t &count)
+{
+    const uint4 *L = reinterpret_cast<const uint4 *>(line);
+    const uint32_t lo = (uint32_t)key;
+    constexpr int FC = S / 4; // 16-byte chunks made of low words only; S % 4 == 2 leaves one half chunk
+    int idx = -1;
+#pragma unroll
+    for (int jj = 0; jj < FC; ++jj) {
+        int j = jj + (int)rot; // rot < FC
+        if (j >= FC) j -= FC;
+        const uint4 v = L[j];
+        if (v.x == lo) idx = 4 * j;
+        if (v.y == lo) idx = 4 * j + 1;
+        if (v.z == lo) idx = 4 * j + 2;
+        if (v.w == lo) idx = 4 * j + 3;
+    }
+    if (S % 4) {
+        const uint2 v = reinterpret_cast<const uint2 *>(line)[2 * FC];
+        if (v.x == lo) idx = 4 * FC;
+        if (v.y == lo) idx = 4 * FC + 1;
+    }
+    if (idx < 0) return false;
+    if (reinterpret_cast<const uint32_t *>(line)[S + idx] != (uint32_t)(key >> 32)) return false;
+    count = kcf_slot_count(line, (uint32_t)idx, g);
+    return true;
+}
+
+template <int S>
+__global__ void __launch_bounds__(32) kcf_screen_kernel(KcfScreenParams p, KcfTableGeom g)
+{
+    extern __shared__ __align__(128) uint8_t kcf_smem_raw[];
+    KcfWarpSmem &W = *reinterpret_cast<KcfWarpSmem *>(kcf_smem_raw);
+
+    const uint32_t lane = threadIdx.x;
     const uint32_t k = g.k;
     const uint64_t km1 = (k == 32) ? 0xFFFFFFFFULL : ((1ULL << k) - 1ULL);
+    const uint32_t lines_sa = kcf_smem_u32(W.lines);
+    constexpr uint32_t ROTN = S / 4;
 
     for (;;) {
-        __syncthreads(); // shared buffers of the previous tile are no longer read
-        if (tid == 0) {
-            uint64_t t = p.tile_begin + atomicAdd(p.tile_counter, 1ULL);
-            s_tile = t;
-            if (t < p.tile_end) {
-                // window owning tile t: last w with tile_first[w] <= t
-                uint64_t lo = 0, hi = p.n_wins;
+        // ---- take a tile: KCF_TILE consecutive positions of one window ----
+        uint64_t tile = 0;
+        uint32_t w = 0;
+        if (lane == 0) {
+            tile = p.tile_begin + atomicAdd(p.tile_counter, 1ULL);
+            if (tile < p.tile_end) {
+                uint64_t lo = 0, hi = p.n_wins; // window owning the tile: last w with tile_first[w] <= tile
                 while (lo < hi) {
                     uint64_t mid = (lo + hi) >> 1;
-                    if (p.tile_first[mid] <= t) lo = mid + 1;
+                    if (p.tile_first[mid] <= tile) lo = mid + 1;
                     else hi = mid;
                 }
-                s_win = (uint32_t)(lo - 1);
+                w = (uint32_t)(lo - 1);
             }
         }
-        __syncthreads();
-        const uint64_t tile = s_tile;
+        tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= p.tile_end) break;
-        const uint32_t w = s_win;
+        w = __shfl_sync(0xffffffffu, w, 0);
         const kcf_window_t win = p.wins[w];
         const uint32_t wlen = p.win_len[w];
-        const int64_t o = (int64_t)(tile - p.tile_first[w]) * KCF_TILE; // window position of the tile's first k-mer end
+        const int64_t o_tile = (int64_t)(tile - p.tile_first[w]) * KCF_TILE; // window position of the tile's first k-mer end
 
-        // ---- stage bases [o - HALO, o + TILE) of the window: 8 positions per thread step ----
-        for (uint32_t u = tid; u < (KCF_TILE + KCF_HALO) / 8; u += KCF_THREADS) {
-            const int64_t pos0 = o - KCF_HALO + 8 * (int64_t)u;
-            uint32_t c16 = 0, v8 = 0;
-            if (pos0 + 8 > 0 && pos0 < (int64_t)wlen) {
-                if (win.n_segs == 1 && pos0 >= 0 && pos0 + 8 <= (int64_t)wlen) {
-                    // fixed / sliding window, fully inside: two funnel shifts over the packed words
-                    const kcf_segment_t sg = p.segs[win.first_seg];
-                    const KcfSeqDev sq = p.seqs[sg.seq_id];
-                    const uint32_t sp = (uint32_t)(sg.start0 + pos0);
-                    const uint32_t wi = sp >> 4, vi = sp >> 5;
-                    c16 = __funnelshift_r(__ldg(sq.codes + wi), __ldg(sq.codes + wi + 1), (sp & 15u) * 2u) & 0xFFFFu;
-                    v8 = __funnelshift_r(__ldg(sq.valid + vi), __ldg(sq.valid + vi + 1), sp & 31u) & 0xFFu;
-                } else {
-                    // window edges and multi-segment (gene / transcript) windows: base by base
-                    uint32_t s = 0;
-                    bool have = false;
-                    for (int j = 0; j < 8; ++j) {
-                        const int64_t pos = pos0 + j;
-                        if (pos < 0 || pos >= (int64_t)wlen) continue;
-                        if (!have) {
-                            uint32_t lo = 0, hi = win.n_segs; // last segment with seg_off <= pos
-                            while (lo < hi) {
-                                uint32_t mid = (lo + hi) >> 1;
-                                if (p.seg_off[win.first_seg + mid] <= (uint32_t)pos) lo = mid + 1;
-                                else hi = mid;
-                            }
-                            s = lo - 1;
-                            have = true;
-                        }
-                        while (s + 1 < win.n_segs && p.seg_off[win.first_seg + s + 1] <= (uint32_t)pos) ++s;
-                        const kcf_segment_t sg = p.segs[win.first_seg + s];
+        KcfGap acc; // summary of the steps done so far (meaningful in lane 0)
+        acc.n = acc.obs = acc.lead = acc.trail = acc.vin = acc.inner = acc.has = acc.starts = 0;
+        acc.sum = 0;
+        uint32_t carry_hash = 0; // order hash of position KCF_SUB + lane of the previous step = position lane of this one
+
+        for (uint32_t step = 0; step < KCF_TILE / KCF_SUB; ++step) {
+            const int64_t o = o_tile + (int64_t)step * KCF_SUB;
+            if (o >= (int64_t)wlen) break;
+            __syncwarp(); // the previous step's shared buffers are no longer read
+
+            // ---- stage bases [o - HALO, o + SUB): 8 positions per lane; the halo is carried over between steps ----
+            if (step > 0) {
+                uint32_t c16 = 0, v8 = 0;
+                if (lane < KCF_HALO / 8) {
+                    c16 = reinterpret_cast<uint16_t *>(W.codes)[KCF_SUB / 8 + lane];
+                    v8 = reinterpret_cast<uint8_t *>(W.valid)[KCF_SUB / 8 + lane];
+                }
+                __syncwarp();
+                if (lane < KCF_HALO / 8) {
+                    reinterpret_cast<uint16_t *>(W.codes)[lane] = (uint16_t)c16;
+                    reinterpret_cast<uint8_t *>(W.valid)[lane] = (uint8_t)v8;
+                }
+            }
+            for (int u = (step > 0 ? KCF_HALO / 8 : 0) + (int)lane; u < (KCF_SUB + KCF_HALO) / 8; u += 32) {
+                const int64_t pos0 = o - KCF_HALO + 8 * (int64_t)u;
+                uint32_t c16 = 0, v8 = 0;
+                if (pos0 + 8 > 0 && pos0 < (int64_t)wlen) {
+                    if (win.n_segs == 1 && pos0 >= 0 && pos0 + 8 <= (int64_t)wlen) {
+                        // fixed / sliding window, fully inside: two funnel shifts over the packed words
+                        const kcf_segment_t sg = p.segs[win.first_seg];
                         const KcfSeqDev sq = p.seqs[sg.seq_id];
-                        const uint32_t sp = (uint32_t)sg.start0 + ((uint32_t)pos - p.seg_off[win.first_seg + s]);
-                        const uint32_t c = (__ldg(sq.codes + (sp >> 4)) >> ((sp & 15u) * 2u)) & 3u;
-                        const uint32_t v = (__ldg(sq.valid + (sp >> 5)) >> (sp & 31u)) & 1u;
-                        c16 |= c << (2 * j);
-                        v8 |= v << j;
+                        const uint32_t sp = (uint32_t)(sg.start0 + pos0);
+                        const uint32_t wi = sp >> 4, vi = sp >> 5;
+                        c16 = __funnelshift_r(__ldg(sq.codes + wi), __ldg(sq.codes + wi + 1), (sp & 15u) * 2u) & 0xFFFFu;
+                        v8 = __funnelshift_r(__ldg(sq.valid + vi), __ldg(sq.valid + vi + 1), sp & 31u) & 0xFFu;
+                    } else {
+                        // window edges and multi-segment (gene / transcript) windows: base by base
+                        uint32_t s = 0;
+                        bool have = false;
+                        for (int j = 0; j < 8; ++j) {
+                            const int64_t pos = pos0 + j;
+                            if (pos < 0 || pos >= (int64_t)wlen) continue;
+                            if (!have) {
+                                uint32_t lo = 0, hi = win.n_segs; // last segment with seg_off <= pos
+                                while (lo < hi) {
+                                    uint32_t mid = (lo + hi) >> 1;
+                                    if (p.seg_off[win.first_seg + mid] <= (uint32_t)pos) lo = mid + 1;
+                                    else hi = mid;
+                                }
+                                s = lo - 1;
+                                have = true;
+                            }
+                            while (s + 1 < win.n_segs && p.seg_off[win.first_seg + s + 1] <= (uint32_t)pos) ++s;
+                            const kcf_segment_t sg = p.segs[win.first_seg + s];
+                            const KcfSeqDev sq = p.seqs[sg.seq_id];
+                            const uint32_t sp = (uint32_t)sg.start0 + ((uint32_t)pos - p.seg_off[win.first_seg + s]);
+                            const uint32_t c = (__ldg(sq.codes + (sp >> 4)) >> ((sp & 15u) * 2u)) & 3u;
+                            const uint32_t v = (__ldg(sq.valid + (sp >> 5)) >> (sp & 31u)) & 1u;
+                            c16 |= c << (2 * j);
+                            v8 |= v << j;
+                        }
                     }
                 }
+                reinterpret_cast<uint16_t *>(W.codes)[u] = (uint16_t)c16;
+                reinterpret_cast<uint8_t *>(W.valid)[u] = (uint8_t)v8;
             }
-            reinterpret_cast<uint16_t *>(s_codes)[u] = (uint16_t)c16;
-            reinterpret_cast<uint8_t *>(s_valid)[u] = (uint8_t)v8;
-        }
-        __syncthreads();
+            __syncwarp();
 
-        // ---- this thread's 40-base buffer: local bases [8 tid, 8 tid + 40); k-mer i ends at buffer base 32 + i ----
-        uint64_t blo, bhi, V;
-        {
-            const uint32_t wq = tid >> 1;
-            const uint32_t w0 = s_codes[wq], w1 = s_codes[wq + 1], w2 = s_codes[wq + 2];
-            const uint64_t t01 = ((uint64_t)w1 << 32) | w0;
-            if (tid & 1) {
-                blo = (t01 >> 16) | ((uint64_t)w2 << 48);
-                bhi = w2 >> 16;
-            } else {
-                blo = t01;
-                bhi = w2 & 0xFFFFu;
-            }
-            const uint32_t vq = tid >> 2;
-            const uint64_t v01 = ((uint64_t)s_valid[vq + 1] << 32) | s_valid[vq];
-            V = v01 >> (8 * (tid & 3));
-        }
-        const uint32_t sh0 = 2 * (33 - k); // 2..60
-        uint64_t X = ((blo >> sh0) | (bhi << (64 - sh0))) & g.kmask; // k-mer 0, base j in bits 2j
-        uint64_t fw = kcf_pair_reverse(X, g.kshift);                   // first base most significant (Kmer.java:232-252)
-        bool ok_prev = ((V >> (32 - k)) & km1) == km1;                 // k-mer ending one position before this thread's first
-
-        uint64_t key[KCF_PER_THREAD], hh[KCF_PER_THREAD];
-        uint64_t s0[KCF_PER_THREAD], s1[KCF_PER_THREAD], s2[KCF_PER_THREAD], s3[KCF_PER_THREAD];
-        uint32_t okmask = 0, startmask = 0;
+            // ---- order hash of the m-mer ending at every staged position (shared by the w k-mers that contain it) ----
+            if (step > 0) W.hash[lane + (lane >> 3)] = carry_hash;
+            for (int u = (step > 0 ? KCF_HALO / 8 : 0) + (int)lane; u < (KCF_SUB + KCF_HALO) / 8; u += 32) {
+                const int q0 = 8 * u;
+                const int b0 = q0 - (int)g.m + 1; // first base of the m-mer ending at q0
+                const int b0c = b0 > 0 ? b0 : 0;  // positions whose m-mer starts before the halo are never used
+                const uint32_t wi = (uint32_t)b0c >> 4, sh = ((uint32_t)b0c & 15u) * 2u;
+                const uint64_t lo = ((uint64_t)W.codes[wi + 1] << 32) | W.codes[wi];
+                const uint64_t E = sh ? ((lo >> sh) | ((uint64_t)W.codes[wi + 2] << (64 - sh))) : lo; // 32 bases from b0c
+                const uint64_t R = kcf_pair_reverse64(~E);
 #pragma unroll
-        for (int i = 0; i < KCF_PER_THREAD; ++i) {
-            if (i > 0) {
-                const uint64_t c = (bhi >> (2 * i)) & 3ULL;
-                X = (X >> 2) | (c << (2 * (k - 1)));
-                fw = ((fw << 2) | c) & g.kmask;
-            }
-            const bool ok = ((V >> (33 + i - k)) & km1) == km1; // Fasta.java:99-104: any non-ACGT restarts the stretch
-            const uint64_t rc = (~X) & g.kmask;                 // reverse complement value (Kmer.java:300-338)
-            // canonical = unsigned-smaller word, tie keeps forward (Kmer.java:72-79, 406-414)
-            const uint64_t kk = (g.both_strands && rc < fw) ? rc : fw;
-            key[i] = kk;
-            hh[i] = kcf_mix(kk, g);
-            okmask |= (uint32_t)ok << i;
-            startmask |= (uint32_t)(ok && !ok_prev) << i;
-            ok_prev = ok;
-            s0[i] = s1[i] = s2[i] = s3[i] = 0;
-            if (ok) kcf_ld_bucket(p.table + 4 * kcf_home_bucket(hh[i], g), s0[i], s1[i], s2[i], s3[i]);
-        }
-
-        // ---- fold the 8 results into this thread's gap summary (GetVariants.java:220-245) ----
-        KcfGap a;
-        a.n = a.obs = a.lead = a.trail = a.vin = a.inner = a.has = 0;
-        a.starts = __popc(startmask);
-        a.sum = 0;
-        uint32_t gap = 0;
-#pragma unroll
-        for (int i = 0; i < KCF_PER_THREAD; ++i) {
-            const bool ok = (okmask >> i) & 1u;
-            uint32_t cnt = 0;
-            if (ok) {
-                const uint64_t tag = ((uint64_t)8u << g.rbits) | (hh[i] & g.rmask);
-                bool full;
-                if (!kcf_match4(s0[i], s1[i], s2[i], s3[i], tag, g, cnt, full)) {
-                    cnt = 0;
-                    if (full) cnt = kcf_lookup_tail(p.table, p.stash, g, key[i], hh[i], kcf_home_bucket(hh[i], g));
+                for (int i = 0; i < 8; ++i) {
+                    const int j = i + (b0 - b0c);
+                    W.hash[9 * u + i] = kcf_mmer_order(E, R, (uint32_t)(j > 0 ? j : 0), g);
                 }
-                a.n += 1;
-                if ((int32_t)cnt >= p.min_count) { // Java int compare (GetVariants.java:224)
-                    a.obs += 1;
-                    a.sum += cnt;
-                    if (!a.has) {
-                        a.lead = gap;
-                        a.has = 1;
-                    } else if (gap > 0) {
-                        a.vin += 1;
-                        a.inner += kcf_gap_distance(gap, k);
-                    }
-                    gap = 0;
+            }
+
+            // ---- this lane's 40-base buffer: local bases [8 lane, 8 lane + 40); k-mer i ends at buffer base 32 + i ----
+            uint64_t blo, bhi, V;
+            {
+                const uint32_t wq = lane >> 1;
+                const uint32_t w0 = W.codes[wq], w1 = W.codes[wq + 1], w2 = W.codes[wq + 2];
+                const uint64_t t01 = ((uint64_t)w1 << 32) | w0;
+                if (lane & 1) {
+                    blo = (t01 >> 16) | ((uint64_t)w2 << 48);
+                    bhi = w2 >> 16;
                 } else {
-                    gap += 1;
+                    blo = t01;
+                    bhi = w2 & 0xFFFFu;
+                }
+                const uint32_t vq = lane >> 2;
+                const uint64_t v01 = ((uint64_t)W.valid[vq + 1] << 32) | W.valid[vq];
+                V = v01 >> (8 * (lane & 3));
+            }
+            const uint32_t sh0 = 2 * (33 - k); // 2..60
+            uint64_t X = ((blo >> sh0) | (bhi << (64 - sh0))) & g.kmask; // k-mer 0, base j in bits 2j
+            uint64_t fw = kcf_pair_reverse(X, g.kshift);                   // first base most significant (Kmer.java:232-252)
+            bool ok_prev = ((V >> (32 - k)) & km1) == km1;                 // k-mer ending one position before this lane's first
+
+            uint64_t key[KCF_PER_THREAD];
+            uint32_t okmask = 0, startmask = 0;
+#pragma unroll
+            for (int i = 0; i < KCF_PER_THREAD; ++i) {
+                if (i > 0) {
+                    const uint64_t c = (bhi >> (2 * i)) & 3ULL;
+                    X = (X >> 2) | (c << (2 * (k - 1)));
+                    fw = ((fw << 2) | c) & g.kmask;
+                }
+                const bool ok = ((V >> (33 + i - k)) & km1) == km1; // Fasta.java:99-104: any non-ACGT restarts the stretch
+                const uint64_t rc = (~X) & g.kmask;                 // reverse complement value (Kmer.java:300-338)
+                // canonical = unsigned-smaller word, tie keeps forward (Kmer.java:72-79, 406-414)
+                key[i] = (g.both_strands && rc < fw) ? rc : fw;
+                okmask |= (uint32_t)ok << i;
+                startmask |= (uint32_t)(ok && !ok_prev) << i;
+                ok_prev = ok;
+            }
+            __syncwarp(); // hashes complete
+
+            // ---- minimizer of each k-mer = sliding minimum over its w m-mer hashes -> home line ----
+            uint32_t line[KCF_PER_THREAD];
+            {
+                const uint32_t hb = KCF_HALO + 8 * lane - (g.w - 1); // first m-mer end position of k-mer 0
+                uint32_t mu[KCF_PER_THREAD];
+#define HASH_AT(j) W.hash[(hb + (j)) + ((hb + (j)) >> 3)]
+                if (g.w >= 8) {
+                    uint32_t core = HASH_AT(7); // positions shared by all 8 windows
+                    for (uint32_t j = 8; j < g.w; ++j) core = min(core, HASH_AT(j));
+                    uint32_t l = 0xFFFFFFFFu;
+                    mu[7] = core;
+#pragma unroll
+                    for (int i = 6; i >= 0; --i) {
+                        l = min(l, HASH_AT(i));
+                        mu[i] = min(core, l);
+                    }
+                    uint32_t r = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int i = 1; i <= 7; ++i) {
+                        r = min(r, HASH_AT(g.w + i - 1));
+                        mu[i] = min(mu[i], r);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < KCF_PER_THREAD; ++i) {
+                        uint32_t v = HASH_AT(i);
+                        for (uint32_t j = 1; j < g.w; ++j) v = min(v, HASH_AT(i + j));
+                        mu[i] = v;
+                    }
+                }
+#undef HASH_AT
+                carry_hash = W.hash[(KCF_SUB + lane) + ((KCF_SUB + lane) >> 3)];
+#pragma unroll
+                for (int i = 0; i < KCF_PER_THREAD; ++i) line[i] = kcf_home_line(mu[i], g);
+            }
+#pragma unroll
+            for (int i = 0; i < KCF_PER_THREAD; i += 2)
+                *reinterpret_cast<ulonglong2 *>(&W.key[8 * lane + i]) = make_ulonglong2(key[i], key[i + 1]);
+
+            // ---- runs of consecutive valid k-mers with the same home line: one fetch per run ----
+            uint32_t headmask = 0;
+            {
+                uint32_t prev = __shfl_up_sync(0xffffffffu, (okmask >> 7) & 1u ? line[7] : 0xFFFFFFFFu, 1);
+                if (lane == 0) prev = 0xFFFFFFFFu;
+#pragma unroll
+                for (int i = 0; i < KCF_PER_THREAD; ++i) {
+                    const bool ok = (okmask >> i) & 1u;
+                    headmask |= (uint32_t)(ok && line[i] != prev) << i;
+                    prev = ok ? line[i] : 0xFFFFFFFFu;
                 }
             }
-            if (p.counts_out) {
-                const uint64_t pos = (tile - p.counts_tile0) * KCF_TILE + 8 * tid + i;
-                p.counts_out[pos] = ok ? (int32_t)cnt : -1;
-            }
-        }
-        a.trail = gap;
-        if (!a.has) a.lead = a.n;
-
-        // ---- ordered reduction: 32 lanes by shuffle, 8 warps through shared memory ----
+            uint32_t hbase, n_heads; // heads before this lane, heads in the step
+            {
+                const uint32_t nh = __popc(headmask);
+                uint32_t incl = nh;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            KcfGap b = kcf_gap_shfl_down(a, d);
-            if ((tid & 31) + d < 32) a = kcf_gap_combine(a, b, k);
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= (uint32_t)d) incl += t;
+                }
+                hbase = incl - nh;
+                n_heads = __shfl_sync(0xffffffffu, incl, 31);
+            }
+
+            // ---- fetch and search, KCF_HCW runs at a time ----
+            uint32_t cnt[KCF_PER_THREAD];
+#pragma unroll
+            for (int i = 0; i < KCF_PER_THREAD; ++i) cnt[i] = 0;
+            for (uint32_t c0 = 0; c0 < n_heads; c0 += KCF_HCW) {
+                const uint32_t c1 = min(c0 + KCF_HCW, n_heads);
+                __syncwarp(); // previous chunk's lines are no longer read
+#pragma unroll
+                for (int i = 0; i < KCF_PER_THREAD; ++i) {
+                    const uint32_t slot = hbase + __popc(headmask & ((1u << i) - 1u));
+                    if (((headmask >> i) & 1u) && slot >= c0 && slot < c1) W.fetch[slot - c0] = line[i];
+                }
+                for (uint32_t j = lane; j < KCF_HCW; j += 32) W.need[j] = 0;
+                __syncwarp();
+                kcf_fetch_lines(lines_sa, W.fetch, c1 - c0, p.table, lane);
+                kcf_fetch_wait();
+
+                // home lines
+                uint32_t pend = 0;
+#pragma unroll
+                for (int i = 0; i < KCF_PER_THREAD; ++i) {
+                    const uint32_t slot = hbase + __popc(headmask & ((2u << i) - 1u)) - 1u; // run this k-mer belongs to
+                    if (!((okmask >> i) & 1u) || slot < c0 || slot >= c1) continue;
+                    const uint32_t hs = slot - c0;
+                    const uint8_t *L = W.lines + hs * KCF_LINE_BYTES;
+                    const bool inl = KCF_KEY_IN_LINES(key[i]);
+                    uint32_t c;
+                    if (inl && kcf_smem_find<S>(L, hs % ROTN, key[i], g, c)) {
+                        cnt[i] = c;
+                        continue;
+                    }
+                    const uint32_t mask = kcf_mask_from_word31(reinterpret_cast<const uint32_t *>(L)[31]);
+                    if (inl && (mask & 0x7FFEu)) pend |= 1u << i;
+                    else if ((mask >> KCF_STASH_BIT) & 1u) cnt[i] = kcf_stash_find(p.stash, g, key[i]);
+                }
+
+                // continuation lines.  Per round: the first unresolved k-mer of a run claims staging slots for the lines
+                // its home mask names; every unresolved k-mer of a served run queues one (k-mer, line) pair per line;
+                // the lines are fetched; the pairs are searched one per lane, densely.
+                for (uint32_t round = 1; __any_sync(0xffffffffu, pend != 0); ++round) {
+                    if (lane == 0) {
+                        W.ext_count = 0;
+                        W.q_count = 0;
+                        W.ext_limit = KCF_ECW;
+                        W.q_limit = KCF_QC;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < KCF_PER_THREAD; ++i) {
+                        if (!((pend >> i) & 1u)) continue;
+                        const uint32_t hs = hbase + __popc(headmask & ((2u << i) - 1u)) - 1u - c0;
+                        if (atomicExch(&W.need[hs], round) == round) continue; // claimed this round already
+                        uint32_t m2 = kcf_mask_from_word31(reinterpret_cast<const uint32_t *>(W.lines + hs * KCF_LINE_BYTES)[31]) & 0x7FFEu;
+                        const uint32_t n = __popc(m2);
+                        uint32_t b = atomicAdd(&W.ext_count, n);
+                        if (b + n <= KCF_ECW) {
+                            W.extbase[hs] = b;
+                            while (m2) {
+                                const uint32_t d = __ffs(m2) - 1;
+                                m2 &= m2 - 1;
+                                W.fetch[KCF_HCW + b++] = kcf_line_wrap(line[i], d, g);
+                            }
+                        } else {
+                            W.extbase[hs] = 0xFFFFFFFFu;
+                            atomicMin(&W.ext_limit, b);
+                        }
+                    }
+                    __syncwarp();
+                    kcf_fetch_lines(lines_sa + KCF_HCW * KCF_LINE_BYTES, W.fetch + KCF_HCW, min(W.ext_count, W.ext_limit), p.table, lane);
+                    uint32_t served = 0;
+#pragma unroll
+                    for (int i = 0; i < KCF_PER_THREAD; ++i) {
+                        if (!((pend >> i) & 1u)) continue;
+                        const uint32_t hs = hbase + __popc(headmask & ((2u << i) - 1u)) - 1u - c0;
+                        const uint32_t b = W.extbase[hs];
+                        if (b == 0xFFFFFFFFu) continue; // next round
+                        const uint32_t mask = kcf_mask_from_word31(reinterpret_cast<const uint32_t *>(W.lines + hs * KCF_LINE_BYTES)[31]);
+                        const uint32_t n = __popc(mask & 0x7FFEu);
+                        const uint32_t qb = atomicAdd(&W.q_count, n);
+                        if (qb + n > KCF_QC) { // queue full: next round
+                            atomicMin(&W.q_limit, qb);
+                            continue;
+                        }
+                        const uint32_t pos = 8 * lane + i;
+                        for (uint32_t j = 0; j < n; ++j) W.queue[qb + j] = (pos << 16) | (b + j);
+                        W.cnt[pos] = (mask >> KCF_STASH_BIT) & 1u ? kcf_stash_find(p.stash, g, key[i]) : 0u;
+                        served |= 1u << i;
+                    }
+                    kcf_fetch_wait();
+                    {
+                        const uint32_t nq = min(W.q_count, W.q_limit); // every entry below was written this round
+                        for (uint32_t q = lane; q < nq; q += 32) {
+                            const uint32_t e = W.queue[q];
+                            const uint32_t pos = e >> 16, es = e & 0xFFFFu;
+                            uint32_t c;
+                            if (kcf_smem_find<S>(W.lines + (KCF_HCW + es) * KCF_LINE_BYTES, es % ROTN, W.key[pos], g, c)) W.cnt[pos] = c;
+                        }
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < KCF_PER_THREAD; ++i)
+                        if ((served >> i) & 1u) cnt[i] = W.cnt[8 * lane + i];
+                    pend &= ~served;
+                }
+            }
+
+            // ---- fold the 8 results into this lane's gap summary (GetVariants.java:220-245) ----
+            KcfGap a;
+            a.n = a.obs = a.lead = a.trail = a.vin = a.inner = a.has = 0;
+            a.starts = __popc(startmask);
+            a.sum = 0;
+            uint32_t gap = 0;
+#pragma unroll
+            for (int i = 0; i < KCF_PER_THREAD; ++i) {
+                const bool ok = (okmask >> i) & 1u;
+                if (ok) {
+                    a.n += 1;
+                    if ((int32_t)cnt[i] >= p.min_count) { // Java int compare (GetVariants.java:224)
+                        a.obs += 1;
+                        a.sum += cnt[i];
+                        if (!a.has) {
+                            a.lead = gap;
+                            a.has = 1;
+                        } else if (gap > 0) {
+                            a.vin += 1;
+                            a.inner += kcf_gap_distance(gap, k);
+                        }
+                        gap = 0;
+                    } else {
+                        gap += 1;
+                    }
+                }
+                if (p.counts_out) {
+                    const uint64_t pos = (tile - p.counts_tile0) * KCF_TILE + step * KCF_SUB + 8 * lane + i;
+                    p.counts_out[pos] = ok ? (int32_t)cnt[i] : -1;
+                }
+            }
+            a.trail = gap;
+            if (!a.has) a.lead = a.n;
+
+            // ---- ordered reduction over the 32 lanes, then onto the tile's running summary ----
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                KcfGap b = kcf_gap_shfl_down(a, d);
+                if (lane + d < 32) a = kcf_gap_combine(a, b, k);
+            }
+            acc = kcf_gap_combine(acc, a, k);
         }
-        if ((tid & 31) == 0) s_warp[tid >> 5] = a;
-        __syncthreads();
-        if (tid == 0) {
-            KcfGap r = s_warp[0];
-            for (int i = 1; i < KCF_THREADS / 32; ++i) r = kcf_gap_combine(r, s_warp[i], k);
-            p.tile_sum[tile] = r;
-        }
+        if (lane == 0) p.tile_sum[tile] = acc;
     }
 }
 
@@ -316,6 +578,12 @@ __global__ void kcf_finalize_kernel(const KcfGap *__restrict__ tile_sum, const u
     }
     o.score = score;
     out[w] = o;
+}
+
+// one 32-byte sector with a single 256-bit load that bypasses L1 allocation
+__device__ __forceinline__ void kcf_ld_bucket(const uint64_t *p, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d)
+{
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
 }
 
 // ---- random 32-byte sector gather microbenchmark (the random-access roofline of SURVEY §8(d)) ----
@@ -526,11 +794,15 @@ static int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t m
     p.min_count = min_count;
     p.counts_out = d_counts;
     p.counts_tile0 = tile_begin;
+    const size_t smem = sizeof(KcfWarpSmem);
+    void (*kern)(KcfScreenParams, KcfTableGeom) =
+        db->geom.S == 14 ? kcf_screen_kernel<14> : (db->geom.S == 12 ? kcf_screen_kernel<12> : kcf_screen_kernel<10>);
+    KCF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    KCF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kcf_screen_kernel, KCF_THREADS, 0));
+    KCF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
     const uint64_t n = tile_end - tile_begin;
     const unsigned grid = (unsigned)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * std::max(per_sm, 1));
-    if (grid) kcf_screen_kernel<<<grid, KCF_THREADS, 0, ctx->stream>>>(p, db->geom);
+    if (grid) kern<<<grid, 32, smem, ctx->stream>>>(p, db->geom);
     KCF_CUDA(ctx, cudaGetLastError());
     return KCF_OK;
 }

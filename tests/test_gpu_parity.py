@@ -162,6 +162,29 @@ def test_high_load_factor_uses_displacement_and_stash(ctx, sc_main):
     db.close()
 
 
+@pytest.mark.parametrize("m,lf", [(16, 0.5), (12, 0.3), (4, 0.5), (1, 0.9), (10, 0.9)])
+def test_minimizer_length_and_load_factor_never_change_results(ctx, sc_main, m, lf):
+    """the home-line function (minimizer length) and the load factor are layout knobs only.  m = 4 / 1 pile thousands
+    of keys onto few minimizers: displaced lines, continuation fetches and the stash all get exercised."""
+    sc = sc_main
+    sc.add_to(ctx)
+    ctx.set_minimizer_length(m)
+    ctx.set_load_factor(lf)
+    try:
+        db = KMC(ctx, pre=sc.kmc.pre, suf=sc.kmc.suf)
+    finally:
+        ctx.set_minimizer_length(0)
+        ctx.set_load_factor(0.5)
+    assert db.info.resident_kmers == sc.kmc.total
+    if m <= 4:
+        assert db.info.stash_kmers > 0
+    wins, segs, *_ = fixed_windows(sc.seq_lens, 20_000, 0, 31)
+    rc, want = _oracle_screen(sc, wins, segs)
+    got = ctx.screen(db, wins, segs)
+    assert_results_equal(got, want)
+    db.close()
+
+
 def test_unreachable_records_are_ignored_like_the_reference(ctx):
     """records sitting in a bin their signature does not map to can never be returned by KMC.getCount."""
     sc = Scenario(seq_lens=(20_000,), seed=9, n_bins=16)
