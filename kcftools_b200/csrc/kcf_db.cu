@@ -375,13 +375,13 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
         DB_CUDA(cudaHostAlloc(&h_stage[j], chunk_bytes, cudaHostAllocDefault));
         DB_CUDA(cudaEventCreateWithFlags(&ev[j], cudaEventDisableTiming));
     }
-    for (int pass = 0; pass < 2; ++pass) {
-        if (pass == 1) {
+    for (int pass = 0; pass < 4; ++pass) {
+        if (pass > 0) {
             // the overflow list was too short (a table whose minimizers collide massively): the device counted
             // how long it has to be; reset the table and stream the records once more
             cudaFree(d_ovf);
             d_ovf = nullptr;
-            ovf_cap = counters[2];
+            ovf_cap = counters[2] + counters[2] / 8 + 4096; // placement races make the count vary a little between passes
             DB_CUDA(cudaMalloc(&d_ovf, ovf_cap * sizeof(KcfStashEntry)));
             DB_CUDA(cudaMemsetAsync(db->table, 0xFF, nb * KCF_LINE_BYTES, ctx->stream));
             DB_CUDA(cudaMemsetAsync(d_counters, 0, 3 * sizeof(unsigned long long), ctx->stream));

@@ -156,12 +156,7 @@ struct kcf_plan {
 };
 
 #define KCF_TILE 2048          // positions per tile = the unit of work one warp takes
-#define KCF_SUB 256            // positions per step of a warp (32 lanes x 8)
-#define KCF_PER_THREAD 8
-#define KCF_HALO 32            // bases staged before a step (>= k-1, word aligned)
-#define KCF_HCW 40             // home lines staged per chunk of runs
-#define KCF_ECW 56             // continuation lines staged per round
-#define KCF_QC 512             // (k-mer, continuation line) pairs searched per round
+#define KCF_HALO 32            // bases staged before a chunk (>= k-1, word aligned)
 
 // indices into kcf_ctx::d_flags
 enum { FLAG_LUT_BAD = 0, FLAG_ORDER_BAD = 1, FLAG_SCORE_USED = 2, FLAG_COUNT = 8 };

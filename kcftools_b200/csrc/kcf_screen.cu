@@ -90,89 +90,161 @@ __device__ __forceinline__ KcfGap kcf_gap_shfl_down(const KcfGap &a, int delta)
     return r;
 }
 
-#define S_CODE_WORDS ((KCF_SUB + KCF_HALO) / 16 + 4)
-#define S_VALID_WORDS ((KCF_SUB + KCF_HALO) / 32 + 2)
-#define S_HASH_WORDS ((KCF_SUB + KCF_HALO) + (KCF_SUB + KCF_HALO) / 8) // one pad word per 8: bank-conflict-free windows
+// ------------------------------------------------------------------------------------------------------------
+// K3/K4.  One warp = one CTA takes a tile (KCF_TILE consecutive positions of one window) and walks it in chunks of
+// KCF_CHUNK positions.  Inside a chunk LANES own consecutive positions (position = 32 j + lane in iteration j), so
+// the ~(w+1)/2 neighbouring k-mers that share a minimizer — hence a 128-byte home line of the table — sit in the
+// same load instruction and the L1 coalescer turns their probes into ONE request for that line: the de-duplication
+// that makes the table's locality pay is done by the memory pipeline, not by code.  Nothing synchronises wider
+// than a warp; the warps of an SM drift apart and hide each other's latencies.
+//
+//   stage    2-bit bases + validity bits of the chunk (+ 32-base halo) into shared memory
+//   hash     order hash of the m-mer ending at every position, then log2 doubling passes of a sliding minimum
+//   probe    per position: canonical k-mer, minimizer -> home line, two 32-byte loads (the 14 low key words),
+//            confirm on the high word, read the count; k-mers whose home mask names other lines go to a queue
+//   queue    searched one item per lane, densely (continuation lines are rare per k-mer but not per warp)
+//   fold     hit / valid bitmaps (one ballot per 32 positions) -> gap summary by bit tricks -> one shuffle reduction
+// ------------------------------------------------------------------------------------------------------------
+#define KCF_CHUNK 1024
+#define S_CODE_WORDS ((KCF_CHUNK + KCF_HALO) / 16 + 4)
+#define S_VALID_WORDS ((KCF_CHUNK + KCF_HALO) / 32 + 2)
+#define S_HASH_WORDS ((KCF_CHUNK + KCF_HALO) + (KCF_CHUNK + KCF_HALO) / 8 + 8) // one pad word per 8 (the writers stride by 8)
+#define KCF_QCAP 256
 
-// Shared memory of one warp (one warp = one CTA: nothing in this kernel synchronises wider than a warp, so the
-// warps of an SM drift apart and one warp's table fetches overlap the others' arithmetic).  `lines` is the staging
-// area the table lines land in: the first KCF_HCW slots take the home lines of a chunk of runs, the last KCF_ECW
-// the continuation lines their masks name.
-struct KcfWarpSmem {
-    uint8_t lines[(KCF_HCW + KCF_ECW) * KCF_LINE_BYTES];
-    unsigned long long key[KCF_SUB]; // canonical k-mer of every position of the step (read back by the pair queue)
-    uint32_t hash[S_HASH_WORDS];
-    uint32_t cnt[KCF_SUB];           // counts found through the pair queue
-    uint32_t queue[KCF_QC];          // (position << 16 | continuation slot)
-    uint32_t fetch[KCF_HCW + KCF_ECW]; // table line staged in each slot
-    uint32_t need[KCF_HCW];          // run -> round in which its continuation lines were claimed
-    uint32_t extbase[KCF_HCW];       // run -> first continuation slot (0xFFFFFFFF: not this round)
-    uint32_t codes[S_CODE_WORDS];
-    uint32_t valid[S_VALID_WORDS];
-    uint32_t ext_count, q_count;
-    uint32_t ext_limit, q_limit; // first staging slot / queue entry of a claim that did not fit this round
+struct KcfQueueItem {
+    unsigned long long key;
+    uint32_t home;  // home line
+    uint32_t info;  // chunk position << 16 | home mask (bit 0 cleared)
 };
 
-__device__ __forceinline__ uint32_t kcf_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+struct KcfWarpSmem {
+    KcfQueueItem queue[KCF_QCAP];
+    uint32_t hash[S_HASH_WORDS];
+    uint32_t codes[S_CODE_WORDS];
+    uint32_t valid[S_VALID_WORDS];
+    uint32_t hit[KCF_CHUNK / 32];   // bit = k-mer observed (count >= min_count)
+    uint32_t okw[KCF_CHUNK / 32];   // bit = a k-mer ends at this position
+    uint32_t start[KCF_CHUNK / 32]; // bit = k-mer opens a valid stretch (EFFLEN)
+};
 
-// Cooperative fetch of n table lines into consecutive staging slots: 8 lanes move one 128-byte line (one coalesced
-// request per line) with 16-byte asynchronous copies that bypass the register file.
-__device__ __forceinline__ void kcf_fetch_lines(uint32_t dst_sa, const uint32_t *ids, uint32_t n, const uint8_t *table, uint32_t lane)
+__device__ __forceinline__ uint32_t kcf_hidx(uint32_t q) { return q + (q >> 3); }
+
+// the S low key words of a table line: its first two 32-byte sectors (L1-allocating loads: the high word, the count
+// and the mask of the same line are read right after)
+__device__ __forceinline__ void kcf_ld_lo(const uint8_t *line, uint4 &a, uint4 &b, uint4 &c, uint4 &d)
 {
-    for (uint32_t q = lane; q < n * 8; q += 32) {
-        const uint8_t *src = table + (uint64_t)ids[q >> 3] * KCF_LINE_BYTES + (q & 7u) * 16u;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_sa + q * 16u), "l"(src) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void kcf_fetch_wait()
-{
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(line));
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(line + 16));
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w) : "l"(line + 32));
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w) : "l"(line + 48));
 }
 
-// Search a line staged in shared memory: S key low words, then S high words, then the counts.  Low words of the live
-// keys of a line are distinct, so there is one candidate at most; it is confirmed on the high word.  `rot` staggers the
-// order in which lanes walk the 16-byte chunks (lanes look at different lines: same offsets would share banks).
+// slot of the line whose low word equals lo (live low words of a line are distinct), -1 if none
 template <int S>
-__device__ __forceinline__ bool kcf_smem_find(const uint8_t *line, uint32_t rot, uint64_t key, const KcfTableGeom &g, uint32_t &count)
+__device__ __forceinline__ int kcf_match_lo(const uint4 &a, const uint4 &b, const uint4 &c, const uint4 &d, uint32_t lo)
 {
-    const uint4 *L = reinterpret_cast<const uint4 *>(line);
-    const uint32_t lo = (uint32_t)key;
-    constexpr int FC = S / 4; // 16-byte chunks made of low words only; S % 4 == 2 leaves one half chunk
     int idx = -1;
-#pragma unroll
-    for (int jj = 0; jj < FC; ++jj) {
-        int j = jj + (int)rot; // rot < FC
-        if (j >= FC) j -= FC;
-        const uint4 v = L[j];
-        if (v.x == lo) idx = 4 * j;
-        if (v.y == lo) idx = 4 * j + 1;
-        if (v.z == lo) idx = 4 * j + 2;
-        if (v.w == lo) idx = 4 * j + 3;
-    }
-    if (S % 4) {
-        const uint2 v = reinterpret_cast<const uint2 *>(line)[2 * FC];
-        if (v.x == lo) idx = 4 * FC;
-        if (v.y == lo) idx = 4 * FC + 1;
-    }
+    if (a.x == lo) idx = 0;
+    if (a.y == lo) idx = 1;
+    if (a.z == lo) idx = 2;
+    if (a.w == lo) idx = 3;
+    if (b.x == lo) idx = 4;
+    if (b.y == lo) idx = 5;
+    if (b.z == lo) idx = 6;
+    if (b.w == lo) idx = 7;
+    if (c.x == lo) idx = 8;
+    if (c.y == lo) idx = 9;
+    if (S > 10 && c.z == lo) idx = 10;
+    if (S > 11 && c.w == lo) idx = 11;
+    if (S > 12 && d.x == lo) idx = 12;
+    if (S > 13 && d.y == lo) idx = 13;
+    return idx;
+}
+
+// probe one table line for `key`: true + count when it is there
+template <int S>
+__device__ __forceinline__ bool kcf_probe_line(const uint8_t *line, uint64_t key, const KcfTableGeom &g, uint32_t &count)
+{
+    uint4 a, b, c, d;
+    kcf_ld_lo(line, a, b, c, d);
+    const int idx = kcf_match_lo<S>(a, b, c, d, (uint32_t)key);
     if (idx < 0) return false;
-    if (reinterpret_cast<const uint32_t *>(line)[S + idx] != (uint32_t)(key >> 32)) return false;
+    if (__ldg(reinterpret_cast<const uint32_t *>(line) + S + idx) != (uint32_t)(key >> 32)) return false;
     count = kcf_slot_count(line, (uint32_t)idx, g);
     return true;
 }
 
+// gap summary of 32 consecutive positions from their bitmaps (bit i = position i): `vw` marks the positions where a
+// k-mer ends, `hw` (a subset) the observed ones.  Positions without a k-mer are transparent: a miss run continues
+// across them (GetVariants.java:217-245 runs over the compacted k-mer list).
+__device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, uint32_t sw, uint64_t sum, uint32_t k)
+{
+    KcfGap a;
+    a.n = __popc(vw);
+    a.obs = __popc(hw);
+    a.starts = __popc(sw);
+    a.sum = sum;
+    a.vin = a.inner = 0;
+    a.has = hw != 0;
+    if (!hw) {
+        a.lead = a.trail = a.n;
+        return a;
+    }
+    const uint32_t first = __ffs(hw) - 1, last = 31 - __clz(hw);
+    a.lead = __popc(vw & ((1u << first) - 1u));
+    a.trail = __popc(vw & ~(0xFFFFFFFFu >> (31 - last)));
+    uint32_t zr = ~hw & (0xFFFFFFFFu >> (31 - last)) & ~((1u << first) - 1u); // non-hit positions between two hits
+    while (zr) {
+        const uint32_t s = __ffs(zr) - 1;
+        const uint32_t e = __ffs(~(zr >> s)) - 1; // length of this run of non-hit positions (ends before bit `last`)
+        const uint32_t gm = ((1u << e) - 1u) << s;
+        const uint32_t glen = __popc(vw & gm);
+        if (glen) {
+            a.vin += 1;
+            a.inner += kcf_gap_distance(glen, k);
+        }
+        zr &= ~gm;
+    }
+    return a;
+}
+
+// search the queued k-mers in the lines their home masks name; one item per lane
+#define KCF_FLUSH_QUEUE()                                                                                              \
+    do {                                                                                                               \
+        __syncwarp();                                                                                                  \
+        _Pragma("unroll 1") for (uint32_t t = lane; t < qn; t += 32)                                                   \
+        {                                                                                                              \
+            const KcfQueueItem it = W.queue[t];                                                                        \
+            uint32_t m2 = it.info & 0x7FFEu, c2 = 0;                                                                   \
+            bool found = false;                                                                                        \
+            while (m2 && !found) {                                                                                     \
+                const uint32_t d = __ffs(m2) - 1;                                                                      \
+                m2 &= m2 - 1;                                                                                          \
+                found = kcf_probe_line<S>(p.table + (uint64_t)kcf_line_wrap(it.home, d, g) * KCF_LINE_BYTES, it.key, g, c2); \
+            }                                                                                                          \
+            if (!found && (it.info & (1u << KCF_STASH_BIT))) c2 = kcf_stash_find(p.stash, g, it.key);                  \
+            const uint32_t pc = it.info >> 16;                                                                         \
+            if ((int32_t)c2 >= p.min_count) {                                                                          \
+                sum += c2;                                                                                             \
+                atomicOr(&W.hit[pc >> 5], 1u << (pc & 31u));                                                           \
+            }                                                                                                          \
+            if (p.counts_out) p.counts_out[(tile - p.counts_tile0) * KCF_TILE + chunk * KCF_CHUNK + pc] = (int32_t)c2; \
+        }                                                                                                              \
+        qn = 0;                                                                                                        \
+        __syncwarp();                                                                                                  \
+    } while (0)
+
 template <int S>
 __global__ void __launch_bounds__(32) kcf_screen_kernel(KcfScreenParams p, KcfTableGeom g)
 {
-    extern __shared__ __align__(128) uint8_t kcf_smem_raw[];
+    extern __shared__ __align__(16) uint8_t kcf_smem_raw[];
     KcfWarpSmem &W = *reinterpret_cast<KcfWarpSmem *>(kcf_smem_raw);
 
     const uint32_t lane = threadIdx.x;
     const uint32_t k = g.k;
     const uint64_t km1 = (k == 32) ? 0xFFFFFFFFULL : ((1ULL << k) - 1ULL);
-    const uint32_t lines_sa = kcf_smem_u32(W.lines);
-    constexpr uint32_t ROTN = S / 4;
+    uint32_t P2 = 1; // largest power of two <= w: the sliding minimum is built by doubling up to it
+    while (2 * P2 <= g.w) P2 *= 2;
 
     for (;;) {
         // ---- take a tile: KCF_TILE consecutive positions of one window ----
@@ -197,22 +269,22 @@ __global__ void __launch_bounds__(32) kcf_screen_kernel(KcfScreenParams p, KcfTa
         const uint32_t wlen = p.win_len[w];
         const int64_t o_tile = (int64_t)(tile - p.tile_first[w]) * KCF_TILE; // window position of the tile's first k-mer end
 
-        KcfGap acc; // summary of the steps done so far (meaningful in lane 0)
+        KcfGap acc; // summary of the chunks done so far (meaningful in lane 0)
         acc.n = acc.obs = acc.lead = acc.trail = acc.vin = acc.inner = acc.has = acc.starts = 0;
         acc.sum = 0;
-        uint32_t carry_hash = 0; // order hash of position KCF_SUB + lane of the previous step = position lane of this one
+        uint32_t carry_hash = 0; // order hash of position KCF_CHUNK + lane of the previous chunk = position lane of this one
 
-        for (uint32_t step = 0; step < KCF_TILE / KCF_SUB; ++step) {
-            const int64_t o = o_tile + (int64_t)step * KCF_SUB;
+        for (uint32_t chunk = 0; chunk < KCF_TILE / KCF_CHUNK; ++chunk) {
+            const int64_t o = o_tile + (int64_t)chunk * KCF_CHUNK;
             if (o >= (int64_t)wlen) break;
-            __syncwarp(); // the previous step's shared buffers are no longer read
+            const int g0 = chunk > 0 ? KCF_HALO / 8 : 0; // groups of 8 positions carried over from the previous chunk
 
-            // ---- stage bases [o - HALO, o + SUB): 8 positions per lane; the halo is carried over between steps ----
-            if (step > 0) {
+            // ---- stage bases [o - HALO, o + CHUNK): 8 positions per lane and step ----
+            if (chunk > 0) {
                 uint32_t c16 = 0, v8 = 0;
                 if (lane < KCF_HALO / 8) {
-                    c16 = reinterpret_cast<uint16_t *>(W.codes)[KCF_SUB / 8 + lane];
-                    v8 = reinterpret_cast<uint8_t *>(W.valid)[KCF_SUB / 8 + lane];
+                    c16 = reinterpret_cast<uint16_t *>(W.codes)[KCF_CHUNK / 8 + lane];
+                    v8 = reinterpret_cast<uint8_t *>(W.valid)[KCF_CHUNK / 8 + lane];
                 }
                 __syncwarp();
                 if (lane < KCF_HALO / 8) {
@@ -220,7 +292,8 @@ __global__ void __launch_bounds__(32) kcf_screen_kernel(KcfScreenParams p, KcfTa
                     reinterpret_cast<uint8_t *>(W.valid)[lane] = (uint8_t)v8;
                 }
             }
-            for (int u = (step > 0 ? KCF_HALO / 8 : 0) + (int)lane; u < (KCF_SUB + KCF_HALO) / 8; u += 32) {
+#pragma unroll 1
+            for (int u = g0 + (int)lane; u < (KCF_CHUNK + KCF_HALO) / 8; u += 32) {
                 const int64_t pos0 = o - KCF_HALO + 8 * (int64_t)u;
                 uint32_t c16 = 0, v8 = 0;
                 if (pos0 + 8 > 0 && pos0 < (int64_t)wlen) {
@@ -266,8 +339,9 @@ __global__ void __launch_bounds__(32) kcf_screen_kernel(KcfScreenParams p, KcfTa
             __syncwarp();
 
             // ---- order hash of the m-mer ending at every staged position (shared by the w k-mers that contain it) ----
-            if (step > 0) W.hash[lane + (lane >> 3)] = carry_hash;
-            for (int u = (step > 0 ? KCF_HALO / 8 : 0) + (int)lane; u < (KCF_SUB + KCF_HALO) / 8; u += 32) {
+            if (chunk > 0) W.hash[kcf_hidx(lane)] = carry_hash;
+#pragma unroll 1
+            for (int u = g0 + (int)lane; u < (KCF_CHUNK + KCF_HALO) / 8; u += 32) {
                 const int q0 = 8 * u;
                 const int b0 = q0 - (int)g.m + 1; // first base of the m-mer ending at q0
                 const int b0c = b0 > 0 ? b0 : 0;  // positions whose m-mer starts before the halo are never used
@@ -281,259 +355,110 @@ __global__ void __launch_bounds__(32) kcf_screen_kernel(KcfScreenParams p, KcfTa
                     W.hash[9 * u + i] = kcf_mmer_order(E, R, (uint32_t)(j > 0 ? j : 0), g);
                 }
             }
-
-            // ---- this lane's 40-base buffer: local bases [8 lane, 8 lane + 40); k-mer i ends at buffer base 32 + i ----
-            uint64_t blo, bhi, V;
-            {
-                const uint32_t wq = lane >> 1;
-                const uint32_t w0 = W.codes[wq], w1 = W.codes[wq + 1], w2 = W.codes[wq + 2];
-                const uint64_t t01 = ((uint64_t)w1 << 32) | w0;
-                if (lane & 1) {
-                    blo = (t01 >> 16) | ((uint64_t)w2 << 48);
-                    bhi = w2 >> 16;
-                } else {
-                    blo = t01;
-                    bhi = w2 & 0xFFFFu;
-                }
-                const uint32_t vq = lane >> 2;
-                const uint64_t v01 = ((uint64_t)W.valid[vq + 1] << 32) | W.valid[vq];
-                V = v01 >> (8 * (lane & 3));
-            }
-            const uint32_t sh0 = 2 * (33 - k); // 2..60
-            uint64_t X = ((blo >> sh0) | (bhi << (64 - sh0))) & g.kmask; // k-mer 0, base j in bits 2j
-            uint64_t fw = kcf_pair_reverse(X, g.kshift);                   // first base most significant (Kmer.java:232-252)
-            bool ok_prev = ((V >> (32 - k)) & km1) == km1;                 // k-mer ending one position before this lane's first
-
-            uint64_t key[KCF_PER_THREAD];
-            uint32_t okmask = 0, startmask = 0;
-#pragma unroll
-            for (int i = 0; i < KCF_PER_THREAD; ++i) {
-                if (i > 0) {
-                    const uint64_t c = (bhi >> (2 * i)) & 3ULL;
-                    X = (X >> 2) | (c << (2 * (k - 1)));
-                    fw = ((fw << 2) | c) & g.kmask;
-                }
-                const bool ok = ((V >> (33 + i - k)) & km1) == km1; // Fasta.java:99-104: any non-ACGT restarts the stretch
-                const uint64_t rc = (~X) & g.kmask;                 // reverse complement value (Kmer.java:300-338)
-                // canonical = unsigned-smaller word, tie keeps forward (Kmer.java:72-79, 406-414)
-                key[i] = (g.both_strands && rc < fw) ? rc : fw;
-                okmask |= (uint32_t)ok << i;
-                startmask |= (uint32_t)(ok && !ok_prev) << i;
-                ok_prev = ok;
-            }
-            __syncwarp(); // hashes complete
-
-            // ---- minimizer of each k-mer = sliding minimum over its w m-mer hashes -> home line ----
-            uint32_t line[KCF_PER_THREAD];
-            {
-                const uint32_t hb = KCF_HALO + 8 * lane - (g.w - 1); // first m-mer end position of k-mer 0
-                uint32_t mu[KCF_PER_THREAD];
-#define HASH_AT(j) W.hash[(hb + (j)) + ((hb + (j)) >> 3)]
-                if (g.w >= 8) {
-                    uint32_t core = HASH_AT(7); // positions shared by all 8 windows
-                    for (uint32_t j = 8; j < g.w; ++j) core = min(core, HASH_AT(j));
-                    uint32_t l = 0xFFFFFFFFu;
-                    mu[7] = core;
-#pragma unroll
-                    for (int i = 6; i >= 0; --i) {
-                        l = min(l, HASH_AT(i));
-                        mu[i] = min(core, l);
-                    }
-                    uint32_t r = 0xFFFFFFFFu;
-#pragma unroll
-                    for (int i = 1; i <= 7; ++i) {
-                        r = min(r, HASH_AT(g.w + i - 1));
-                        mu[i] = min(mu[i], r);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < KCF_PER_THREAD; ++i) {
-                        uint32_t v = HASH_AT(i);
-                        for (uint32_t j = 1; j < g.w; ++j) v = min(v, HASH_AT(i + j));
-                        mu[i] = v;
-                    }
-                }
-#undef HASH_AT
-                carry_hash = W.hash[(KCF_SUB + lane) + ((KCF_SUB + lane) >> 3)];
-#pragma unroll
-                for (int i = 0; i < KCF_PER_THREAD; ++i) line[i] = kcf_home_line(mu[i], g);
-            }
-#pragma unroll
-            for (int i = 0; i < KCF_PER_THREAD; i += 2)
-                *reinterpret_cast<ulonglong2 *>(&W.key[8 * lane + i]) = make_ulonglong2(key[i], key[i + 1]);
-
-            // ---- runs of consecutive valid k-mers with the same home line: one fetch per run ----
-            uint32_t headmask = 0;
-            {
-                uint32_t prev = __shfl_up_sync(0xffffffffu, (okmask >> 7) & 1u ? line[7] : 0xFFFFFFFFu, 1);
-                if (lane == 0) prev = 0xFFFFFFFFu;
-#pragma unroll
-                for (int i = 0; i < KCF_PER_THREAD; ++i) {
-                    const bool ok = (okmask >> i) & 1u;
-                    headmask |= (uint32_t)(ok && line[i] != prev) << i;
-                    prev = ok ? line[i] : 0xFFFFFFFFu;
-                }
-            }
-            uint32_t hbase, n_heads; // heads before this lane, heads in the step
-            {
-                const uint32_t nh = __popc(headmask);
-                uint32_t incl = nh;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= (uint32_t)d) incl += t;
-                }
-                hbase = incl - nh;
-                n_heads = __shfl_sync(0xffffffffu, incl, 31);
-            }
-
-            // ---- fetch and search, KCF_HCW runs at a time ----
-            uint32_t cnt[KCF_PER_THREAD];
-#pragma unroll
-            for (int i = 0; i < KCF_PER_THREAD; ++i) cnt[i] = 0;
-            for (uint32_t c0 = 0; c0 < n_heads; c0 += KCF_HCW) {
-                const uint32_t c1 = min(c0 + KCF_HCW, n_heads);
-                __syncwarp(); // previous chunk's lines are no longer read
-#pragma unroll
-                for (int i = 0; i < KCF_PER_THREAD; ++i) {
-                    const uint32_t slot = hbase + __popc(headmask & ((1u << i) - 1u));
-                    if (((headmask >> i) & 1u) && slot >= c0 && slot < c1) W.fetch[slot - c0] = line[i];
-                }
-                for (uint32_t j = lane; j < KCF_HCW; j += 32) W.need[j] = 0;
+            __syncwarp();
+            carry_hash = W.hash[kcf_hidx(KCF_CHUNK + lane)];
+            // sliding minimum by doubling, in place: after the pass with stride s, hash[q] = min over [q, q + 2s)
+#pragma unroll 1
+            for (uint32_t s = 1; s < P2; s <<= 1) {
                 __syncwarp();
-                kcf_fetch_lines(lines_sa, W.fetch, c1 - c0, p.table, lane);
-                kcf_fetch_wait();
-
-                // home lines
-                uint32_t pend = 0;
-#pragma unroll
-                for (int i = 0; i < KCF_PER_THREAD; ++i) {
-                    const uint32_t slot = hbase + __popc(headmask & ((2u << i) - 1u)) - 1u; // run this k-mer belongs to
-                    if (!((okmask >> i) & 1u) || slot < c0 || slot >= c1) continue;
-                    const uint32_t hs = slot - c0;
-                    const uint8_t *L = W.lines + hs * KCF_LINE_BYTES;
-                    const bool inl = KCF_KEY_IN_LINES(key[i]);
-                    uint32_t c;
-                    if (inl && kcf_smem_find<S>(L, hs % ROTN, key[i], g, c)) {
-                        cnt[i] = c;
-                        continue;
-                    }
-                    const uint32_t mask = kcf_mask_from_word31(reinterpret_cast<const uint32_t *>(L)[31]);
-                    if (inl && (mask & 0x7FFEu)) pend |= 1u << i;
-                    else if ((mask >> KCF_STASH_BIT) & 1u) cnt[i] = kcf_stash_find(p.stash, g, key[i]);
-                }
-
-                // continuation lines.  Per round: the first unresolved k-mer of a run claims staging slots for the lines
-                // its home mask names; every unresolved k-mer of a served run queues one (k-mer, line) pair per line;
-                // the lines are fetched; the pairs are searched one per lane, densely.
-                for (uint32_t round = 1; __any_sync(0xffffffffu, pend != 0); ++round) {
-                    if (lane == 0) {
-                        W.ext_count = 0;
-                        W.q_count = 0;
-                        W.ext_limit = KCF_ECW;
-                        W.q_limit = KCF_QC;
-                    }
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < KCF_PER_THREAD; ++i) {
-                        if (!((pend >> i) & 1u)) continue;
-                        const uint32_t hs = hbase + __popc(headmask & ((2u << i) - 1u)) - 1u - c0;
-                        if (atomicExch(&W.need[hs], round) == round) continue; // claimed this round already
-                        uint32_t m2 = kcf_mask_from_word31(reinterpret_cast<const uint32_t *>(W.lines + hs * KCF_LINE_BYTES)[31]) & 0x7FFEu;
-                        const uint32_t n = __popc(m2);
-                        uint32_t b = atomicAdd(&W.ext_count, n);
-                        if (b + n <= KCF_ECW) {
-                            W.extbase[hs] = b;
-                            while (m2) {
-                                const uint32_t d = __ffs(m2) - 1;
-                                m2 &= m2 - 1;
-                                W.fetch[KCF_HCW + b++] = kcf_line_wrap(line[i], d, g);
-                            }
-                        } else {
-                            W.extbase[hs] = 0xFFFFFFFFu;
-                            atomicMin(&W.ext_limit, b);
-                        }
-                    }
-                    __syncwarp();
-                    kcf_fetch_lines(lines_sa + KCF_HCW * KCF_LINE_BYTES, W.fetch + KCF_HCW, min(W.ext_count, W.ext_limit), p.table, lane);
-                    uint32_t served = 0;
-#pragma unroll
-                    for (int i = 0; i < KCF_PER_THREAD; ++i) {
-                        if (!((pend >> i) & 1u)) continue;
-                        const uint32_t hs = hbase + __popc(headmask & ((2u << i) - 1u)) - 1u - c0;
-                        const uint32_t b = W.extbase[hs];
-                        if (b == 0xFFFFFFFFu) continue; // next round
-                        const uint32_t mask = kcf_mask_from_word31(reinterpret_cast<const uint32_t *>(W.lines + hs * KCF_LINE_BYTES)[31]);
-                        const uint32_t n = __popc(mask & 0x7FFEu);
-                        const uint32_t qb = atomicAdd(&W.q_count, n);
-                        if (qb + n > KCF_QC) { // queue full: next round
-                            atomicMin(&W.q_limit, qb);
-                            continue;
-                        }
-                        const uint32_t pos = 8 * lane + i;
-                        for (uint32_t j = 0; j < n; ++j) W.queue[qb + j] = (pos << 16) | (b + j);
-                        W.cnt[pos] = (mask >> KCF_STASH_BIT) & 1u ? kcf_stash_find(p.stash, g, key[i]) : 0u;
-                        served |= 1u << i;
-                    }
-                    kcf_fetch_wait();
-                    {
-                        const uint32_t nq = min(W.q_count, W.q_limit); // every entry below was written this round
-                        for (uint32_t q = lane; q < nq; q += 32) {
-                            const uint32_t e = W.queue[q];
-                            const uint32_t pos = e >> 16, es = e & 0xFFFFu;
-                            uint32_t c;
-                            if (kcf_smem_find<S>(W.lines + (KCF_HCW + es) * KCF_LINE_BYTES, es % ROTN, W.key[pos], g, c)) W.cnt[pos] = c;
-                        }
-                    }
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < KCF_PER_THREAD; ++i)
-                        if ((served >> i) & 1u) cnt[i] = W.cnt[8 * lane + i];
-                    pend &= ~served;
+#pragma unroll 1
+                for (uint32_t q = lane; q + s < KCF_CHUNK + KCF_HALO; q += 32) {
+                    const uint32_t v = min(W.hash[kcf_hidx(q)], W.hash[kcf_hidx(q + s)]);
+                    __syncwarp(__activemask());
+                    W.hash[kcf_hidx(q)] = v;
                 }
             }
+            for (uint32_t j = lane; j < KCF_CHUNK / 32; j += 32) W.hit[j] = 0;
+            __syncwarp();
 
-            // ---- fold the 8 results into this lane's gap summary (GetVariants.java:220-245) ----
-            KcfGap a;
-            a.n = a.obs = a.lead = a.trail = a.vin = a.inner = a.has = 0;
-            a.starts = __popc(startmask);
-            a.sum = 0;
-            uint32_t gap = 0;
-#pragma unroll
-            for (int i = 0; i < KCF_PER_THREAD; ++i) {
-                const bool ok = (okmask >> i) & 1u;
+            // ---- probe: lanes own consecutive positions ----
+            uint64_t sum = 0;  // Σ count over this lane's observed k-mers
+            uint32_t qn = 0;   // queue length (warp uniform)
+            const uint32_t npos = (uint32_t)min((int64_t)KCF_CHUNK, (int64_t)wlen - o);
+#pragma unroll 1
+            for (uint32_t j = 0; j < KCF_CHUNK / 32; ++j) {
+                if (32 * j >= npos) { // past the window's end: no k-mers
+                    if (lane == 0) W.okw[j] = W.start[j] = 0;
+                    continue;
+                }
+                const uint32_t c = 32 * j + lane;  // chunk position of this lane's k-mer end
+                const uint32_t q = KCF_HALO + c;   // the same in staged coordinates
+                const uint32_t b0 = q - k + 1;     // first base
+                // validity of this k-mer and of the one ending one position earlier (Fasta.java:99-104)
+                bool ok, ok_prev;
+                {
+                    const uint32_t vb = b0 - 1, vi = vb >> 5;
+                    const uint64_t vwin = ((((uint64_t)W.valid[vi + 1] << 32) | W.valid[vi]) >> (vb & 31u));
+                    ok_prev = (vwin & km1) == km1;
+                    ok = ((vwin >> 1) & km1) == km1;
+                }
+                // canonical k-mer (Kmer.java:57-79, 232-252, 300-338)
+                uint64_t key;
+                {
+                    const uint32_t wi = b0 >> 4, sh = (b0 & 15u) * 2u;
+                    const uint64_t lo = ((uint64_t)W.codes[wi + 1] << 32) | W.codes[wi];
+                    const uint64_t X = (sh ? ((lo >> sh) | ((uint64_t)W.codes[wi + 2] << (64 - sh))) : lo) & g.kmask; // base j in bits 2j
+                    const uint64_t fw = kcf_pair_reverse(X, g.kshift); // first base most significant
+                    const uint64_t rc = (~X) & g.kmask;                // reverse complement value
+                    key = (g.both_strands && rc < fw) ? rc : fw;       // unsigned-smaller word, tie keeps forward
+                }
+                // minimizer = min over the w m-mers ending at q-w+1 .. q -> home line
+                const uint32_t h0 = q - g.w + 1;
+                const uint32_t mu = min(W.hash[kcf_hidx(h0)], W.hash[kcf_hidx(h0 + g.w - P2)]);
+                const uint32_t home = kcf_home_line(mu, g);
+                const uint8_t *L = p.table + (uint64_t)home * KCF_LINE_BYTES;
+
+                uint32_t cnt = 0;
+                bool pending = false;
+                uint32_t mask = 0;
                 if (ok) {
-                    a.n += 1;
-                    if ((int32_t)cnt[i] >= p.min_count) { // Java int compare (GetVariants.java:224)
-                        a.obs += 1;
-                        a.sum += cnt[i];
-                        if (!a.has) {
-                            a.lead = gap;
-                            a.has = 1;
-                        } else if (gap > 0) {
-                            a.vin += 1;
-                            a.inner += kcf_gap_distance(gap, k);
-                        }
-                        gap = 0;
-                    } else {
-                        gap += 1;
+                    const bool inl = KCF_KEY_IN_LINES(key);
+                    if (!(inl && kcf_probe_line<S>(L, key, g, cnt))) {
+                        cnt = 0;
+                        mask = kcf_mask_from_word31(__ldg(reinterpret_cast<const uint32_t *>(L) + 31));
+                        if (inl && (mask & 0x7FFEu)) pending = true;
+                        else if ((mask >> KCF_STASH_BIT) & 1u) cnt = kcf_stash_find(p.stash, g, key);
                     }
                 }
-                if (p.counts_out) {
-                    const uint64_t pos = (tile - p.counts_tile0) * KCF_TILE + step * KCF_SUB + 8 * lane + i;
-                    p.counts_out[pos] = ok ? (int32_t)cnt[i] : -1;
+                const bool hit = ok && (int32_t)cnt >= p.min_count; // Java int compare (GetVariants.java:224)
+                if (hit) sum += cnt;
+                const uint32_t hb = __ballot_sync(0xffffffffu, hit);
+                const uint32_t vb = __ballot_sync(0xffffffffu, ok);
+                const uint32_t sb = __ballot_sync(0xffffffffu, ok && !ok_prev);
+                const uint32_t pb = __ballot_sync(0xffffffffu, pending);
+                if (lane == 0) {
+                    atomicOr(&W.hit[j], hb);
+                    W.okw[j] = vb;
+                    W.start[j] = sb;
                 }
+                if (p.counts_out) p.counts_out[(tile - p.counts_tile0) * KCF_TILE + chunk * KCF_CHUNK + c] = ok ? (int32_t)cnt : -1;
+                if (pb) {
+                    if (pending) {
+                        KcfQueueItem it;
+                        it.key = key;
+                        it.home = home;
+                        it.info = (c << 16) | (mask & 0xFFFEu);
+                        W.queue[qn + __popc(pb & ((1u << lane) - 1u))] = it;
+                    }
+                    qn += __popc(pb);
+                }
+                // queue nearly full: search it now (one item per lane, densely)
+                if (qn + 32 > KCF_QCAP) KCF_FLUSH_QUEUE();
             }
-            a.trail = gap;
-            if (!a.has) a.lead = a.n;
+            if (qn) KCF_FLUSH_QUEUE();
+            __syncwarp();
 
-            // ---- ordered reduction over the 32 lanes, then onto the tile's running summary ----
-#pragma unroll
+            // ---- fold: lane j summarises positions [32 j, 32 j + 32), one ordered shuffle reduction per chunk ----
+            KcfGap a = kcf_gap_from_bits(W.hit[lane], W.okw[lane], W.start[lane], 0, k);
+#pragma unroll 1
             for (int d = 1; d < 32; d <<= 1) {
                 KcfGap b = kcf_gap_shfl_down(a, d);
                 if (lane + d < 32) a = kcf_gap_combine(a, b, k);
+                sum += __shfl_down_sync(0xffffffffu, sum, d); // Σ count is not tied to positions: plain warp sum
             }
+            a.sum = sum;
             acc = kcf_gap_combine(acc, a, k);
+            __syncwarp(); // the bitmaps are rewritten by the next chunk
         }
         if (lane == 0) p.tile_sum[tile] = acc;
     }
