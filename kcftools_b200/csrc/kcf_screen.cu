@@ -109,7 +109,8 @@ __device__ __forceinline__ KcfGap kcf_gap_shfl_down(const KcfGap &a, int delta)
 #define S_CODE_WORDS ((KCF_CHUNK + KCF_HALO) / 16 + 4)
 #define S_VALID_WORDS ((KCF_CHUNK + KCF_HALO) / 32 + 2)
 #define S_HASH_WORDS ((KCF_CHUNK + KCF_HALO) + (KCF_CHUNK + KCF_HALO) / 8 + 8) // one pad word per 8 (the writers stride by 8)
-#define KCF_QCAP 256
+#define KCF_QCAP 128
+#define KCF_PF 8 // prefetch distance, in iterations of 32 positions
 
 struct KcfQueueItem {
     unsigned long long key;
@@ -125,24 +126,20 @@ struct KcfWarpSmem {
     uint32_t hit[KCF_CHUNK / 32];   // bit = k-mer observed (count >= min_count)
     uint32_t okw[KCF_CHUNK / 32];   // bit = a k-mer ends at this position
     uint32_t start[KCF_CHUNK / 32]; // bit = k-mer opens a valid stretch (EFFLEN)
+    uint32_t home[KCF_PF][32];      // home lines computed ahead of the probes
 };
 
 __device__ __forceinline__ uint32_t kcf_hidx(uint32_t q) { return q + (q >> 3); }
 
-// the S low key words of a table line: its first two 32-byte sectors (L1-allocating loads: the high word, the count
-// and the mask of the same line are read right after)
-__device__ __forceinline__ void kcf_ld_lo(const uint8_t *line, uint4 &a, uint4 &b, uint4 &c, uint4 &d)
-{
-    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(line));
-    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(line + 16));
-    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w) : "l"(line + 32));
-    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w) : "l"(line + 48));
-}
-
-// slot of the line whose low word equals lo (live low words of a line are distinct), -1 if none
+// Probe one table line for `key`: the S low key words sit in the line's first two 32-byte sectors (4 x 16-byte loads);
+// live low words of a line are distinct, so the low-word match is the only candidate and is confirmed on the high word.
+// The loads allocate in L1: the high word, the count and the mask of the same line are read right after.
 template <int S>
-__device__ __forceinline__ int kcf_match_lo(const uint4 &a, const uint4 &b, const uint4 &c, const uint4 &d, uint32_t lo)
+__device__ __forceinline__ bool kcf_probe_line(const uint8_t *line, uint64_t key, const KcfTableGeom &g, uint32_t &count)
 {
+    const uint4 *q = reinterpret_cast<const uint4 *>(line);
+    const uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+    const uint32_t lo = (uint32_t)key;
     int idx = -1;
     if (a.x == lo) idx = 0;
     if (a.y == lo) idx = 1;
@@ -158,19 +155,11 @@ __device__ __forceinline__ int kcf_match_lo(const uint4 &a, const uint4 &b, cons
     if (S > 11 && c.w == lo) idx = 11;
     if (S > 12 && d.x == lo) idx = 12;
     if (S > 13 && d.y == lo) idx = 13;
-    return idx;
-}
-
-// probe one table line for `key`: true + count when it is there
-template <int S>
-__device__ __forceinline__ bool kcf_probe_line(const uint8_t *line, uint64_t key, const KcfTableGeom &g, uint32_t &count)
-{
-    uint4 a, b, c, d;
-    kcf_ld_lo(line, a, b, c, d);
-    const int idx = kcf_match_lo<S>(a, b, c, d, (uint32_t)key);
     if (idx < 0) return false;
     if (__ldg(reinterpret_cast<const uint32_t *>(line) + S + idx) != (uint32_t)(key >> 32)) return false;
-    count = kcf_slot_count(line, (uint32_t)idx, g);
+    constexpr int CW = S == 14 ? 1 : (S == 12 ? 2 : 4);
+    const uint8_t *cp = line + 8 * S + CW * idx;
+    count = CW == 1 ? (uint32_t)__ldg(cp) : (CW == 2 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(cp)) : __ldg(reinterpret_cast<const uint32_t *>(cp)));
     return true;
 }
 
@@ -207,6 +196,79 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
     }
     return a;
 }
+
+// Home line of the k-mer ending at chunk position 32 JJ + lane: minimizer = min over the w m-mers ending at
+// q-w+1 .. q.  Computed KCF_PF iterations ahead of the probe so that the line can be prefetched into L2: one request
+// per run of lanes sharing it (the first lane of the run issues it).
+#define KCF_HOME_AHEAD(JJ)                                                                                    \
+    do {                                                                                                      \
+        const uint32_t h0 = KCF_HALO + 32 * (JJ) + lane - g.w + 1;                                            \
+        const uint32_t hm = kcf_home_line(min(W.hash[kcf_hidx(h0)], W.hash[kcf_hidx(h0 + g.w - P2)]), g);     \
+        W.home[(JJ) % KCF_PF][lane] = hm;                                                                     \
+        const uint32_t left = __shfl_up_sync(0xffffffffu, hm, 1);                                             \
+        if (lane == 0 || left != hm)                                                                          \
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.table + (uint64_t)hm * KCF_LINE_BYTES));          \
+    } while (0)
+
+// One probe: canonical k-mer ending at chunk position 32 JJ + lane, its home line, search, publish the warp's bitmaps,
+// queue what needs other lines.
+#define KCF_PROBE(JJ, home)                                                                                                \
+    do {                                                                                                               \
+        const uint32_t cpos = 32 * (JJ) + lane;     /* chunk position of this lane's k-mer end */                      \
+        const uint32_t q = KCF_HALO + cpos;         /* the same in staged coordinates */                               \
+        const uint32_t b0 = q - k + 1;              /* first base */                                                   \
+        bool ok, ok_prev; /* validity of this k-mer and of the one ending one position earlier (Fasta.java:99-104) */  \
+        {                                                                                                              \
+            const uint32_t vb = b0 - 1, vi = vb >> 5;                                                                  \
+            const uint64_t vwin = ((((uint64_t)W.valid[vi + 1] << 32) | W.valid[vi]) >> (vb & 31u));                   \
+            ok_prev = (vwin & km1) == km1;                                                                             \
+            ok = ((vwin >> 1) & km1) == km1;                                                                           \
+        }                                                                                                              \
+        uint64_t key; /* canonical k-mer (Kmer.java:57-79, 232-252, 300-338) */                                        \
+        {                                                                                                              \
+            const uint32_t wi = b0 >> 4, sh = (b0 & 15u) * 2u;                                                         \
+            const uint64_t lo = ((uint64_t)W.codes[wi + 1] << 32) | W.codes[wi];                                       \
+            const uint64_t X = (sh ? ((lo >> sh) | ((uint64_t)W.codes[wi + 2] << (64 - sh))) : lo) & g.kmask;          \
+            const uint64_t fw = kcf_pair_reverse(X, g.kshift); /* first base most significant */                       \
+            const uint64_t rc = (~X) & g.kmask;                /* reverse complement value */                          \
+            key = (g.both_strands && rc < fw) ? rc : fw;       /* unsigned-smaller word, tie keeps forward */          \
+        }                                                                                                              \
+        const uint8_t *L = p.table + (uint64_t)home * KCF_LINE_BYTES;                                                  \
+        uint32_t cnt = 0, mask = 0;                                                                                    \
+        bool pending = false;                                                                                          \
+        if (ok) {                                                                                                      \
+            const bool inl = KCF_KEY_IN_LINES(key);                                                                    \
+            if (!(inl && kcf_probe_line<S>(L, key, g, cnt))) {                                                         \
+                cnt = 0;                                                                                               \
+                mask = kcf_mask_from_word31(__ldg(reinterpret_cast<const uint32_t *>(L) + 31));                        \
+                if (inl && (mask & 0x7FFEu)) pending = true;                                                           \
+                else if ((mask >> KCF_STASH_BIT) & 1u) cnt = kcf_stash_find(p.stash, g, key);                          \
+            }                                                                                                          \
+        }                                                                                                              \
+        const bool hit = ok && (int32_t)cnt >= p.min_count; /* Java int compare (GetVariants.java:224) */              \
+        if (hit) sum += cnt;                                                                                           \
+        const uint32_t hb = __ballot_sync(0xffffffffu, hit);                                                           \
+        const uint32_t vb = __ballot_sync(0xffffffffu, ok);                                                            \
+        const uint32_t sb = __ballot_sync(0xffffffffu, ok && !ok_prev);                                                \
+        const uint32_t pb = __ballot_sync(0xffffffffu, pending);                                                       \
+        if (lane == 0) {                                                                                               \
+            atomicOr(&W.hit[JJ], hb);                                                                                  \
+            W.okw[JJ] = vb;                                                                                            \
+            W.start[JJ] = sb;                                                                                          \
+        }                                                                                                              \
+        if (p.counts_out) p.counts_out[(tile - p.counts_tile0) * KCF_TILE + chunk * KCF_CHUNK + cpos] = ok ? (int32_t)cnt : -1; \
+        if (pb) {                                                                                                      \
+            if (pending) {                                                                                             \
+                KcfQueueItem it;                                                                                       \
+                it.key = key;                                                                                          \
+                it.home = home;                                                                                        \
+                it.info = (cpos << 16) | (mask & 0xFFFEu);                                                             \
+                W.queue[qn + __popc(pb & ((1u << lane) - 1u))] = it;                                                   \
+            }                                                                                                          \
+            qn += __popc(pb);                                                                                          \
+            if (qn + 32 > KCF_QCAP) KCF_FLUSH_QUEUE(); /* nearly full: search it now */                                \
+        }                                                                                                              \
+    } while (0)
 
 // search the queued k-mers in the lines their home masks name; one item per lane
 #define KCF_FLUSH_QUEUE()                                                                                              \
@@ -368,82 +430,21 @@ __global__ void __launch_bounds__(32) kcf_screen_kernel(KcfScreenParams p, KcfTa
                     W.hash[kcf_hidx(q)] = v;
                 }
             }
-            for (uint32_t j = lane; j < KCF_CHUNK / 32; j += 32) W.hit[j] = 0;
+            for (uint32_t j = lane; j < KCF_CHUNK / 32; j += 32) W.hit[j] = W.okw[j] = W.start[j] = 0;
             __syncwarp();
 
-            // ---- probe: lanes own consecutive positions ----
+            // ---- probe: lanes own consecutive positions; home lines are prefetched KCF_PF iterations ahead ----
             uint64_t sum = 0;  // Σ count over this lane's observed k-mers
             uint32_t qn = 0;   // queue length (warp uniform)
             const uint32_t npos = (uint32_t)min((int64_t)KCF_CHUNK, (int64_t)wlen - o);
+            const uint32_t J = (npos + 31) / 32;
 #pragma unroll 1
-            for (uint32_t j = 0; j < KCF_CHUNK / 32; ++j) {
-                if (32 * j >= npos) { // past the window's end: no k-mers
-                    if (lane == 0) W.okw[j] = W.start[j] = 0;
-                    continue;
-                }
-                const uint32_t c = 32 * j + lane;  // chunk position of this lane's k-mer end
-                const uint32_t q = KCF_HALO + c;   // the same in staged coordinates
-                const uint32_t b0 = q - k + 1;     // first base
-                // validity of this k-mer and of the one ending one position earlier (Fasta.java:99-104)
-                bool ok, ok_prev;
-                {
-                    const uint32_t vb = b0 - 1, vi = vb >> 5;
-                    const uint64_t vwin = ((((uint64_t)W.valid[vi + 1] << 32) | W.valid[vi]) >> (vb & 31u));
-                    ok_prev = (vwin & km1) == km1;
-                    ok = ((vwin >> 1) & km1) == km1;
-                }
-                // canonical k-mer (Kmer.java:57-79, 232-252, 300-338)
-                uint64_t key;
-                {
-                    const uint32_t wi = b0 >> 4, sh = (b0 & 15u) * 2u;
-                    const uint64_t lo = ((uint64_t)W.codes[wi + 1] << 32) | W.codes[wi];
-                    const uint64_t X = (sh ? ((lo >> sh) | ((uint64_t)W.codes[wi + 2] << (64 - sh))) : lo) & g.kmask; // base j in bits 2j
-                    const uint64_t fw = kcf_pair_reverse(X, g.kshift); // first base most significant
-                    const uint64_t rc = (~X) & g.kmask;                // reverse complement value
-                    key = (g.both_strands && rc < fw) ? rc : fw;       // unsigned-smaller word, tie keeps forward
-                }
-                // minimizer = min over the w m-mers ending at q-w+1 .. q -> home line
-                const uint32_t h0 = q - g.w + 1;
-                const uint32_t mu = min(W.hash[kcf_hidx(h0)], W.hash[kcf_hidx(h0 + g.w - P2)]);
-                const uint32_t home = kcf_home_line(mu, g);
-                const uint8_t *L = p.table + (uint64_t)home * KCF_LINE_BYTES;
-
-                uint32_t cnt = 0;
-                bool pending = false;
-                uint32_t mask = 0;
-                if (ok) {
-                    const bool inl = KCF_KEY_IN_LINES(key);
-                    if (!(inl && kcf_probe_line<S>(L, key, g, cnt))) {
-                        cnt = 0;
-                        mask = kcf_mask_from_word31(__ldg(reinterpret_cast<const uint32_t *>(L) + 31));
-                        if (inl && (mask & 0x7FFEu)) pending = true;
-                        else if ((mask >> KCF_STASH_BIT) & 1u) cnt = kcf_stash_find(p.stash, g, key);
-                    }
-                }
-                const bool hit = ok && (int32_t)cnt >= p.min_count; // Java int compare (GetVariants.java:224)
-                if (hit) sum += cnt;
-                const uint32_t hb = __ballot_sync(0xffffffffu, hit);
-                const uint32_t vb = __ballot_sync(0xffffffffu, ok);
-                const uint32_t sb = __ballot_sync(0xffffffffu, ok && !ok_prev);
-                const uint32_t pb = __ballot_sync(0xffffffffu, pending);
-                if (lane == 0) {
-                    atomicOr(&W.hit[j], hb);
-                    W.okw[j] = vb;
-                    W.start[j] = sb;
-                }
-                if (p.counts_out) p.counts_out[(tile - p.counts_tile0) * KCF_TILE + chunk * KCF_CHUNK + c] = ok ? (int32_t)cnt : -1;
-                if (pb) {
-                    if (pending) {
-                        KcfQueueItem it;
-                        it.key = key;
-                        it.home = home;
-                        it.info = (c << 16) | (mask & 0xFFFEu);
-                        W.queue[qn + __popc(pb & ((1u << lane) - 1u))] = it;
-                    }
-                    qn += __popc(pb);
-                }
-                // queue nearly full: search it now (one item per lane, densely)
-                if (qn + 32 > KCF_QCAP) KCF_FLUSH_QUEUE();
+            for (uint32_t j = 0; j < KCF_PF && j < J; ++j) KCF_HOME_AHEAD(j);
+#pragma unroll 1
+            for (uint32_t j = 0; j < J; ++j) {
+                const uint32_t home = W.home[j % KCF_PF][lane]; // read before the slot is reused for iteration j + KCF_PF
+                if (j + KCF_PF < J) KCF_HOME_AHEAD(j + KCF_PF);
+                KCF_PROBE(j, home);
             }
             if (qn) KCF_FLUSH_QUEUE();
             __syncwarp();
