@@ -80,6 +80,20 @@ struct KcfIngestParams {
     uint32_t *flags;
 };
 
+// record in the home line's filter that `key` lives outside it (bits are cleared: the filter is stored inverted)
+__device__ __forceinline__ void kcf_filter_add(uint8_t *home_line, uint64_t key, const KcfTableGeom &g)
+{
+    const uint32_t h = kcf_filter_hash(key);
+    uint32_t *f = reinterpret_cast<uint32_t *>(home_line + g.foff);
+    if (g.fbits == 64) {
+        const uint32_t b1 = h >> 26, b2 = (h >> 20) & 63u;
+        atomicAnd(f + (b1 >> 5), ~(1u << (b1 & 31u)));
+        atomicAnd(f + (b2 >> 5), ~(1u << (b2 & 31u)));
+    } else {
+        atomicAnd(f, ~((1u << (h >> 27)) | (1u << ((h >> 22) & 31u))));
+    }
+}
+
 __global__ void __launch_bounds__(256) kcf_ingest_kernel(KcfIngestParams p, KcfTableGeom g)
 {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,11 +166,12 @@ __global__ void __launch_bounds__(256) kcf_ingest_kernel(KcfIngestParams p, KcfT
                         w[g.S + s] = hi;
                         // count and mask bits are cleared out of the all-ones initial image (atomics: several writers
                         // share these 32-bit words)
-                        const uint32_t off = 8 * g.S + g.cw * s;
+                        const uint32_t off = g.coff + g.cw * s;
                         const uint32_t sh = 8 * (off & 3u);
                         const uint32_t field = g.cw == 4 ? 0xFFFFFFFFu : (((1u << (8 * g.cw)) - 1u) << sh);
                         atomicAnd(w + (off >> 2), ~field | (count << sh));
                         atomicAnd(home_w31, ~(1u << (16 + d)));
+                        if (d > 0) kcf_filter_add(p.table + (uint64_t)home * KCF_LINE_BYTES, kmer, g);
                         atomicAdd(&p.counters[0], 1ULL);
                         placed = true;
                         break;
@@ -170,6 +185,7 @@ __global__ void __launch_bounds__(256) kcf_ingest_kernel(KcfIngestParams p, KcfT
         }
     }
     atomicAnd(home_w31, ~(1u << (16 + KCF_STASH_BIT)));
+    kcf_filter_add(p.table + (uint64_t)home * KCF_LINE_BYTES, kmer, g);
     unsigned long long pos = atomicAdd(&p.counters[2], 1ULL);
     if (pos < p.ovf_cap) {
         p.ovf[pos].key = kmer;
@@ -304,7 +320,10 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     g.kshift = 64 - kk2;
     g.kmask = kk2 == 64 ? ~0ULL : ((1ULL << kk2) - 1);
     g.cw = cs <= 1 ? 1u : (cs == 2 ? 2u : 4u);
-    g.S = g.cw == 1 ? 14u : (g.cw == 2 ? 12u : 10u);
+    g.S = g.cw == 1 ? 13u : (g.cw == 2 ? 12u : 10u);
+    g.coff = g.cw == 1 ? 112u : 8u * g.S;
+    g.foff = g.cw == 1 ? 104u : 120u;
+    g.fbits = g.cw == 1 ? 64u : 32u;
     g.both_strands = (uint32_t)info.both_strands;
     {
         // minimizer length: long enough that one m-mer value rarely names more than one locus of the

@@ -19,13 +19,17 @@
 //   o(x)   = mix32(min(x, revcomp(x)))         order hash of an m-mer, strand symmetric
 //   mu(K)  = min o(x) over the w = k-m+1 m-mers of K
 //   home   = floor(mix32(mu ^ c) * n_lines / 2^32)
-//   line   = S key low words | S key high words | S counts | 16-bit mask      (S = 14 for 1-byte counts)
-//            (key = canonical k-mer value, stored in full; low word 0xFFFFFFFF = empty slot)
+//   line   = S key low words | S key high words | filter | S counts | 16-bit mask
+//            (S = 13 slots and a 64-bit filter for 1-byte counts; 12 / 10 slots and 32 bits for 2 / 4-byte counts;
+//             key = canonical k-mer value, stored in full; low word 0xFFFFFFFF = empty slot)
 //
 // A key lives in line home+d, 0 <= d <= 14, the first one with a free slot when it was inserted
 // (no deletions).  Bit d of the HOME line's mask says "some key homed here lives in home+d", bit 15
 // "some key homed here lives in the stash"; a lookup therefore knows after reading the home line
-// exactly which other lines (if any) can hold its key.  Keys are stored in full: a probe is exact.
+// exactly which other lines (if any) can hold its key.  The filter is a 2-hash Bloom filter over the keys homed
+// here that live elsewhere: a k-mer that misses in its home line and fails the filter is absent, and no other line
+// is read for it (absent k-mers are a quarter of a typical reference scan).  Keys are stored in full: a probe is
+// exact; the filter can only cause extra probes, never a wrong answer.
 // ------------------------------------------------------------------------------------------
 #define KCF_LINE_BYTES 128
 #define KCF_MAX_DISP 14
@@ -43,8 +47,11 @@ struct KcfTableGeom {
     uint32_t m;          // minimizer length, 1..16, <= k
     uint32_t w;          // k - m + 1 (1..32)
     uint32_t mmask;      // 2m one-bits
-    uint32_t S;          // slots per line: 14 / 12 / 10 for count width 1 / 2 / 4
+    uint32_t S;          // slots per line: 13 / 12 / 10 for count width 1 / 2 / 4
     uint32_t cw;         // bytes per stored count: 1, 2 or 4 (0-byte counters store nothing)
+    uint32_t coff;       // byte offset of the counts inside a line: 112 / 96 / 80
+    uint32_t foff;       // byte offset of the filter: 104 (64 bits) / 120 (32 bits)
+    uint32_t fbits;      // 64 or 32
     uint32_t both_strands;
 };
 
@@ -62,6 +69,12 @@ __host__ __device__ __forceinline__ uint32_t kcf_mix32(uint32_t x)
     x *= 0x846ca68bU;
     x ^= x >> 16;
     return x;
+}
+
+// the two filter bit positions of a key (6 bits each; the 32-bit filters use 5)
+__host__ __device__ __forceinline__ uint32_t kcf_filter_hash(uint64_t key)
+{
+    return ((uint32_t)key * 0x9E3779B1u) ^ ((uint32_t)(key >> 32) * 0x85EBCA77u);
 }
 
 // 64-bit mixer used for the stash only

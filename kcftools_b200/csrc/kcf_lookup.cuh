@@ -59,10 +59,29 @@ __device__ __forceinline__ uint32_t kcf_line_wrap(uint32_t home, uint32_t d, con
 // the 16-bit mask of a home line (stored inverted so that the table can be initialised with 0xFF bytes)
 __device__ __forceinline__ uint32_t kcf_mask_from_word31(uint32_t w31) { return (~w31) >> 16; }
 
+// does the home line's filter (stored inverted, as read from memory) admit that `key` lives outside its home line?
+__device__ __forceinline__ bool kcf_filter_pass64(uint64_t stored, uint64_t key)
+{
+    const uint32_t h = kcf_filter_hash(key);
+    const uint64_t f = ~stored;
+    return ((f >> (h >> 26)) & (f >> ((h >> 20) & 63u)) & 1ULL) != 0;
+}
+__device__ __forceinline__ bool kcf_filter_pass32(uint32_t stored, uint64_t key)
+{
+    const uint32_t h = kcf_filter_hash(key);
+    const uint32_t f = ~stored;
+    return ((f >> (h >> 27)) & (f >> ((h >> 22) & 31u)) & 1u) != 0;
+}
+__device__ __forceinline__ bool kcf_filter_pass(const uint8_t *home_line, uint64_t key, const KcfTableGeom &g)
+{
+    if (g.fbits == 64) return kcf_filter_pass64(__ldg(reinterpret_cast<const unsigned long long *>(home_line + g.foff)), key);
+    return kcf_filter_pass32(__ldg(reinterpret_cast<const uint32_t *>(home_line + g.foff)), key);
+}
+
 // count of slot s of a line image (global or shared memory)
 __device__ __forceinline__ uint32_t kcf_slot_count(const uint8_t *line, uint32_t s, const KcfTableGeom &g)
 {
-    const uint8_t *c = line + 8 * g.S + g.cw * s;
+    const uint8_t *c = line + g.coff + g.cw * s;
     if (g.cw == 1) return *c;
     if (g.cw == 2) return *reinterpret_cast<const uint16_t *>(c);
     return *reinterpret_cast<const uint32_t *>(c);
@@ -117,6 +136,10 @@ __device__ __forceinline__ uint32_t kcf_lookup(const uint8_t *__restrict__ table
                                                const KcfTableGeom &g, uint64_t key)
 {
     const uint32_t home = kcf_home_line(kcf_minimizer_of_key(key, g), g);
-    const uint32_t w31 = __ldg(reinterpret_cast<const uint32_t *>(table + (uint64_t)home * KCF_LINE_BYTES) + 31);
-    return kcf_probe_lines(table, stash, g, key, home, kcf_mask_from_word31(w31), 0);
+    const uint8_t *L = table + (uint64_t)home * KCF_LINE_BYTES;
+    uint32_t c;
+    if (KCF_KEY_IN_LINES(key) && kcf_line_find(L, key, g, c)) return c;
+    if (!kcf_filter_pass(L, key, g)) return 0; // no key homed here that lives elsewhere looks like this one
+    const uint32_t w31 = __ldg(reinterpret_cast<const uint32_t *>(L) + 31);
+    return kcf_probe_lines(table, stash, g, key, home, kcf_mask_from_word31(w31), 1);
 }

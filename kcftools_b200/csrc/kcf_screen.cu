@@ -108,7 +108,7 @@ __device__ __forceinline__ KcfGap kcf_gap_shfl_down(const KcfGap &a, int delta)
 #define KCF_CHUNK 1024
 #define S_CODE_WORDS ((KCF_CHUNK + KCF_HALO) / 16 + 4)
 #define S_VALID_WORDS ((KCF_CHUNK + KCF_HALO) / 32 + 2)
-#define S_HASH_WORDS ((KCF_CHUNK + KCF_HALO) + (KCF_CHUNK + KCF_HALO) / 8 + 8) // one pad word per 8 (the writers stride by 8)
+#define S_HASH_WORDS (KCF_CHUNK + KCF_HALO + 8)
 #define KCF_QCAP 128
 #define KCF_PF 8 // prefetch distance, in iterations of 32 positions
 
@@ -129,13 +129,12 @@ struct KcfWarpSmem {
     uint32_t home[KCF_PF][32];      // home lines computed ahead of the probes
 };
 
-__device__ __forceinline__ uint32_t kcf_hidx(uint32_t q) { return q + (q >> 3); }
 
 // Probe one table line for `key`: the S low key words sit in the line's first two 32-byte sectors (4 x 16-byte loads);
 // live low words of a line are distinct, so the low-word match is the only candidate and is confirmed on the high word.
-// The loads allocate in L1: the high word, the count and the mask of the same line are read right after.
+// The loads allocate in L1: the high word, the count, the filter and the mask of the same line are read right after.
 template <int S>
-__device__ __forceinline__ bool kcf_probe_line(const uint8_t *line, uint64_t key, const KcfTableGeom &g, uint32_t &count)
+__device__ __forceinline__ bool kcf_probe_line(const uint8_t *line, uint64_t key, uint32_t &count)
 {
     const uint4 *q = reinterpret_cast<const uint4 *>(line);
     const uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
@@ -154,11 +153,11 @@ __device__ __forceinline__ bool kcf_probe_line(const uint8_t *line, uint64_t key
     if (S > 10 && c.z == lo) idx = 10;
     if (S > 11 && c.w == lo) idx = 11;
     if (S > 12 && d.x == lo) idx = 12;
-    if (S > 13 && d.y == lo) idx = 13;
     if (idx < 0) return false;
     if (__ldg(reinterpret_cast<const uint32_t *>(line) + S + idx) != (uint32_t)(key >> 32)) return false;
-    constexpr int CW = S == 14 ? 1 : (S == 12 ? 2 : 4);
-    const uint8_t *cp = line + 8 * S + CW * idx;
+    constexpr int CW = S == 13 ? 1 : (S == 12 ? 2 : 4);
+    constexpr int COFF = S == 13 ? 112 : 8 * S;
+    const uint8_t *cp = line + COFF + CW * idx;
     count = CW == 1 ? (uint32_t)__ldg(cp) : (CW == 2 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(cp)) : __ldg(reinterpret_cast<const uint32_t *>(cp)));
     return true;
 }
@@ -203,7 +202,7 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
 #define KCF_HOME_AHEAD(JJ)                                                                                    \
     do {                                                                                                      \
         const uint32_t h0 = KCF_HALO + 32 * (JJ) + lane - g.w + 1;                                            \
-        const uint32_t hm = kcf_home_line(min(W.hash[kcf_hidx(h0)], W.hash[kcf_hidx(h0 + g.w - P2)]), g);     \
+        const uint32_t hm = kcf_home_line(min(W.hash[h0], W.hash[h0 + g.w - P2]), g);     \
         W.home[(JJ) % KCF_PF][lane] = hm;                                                                     \
         const uint32_t left = __shfl_up_sync(0xffffffffu, hm, 1);                                             \
         if (lane == 0 || left != hm)                                                                          \
@@ -238,11 +237,16 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
         bool pending = false;                                                                                          \
         if (ok) {                                                                                                      \
             const bool inl = KCF_KEY_IN_LINES(key);                                                                    \
-            if (!(inl && kcf_probe_line<S>(L, key, g, cnt))) {                                                         \
+            if (!(inl && kcf_probe_line<S>(L, key, cnt))) {                                                            \
                 cnt = 0;                                                                                               \
-                mask = kcf_mask_from_word31(__ldg(reinterpret_cast<const uint32_t *>(L) + 31));                        \
-                if (inl && (mask & 0x7FFEu)) pending = true;                                                           \
-                else if ((mask >> KCF_STASH_BIT) & 1u) cnt = kcf_stash_find(p.stash, g, key);                          \
+                /* absent unless the home line's filter says a key like this one lives outside it */                   \
+                const bool maybe = S == 13 ? kcf_filter_pass64(__ldg(reinterpret_cast<const unsigned long long *>(L + 104)), key) \
+                                           : kcf_filter_pass32(__ldg(reinterpret_cast<const uint32_t *>(L + 120)), key); \
+                if (maybe) {                                                                                           \
+                    mask = kcf_mask_from_word31(__ldg(reinterpret_cast<const uint32_t *>(L) + 31));                    \
+                    if (inl && (mask & 0x7FFEu)) pending = true;                                                       \
+                    else if ((mask >> KCF_STASH_BIT) & 1u) cnt = kcf_stash_find(p.stash, g, key);                      \
+                }                                                                                                      \
             }                                                                                                          \
         }                                                                                                              \
         const bool hit = ok && (int32_t)cnt >= p.min_count; /* Java int compare (GetVariants.java:224) */              \
@@ -282,7 +286,7 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
             while (m2 && !found) {                                                                                     \
                 const uint32_t d = __ffs(m2) - 1;                                                                      \
                 m2 &= m2 - 1;                                                                                          \
-                found = kcf_probe_line<S>(p.table + (uint64_t)kcf_line_wrap(it.home, d, g) * KCF_LINE_BYTES, it.key, g, c2); \
+                found = kcf_probe_line<S>(p.table + (uint64_t)kcf_line_wrap(it.home, d, g) * KCF_LINE_BYTES, it.key, c2); \
             }                                                                                                          \
             if (!found && (it.info & (1u << KCF_STASH_BIT))) c2 = kcf_stash_find(p.stash, g, it.key);                  \
             const uint32_t pc = it.info >> 16;                                                                         \
@@ -401,7 +405,7 @@ __global__ void __launch_bounds__(32) kcf_screen_kernel(KcfScreenParams p, KcfTa
             __syncwarp();
 
             // ---- order hash of the m-mer ending at every staged position (shared by the w k-mers that contain it) ----
-            if (chunk > 0) W.hash[kcf_hidx(lane)] = carry_hash;
+            if (chunk > 0) W.hash[lane] = carry_hash;
 #pragma unroll 1
             for (int u = g0 + (int)lane; u < (KCF_CHUNK + KCF_HALO) / 8; u += 32) {
                 const int q0 = 8 * u;
@@ -414,20 +418,27 @@ __global__ void __launch_bounds__(32) kcf_screen_kernel(KcfScreenParams p, KcfTa
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int j = i + (b0 - b0c);
-                    W.hash[9 * u + i] = kcf_mmer_order(E, R, (uint32_t)(j > 0 ? j : 0), g);
+                    W.hash[8 * u + i] = kcf_mmer_order(E, R, (uint32_t)(j > 0 ? j : 0), g);
                 }
             }
             __syncwarp();
-            carry_hash = W.hash[kcf_hidx(KCF_CHUNK + lane)];
-            // sliding minimum by doubling, in place: after the pass with stride s, hash[q] = min over [q, q + 2s)
+            carry_hash = W.hash[KCF_CHUNK + lane];
+            // sliding minimum by doubling, in place: a pass with stride s turns "min over [q, q + s)" into "min over
+            // [q, q + 4 s)" (or 2 s for the last pass when log2(P2) is odd); ascending q only reads not-yet-updated entries
+            {
+                uint32_t sd = 1;
+                while (sd < P2) {
+                    const bool four = 4 * sd <= P2;
+                    const uint32_t span = four ? 3 * sd : sd;
+                    __syncwarp();
 #pragma unroll 1
-            for (uint32_t s = 1; s < P2; s <<= 1) {
-                __syncwarp();
-#pragma unroll 1
-                for (uint32_t q = lane; q + s < KCF_CHUNK + KCF_HALO; q += 32) {
-                    const uint32_t v = min(W.hash[kcf_hidx(q)], W.hash[kcf_hidx(q + s)]);
-                    __syncwarp(__activemask());
-                    W.hash[kcf_hidx(q)] = v;
+                    for (uint32_t q = lane; q + span < KCF_CHUNK + KCF_HALO; q += 32) {
+                        uint32_t v = min(W.hash[q], W.hash[q + sd]);
+                        if (four) v = min(v, min(W.hash[q + 2 * sd], W.hash[q + 3 * sd]));
+                        __syncwarp(__activemask());
+                        W.hash[q] = v;
+                    }
+                    sd *= four ? 4 : 2;
                 }
             }
             for (uint32_t j = lane; j < KCF_CHUNK / 32; j += 32) W.hit[j] = W.okw[j] = W.start[j] = 0;
@@ -722,7 +733,7 @@ static int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t m
     p.counts_tile0 = tile_begin;
     const size_t smem = sizeof(KcfWarpSmem);
     void (*kern)(KcfScreenParams, KcfTableGeom) =
-        db->geom.S == 14 ? kcf_screen_kernel<14> : (db->geom.S == 12 ? kcf_screen_kernel<12> : kcf_screen_kernel<10>);
+        db->geom.S == 13 ? kcf_screen_kernel<13> : (db->geom.S == 12 ? kcf_screen_kernel<12> : kcf_screen_kernel<10>);
     KCF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     KCF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
