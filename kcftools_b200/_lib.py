@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkcfgpu.so")
+LIB_PATH = os.environ.get("KCF_LIB_PATH") or os.path.join(_HERE, "libkcfgpu.so")  # KCF_LIB_PATH: tuning builds
 
 RESULT_DTYPE = np.dtype([("total_kmers", "<i4"), ("eff_len", "<i4"), ("obs", "<i4"), ("variations", "<i4"),
                          ("inner", "<i4"), ("left", "<i4"), ("right", "<i4"), ("_pad", "<i4"),

@@ -133,7 +133,7 @@ struct kcf_ctx {
     bool seqs_dirty = false;
     uint8_t *d_raw = nullptr;    // staging for raw FASTA bytes
     size_t d_raw_cap = 0;
-    double load_factor = 0.5;
+    double load_factor = 0.4;
     int minimizer_len = 0;       // 0 = chosen from the database size
     int sm_count = 148;
     int profiling = 0;

@@ -11,6 +11,7 @@
 // order with warp shuffles.  No per-k-mer data ever goes back to HBM.
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 #include "kcf_internal.cuh"
 #include "kcf_lookup.cuh"
 
@@ -105,12 +106,19 @@ __device__ __forceinline__ KcfGap kcf_gap_shfl_down(const KcfGap &a, int delta)
 //   queue    searched one item per lane, densely (continuation lines are rare per k-mer but not per warp)
 //   fold     hit / valid bitmaps (one ballot per 32 positions) -> gap summary by bit tricks -> one shuffle reduction
 // ------------------------------------------------------------------------------------------------------------
-#define KCF_CHUNK 1024
+#ifndef KCF_CHUNK
+#define KCF_CHUNK 512
+#endif
+#ifndef KCF_MIN_WARPS
+#define KCF_MIN_WARPS 40 // resident warps per SM the register allocation is held to (measured best of 32 / 40 / 48)
+#endif
+#define KCF_WPC 2 // independent warps per CTA (an SM holds 32 CTAs at most)
 #define S_CODE_WORDS ((KCF_CHUNK + KCF_HALO) / 16 + 4)
 #define S_VALID_WORDS ((KCF_CHUNK + KCF_HALO) / 32 + 2)
 #define S_HASH_WORDS (KCF_CHUNK + KCF_HALO + 8)
-#define KCF_QCAP 128
-#define KCF_PF 8 // prefetch distance, in iterations of 32 positions
+#ifndef KCF_QCAP
+#define KCF_QCAP 64
+#endif
 
 struct KcfQueueItem {
     unsigned long long key;
@@ -126,7 +134,6 @@ struct KcfWarpSmem {
     uint32_t hit[KCF_CHUNK / 32];   // bit = k-mer observed (count >= min_count)
     uint32_t okw[KCF_CHUNK / 32];   // bit = a k-mer ends at this position
     uint32_t start[KCF_CHUNK / 32]; // bit = k-mer opens a valid stretch (EFFLEN)
-    uint32_t home[KCF_PF][32];      // home lines computed ahead of the probes
 };
 
 
@@ -196,22 +203,9 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
     return a;
 }
 
-// Home line of the k-mer ending at chunk position 32 JJ + lane: minimizer = min over the w m-mers ending at
-// q-w+1 .. q.  Computed KCF_PF iterations ahead of the probe so that the line can be prefetched into L2: one request
-// per run of lanes sharing it (the first lane of the run issues it).
-#define KCF_HOME_AHEAD(JJ)                                                                                    \
-    do {                                                                                                      \
-        const uint32_t h0 = KCF_HALO + 32 * (JJ) + lane - g.w + 1;                                            \
-        const uint32_t hm = kcf_home_line(min(W.hash[h0], W.hash[h0 + g.w - P2]), g);     \
-        W.home[(JJ) % KCF_PF][lane] = hm;                                                                     \
-        const uint32_t left = __shfl_up_sync(0xffffffffu, hm, 1);                                             \
-        if (lane == 0 || left != hm)                                                                          \
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.table + (uint64_t)hm * KCF_LINE_BYTES));          \
-    } while (0)
-
 // One probe: canonical k-mer ending at chunk position 32 JJ + lane, its home line, search, publish the warp's bitmaps,
 // queue what needs other lines.
-#define KCF_PROBE(JJ, home)                                                                                                \
+#define KCF_PROBE(JJ)                                                                                                      \
     do {                                                                                                               \
         const uint32_t cpos = 32 * (JJ) + lane;     /* chunk position of this lane's k-mer end */                      \
         const uint32_t q = KCF_HALO + cpos;         /* the same in staged coordinates */                               \
@@ -232,6 +226,9 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
             const uint64_t rc = (~X) & g.kmask;                /* reverse complement value */                          \
             key = (g.both_strands && rc < fw) ? rc : fw;       /* unsigned-smaller word, tie keeps forward */          \
         }                                                                                                              \
+        /* minimizer = min over the w m-mers ending at q-w+1 .. q -> home line */                                      \
+        const uint32_t h0 = q - g.w + 1;                                                                               \
+        const uint32_t home = kcf_home_line(min(W.hash[h0], W.hash[h0 + g.w - P2]), g);                                \
         const uint8_t *L = p.table + (uint64_t)home * KCF_LINE_BYTES;                                                  \
         uint32_t cnt = 0, mask = 0;                                                                                    \
         bool pending = false;                                                                                          \
@@ -260,7 +257,7 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
             W.okw[JJ] = vb;                                                                                            \
             W.start[JJ] = sb;                                                                                          \
         }                                                                                                              \
-        if (p.counts_out) p.counts_out[(tile - p.counts_tile0) * KCF_TILE + chunk * KCF_CHUNK + cpos] = ok ? (int32_t)cnt : -1; \
+        if (COUNTS) p.counts_out[(tile - p.counts_tile0) * KCF_TILE + chunk * KCF_CHUNK + cpos] = ok ? (int32_t)cnt : -1; \
         if (pb) {                                                                                                      \
             if (pending) {                                                                                             \
                 KcfQueueItem it;                                                                                       \
@@ -294,19 +291,19 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
                 sum += c2;                                                                                             \
                 atomicOr(&W.hit[pc >> 5], 1u << (pc & 31u));                                                           \
             }                                                                                                          \
-            if (p.counts_out) p.counts_out[(tile - p.counts_tile0) * KCF_TILE + chunk * KCF_CHUNK + pc] = (int32_t)c2; \
+            if (COUNTS) p.counts_out[(tile - p.counts_tile0) * KCF_TILE + chunk * KCF_CHUNK + pc] = (int32_t)c2; \
         }                                                                                                              \
         qn = 0;                                                                                                        \
         __syncwarp();                                                                                                  \
     } while (0)
 
-template <int S>
-__global__ void __launch_bounds__(32) kcf_screen_kernel(KcfScreenParams p, KcfTableGeom g)
+template <int S, bool COUNTS>
+__global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_screen_kernel(KcfScreenParams p, KcfTableGeom g)
 {
     extern __shared__ __align__(16) uint8_t kcf_smem_raw[];
-    KcfWarpSmem &W = *reinterpret_cast<KcfWarpSmem *>(kcf_smem_raw);
+    KcfWarpSmem &W = reinterpret_cast<KcfWarpSmem *>(kcf_smem_raw)[threadIdx.x >> 5]; // the warps of a CTA share nothing
 
-    const uint32_t lane = threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
     const uint32_t k = g.k;
     const uint64_t km1 = (k == 32) ? 0xFFFFFFFFULL : ((1ULL << k) - 1ULL);
     uint32_t P2 = 1; // largest power of two <= w: the sliding minimum is built by doubling up to it
@@ -444,24 +441,19 @@ __global__ void __launch_bounds__(32) kcf_screen_kernel(KcfScreenParams p, KcfTa
             for (uint32_t j = lane; j < KCF_CHUNK / 32; j += 32) W.hit[j] = W.okw[j] = W.start[j] = 0;
             __syncwarp();
 
-            // ---- probe: lanes own consecutive positions; home lines are prefetched KCF_PF iterations ahead ----
+            // ---- probe: lanes own consecutive positions ----
             uint64_t sum = 0;  // Σ count over this lane's observed k-mers
             uint32_t qn = 0;   // queue length (warp uniform)
             const uint32_t npos = (uint32_t)min((int64_t)KCF_CHUNK, (int64_t)wlen - o);
             const uint32_t J = (npos + 31) / 32;
 #pragma unroll 1
-            for (uint32_t j = 0; j < KCF_PF && j < J; ++j) KCF_HOME_AHEAD(j);
-#pragma unroll 1
-            for (uint32_t j = 0; j < J; ++j) {
-                const uint32_t home = W.home[j % KCF_PF][lane]; // read before the slot is reused for iteration j + KCF_PF
-                if (j + KCF_PF < J) KCF_HOME_AHEAD(j + KCF_PF);
-                KCF_PROBE(j, home);
-            }
+            for (uint32_t j = 0; j < J; ++j) KCF_PROBE(j);
             if (qn) KCF_FLUSH_QUEUE();
             __syncwarp();
 
             // ---- fold: lane j summarises positions [32 j, 32 j + 32), one ordered shuffle reduction per chunk ----
-            KcfGap a = kcf_gap_from_bits(W.hit[lane], W.okw[lane], W.start[lane], 0, k);
+            constexpr uint32_t NWORDS = KCF_CHUNK / 32;
+            KcfGap a = kcf_gap_from_bits(lane < NWORDS ? W.hit[lane] : 0u, lane < NWORDS ? W.okw[lane] : 0u, lane < NWORDS ? W.start[lane] : 0u, 0, k);
 #pragma unroll 1
             for (int d = 1; d < 32; d <<= 1) {
                 KcfGap b = kcf_gap_shfl_down(a, d);
@@ -731,15 +723,17 @@ static int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t m
     p.min_count = min_count;
     p.counts_out = d_counts;
     p.counts_tile0 = tile_begin;
-    const size_t smem = sizeof(KcfWarpSmem);
-    void (*kern)(KcfScreenParams, KcfTableGeom) =
-        db->geom.S == 13 ? kcf_screen_kernel<13> : (db->geom.S == 12 ? kcf_screen_kernel<12> : kcf_screen_kernel<10>);
+    const size_t smem = KCF_WPC * sizeof(KcfWarpSmem);
+    void (*kern)(KcfScreenParams, KcfTableGeom);
+    if (d_counts) kern = db->geom.S == 13 ? kcf_screen_kernel<13, true> : (db->geom.S == 12 ? kcf_screen_kernel<12, true> : kcf_screen_kernel<10, true>);
+    else kern = db->geom.S == 13 ? kcf_screen_kernel<13, false> : (db->geom.S == 12 ? kcf_screen_kernel<12, false> : kcf_screen_kernel<10, false>);
     KCF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    KCF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
+    KCF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * KCF_WPC, smem));
     const uint64_t n = tile_end - tile_begin;
-    const unsigned grid = (unsigned)std::min<uint64_t>(n, (uint64_t)ctx->sm_count * std::max(per_sm, 1));
-    if (grid) kern<<<grid, 32, smem, ctx->stream>>>(p, db->geom);
+    if (const char *e = getenv("KCF_TUNE_WARPS")) per_sm = std::min(per_sm, std::max(atoi(e) / KCF_WPC, 1)); // occupancy experiments
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + KCF_WPC - 1) / KCF_WPC, (uint64_t)ctx->sm_count * std::max(per_sm, 1));
+    if (grid) kern<<<grid, 32 * KCF_WPC, smem, ctx->stream>>>(p, db->geom);
     KCF_CUDA(ctx, cudaGetLastError());
     return KCF_OK;
 }
