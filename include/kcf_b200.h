@@ -135,6 +135,14 @@ int kcf_db_count(kcf_ctx *ctx, kcf_db *db, const char *kmers_ascii, uint64_t n, 
  * newlines included; line_bases / line_width / seq_len are the .faidx columns. */
 int kcf_ref_add(kcf_ctx *ctx, const uint8_t *fasta_seq_bytes, uint64_t n_bytes, uint32_t line_bases,
                 uint32_t line_width, uint64_t seq_len, int *seq_id_out);
+/* Same without the final synchronisation: the copy is queued on the context's copy stream (it overlaps the 2-bit
+ * packing of the previous sequence and any screening already queued), and `fasta_seq_bytes` must stay valid and
+ * unmodified until kcf_ref_sync, kcf_plan_fetch or kcf_screen returns.  Lets a host upload chromosome i+1 while
+ * chromosome i is being screened (the reference walks the sequences one after the other, GetVariants.java:117-121). */
+int kcf_ref_add_async(kcf_ctx *ctx, const uint8_t *fasta_seq_bytes, uint64_t n_bytes, uint32_t line_bases,
+                      uint32_t line_width, uint64_t seq_len, int *seq_id_out);
+int kcf_ref_sync(kcf_ctx *ctx);
+/* Forget all sequences (their device memory is kept for reuse by later kcf_ref_add calls). */
 int kcf_ref_clear(kcf_ctx *ctx);
 
 /* ---- screening: replaces GetVariants.java:126-159 ---------------------------------------- */

@@ -50,6 +50,8 @@ SYMBOLS = {
     "kcf_set_minimizer_length": (C.c_int, [_P, C.c_int]),
     "kcf_db_count": (C.c_int, [_P, _P, _P, C.c_uint64, _P]),
     "kcf_ref_add": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_int)]),
+    "kcf_ref_add_async": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_int)]),
+    "kcf_ref_sync": (C.c_int, [_P]),
     "kcf_ref_clear": (C.c_int, [_P]),
     "kcf_screen": (C.c_int, [_P, _P, _P, C.c_uint64, _P, C.c_uint64, C.c_int32, C.POINTER(C.c_double), _P]),
     "kcf_plan_create": (C.c_int, [_P, C.c_int32, _P, C.c_uint64, _P, C.c_uint64, C.POINTER(_P)]),

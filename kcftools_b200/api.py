@@ -92,6 +92,19 @@ class Context:
         self.n_seqs += 1
         return sid.value
 
+    def ref_add_async(self, seq_bytes: np.ndarray, line_bases: int, line_width: int, seq_len: int) -> int:
+        """as ref_add, but only queued: `seq_bytes` (ideally pinned, see `pinned`) must stay untouched until ref_sync /
+        Plan.fetch / screen returns."""
+        a = seq_bytes
+        assert a.dtype == np.uint8 and a.flags.c_contiguous
+        sid = C.c_int()
+        self._check(self._lib.kcf_ref_add_async(self._h, _ptr(a), a.size, line_bases, line_width, seq_len, C.byref(sid)))
+        self.n_seqs += 1
+        return sid.value
+
+    def ref_sync(self):
+        self._check(self._lib.kcf_ref_sync(self._h))
+
     def ref_clear(self):
         self._check(self._lib.kcf_ref_clear(self._h))
         self.n_seqs = 0

@@ -56,6 +56,12 @@ extern "C" int kcf_init(int device, kcf_ctx **out)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&ctx->raw_free[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->h2d_done[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->plan_ready, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_flags, 64 * sizeof(uint32_t));
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e != cudaSuccess) {
@@ -67,17 +73,44 @@ extern "C" int kcf_init(int device, kcf_ctx **out)
     return KCF_OK;
 }
 
+// device memory of cleared sequences is kept and handed out again: a host that re-screens (or a cohort run that swaps
+// references) does not pay cudaMalloc / cudaFree per sequence
+static void *kcf_pool_get(kcf_ctx *ctx, size_t bytes)
+{
+    int best = -1;
+    for (size_t i = 0; i < ctx->pool.size(); ++i)
+        if (ctx->pool[i].bytes >= bytes && ctx->pool[i].bytes <= bytes + bytes / 8 + 4096 &&
+            (best < 0 || ctx->pool[i].bytes < ctx->pool[best].bytes))
+            best = (int)i;
+    if (best >= 0) {
+        void *p = ctx->pool[best].p;
+        ctx->pool.erase(ctx->pool.begin() + best);
+        return p;
+    }
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        // give the pooled blocks back to the driver and try once more
+        for (auto &b : ctx->pool) cudaFree(b.p);
+        ctx->pool.clear();
+        if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+    }
+    return p;
+}
+
 extern "C" int kcf_ref_clear(kcf_ctx *ctx)
 {
     if (!ctx) return KCF_ERR_ARG;
     cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamSynchronize(ctx->stream);
     for (auto &s : ctx->seqs) {
-        if (s.codes) cudaFree(s.codes);
-        if (s.valid) cudaFree(s.valid);
+        const size_t n_words = (size_t)((s.len + 31) / 32 + 2);
+        if (s.codes) ctx->pool.push_back({s.codes, n_words * 8});
+        if (s.valid) ctx->pool.push_back({s.valid, n_words * 4});
     }
     ctx->seqs.clear();
     ctx->seqs_dirty = true;
+    ctx->seqs_uploaded = 0;
     return KCF_OK;
 }
 
@@ -85,11 +118,19 @@ extern "C" void kcf_shutdown(kcf_ctx *ctx)
 {
     if (!ctx) return;
     kcf_ref_clear(ctx);
+    for (auto &b : ctx->pool) cudaFree(b.p);
     if (ctx->d_seqs) cudaFree(ctx->d_seqs);
-    if (ctx->d_raw) cudaFree(ctx->d_raw);
+    if (ctx->h_seqs) cudaFreeHost(ctx->h_seqs);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->d_raw[i]) cudaFree(ctx->d_raw[i]);
+        if (ctx->raw_free[i]) cudaEventDestroy(ctx->raw_free[i]);
+        if (ctx->h2d_done[i]) cudaEventDestroy(ctx->h2d_done[i]);
+    }
+    if (ctx->plan_ready) cudaEventDestroy(ctx->plan_ready);
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     for (int i = 0; i < 4; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -183,8 +224,8 @@ kcf_pack_kernel(const uint8_t *__restrict__ raw, uint64_t n_bytes_padded, uint32
     valid[w] = v;
 }
 
-extern "C" int kcf_ref_add(kcf_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes, uint32_t line_bases, uint32_t line_width,
-                           uint64_t seq_len, int *seq_id_out)
+extern "C" int kcf_ref_add_async(kcf_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes, uint32_t line_bases, uint32_t line_width,
+                                 uint64_t seq_len, int *seq_id_out)
 {
     if (!ctx || (!bytes && n_bytes)) return KCF_ERR_ARG;
     if (seq_len >= (1ULL << 31)) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "sequence length %llu exceeds the reference's int range", (unsigned long long)seq_len);
@@ -201,39 +242,85 @@ extern "C" int kcf_ref_add(kcf_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes,
     s.line_bases = line_bases;
     s.line_width = line_width;
     const uint64_t n_words = (seq_len + 31) / 32 + 2; // +2: the tile loader may read one word past the end
-    KCF_CUDA(ctx, cudaMalloc(&s.codes, n_words * 8));
-    cudaError_t e = cudaMalloc(&s.valid, n_words * 4);
-    if (e != cudaSuccess) { cudaFree(s.codes); return kcf_fail(ctx, KCF_ERR_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); }
-    cudaMemsetAsync(s.codes, 0, n_words * 8, ctx->stream);
-    cudaMemsetAsync(s.valid, 0, n_words * 4, ctx->stream);
+    s.codes = (uint32_t *)kcf_pool_get(ctx, n_words * 8);
+    s.valid = (uint32_t *)kcf_pool_get(ctx, n_words * 4);
+    if (!s.codes || !s.valid) {
+        if (s.codes) cudaFree(s.codes);
+        if (s.valid) cudaFree(s.valid);
+        return kcf_fail(ctx, KCF_ERR_NOMEM, "device memory for a %llu-base sequence", (unsigned long long)seq_len);
+    }
+    // the pack kernel writes every word that holds a base; only the slack words need clearing
+    const uint64_t full = seq_len / 32;
+    cudaMemsetAsync(s.codes + 2 * full, 0, (n_words - full) * 8, ctx->stream);
+    cudaMemsetAsync(s.valid + full, 0, (n_words - full) * 4, ctx->stream);
     if (seq_len > 0) {
+        const int b = ctx->raw_next;
+        ctx->raw_next ^= 1;
         const uint64_t padded = (n_bytes + 15) & ~15ULL;
-        if (ctx->d_raw_cap < padded + 16) {
-            cudaStreamSynchronize(ctx->stream);
-            if (ctx->d_raw) cudaFree(ctx->d_raw);
-            ctx->d_raw = nullptr;
-            ctx->d_raw_cap = 0;
-            e = cudaMalloc(&ctx->d_raw, padded + 16);
-            if (e != cudaSuccess) { cudaFree(s.codes); cudaFree(s.valid); return kcf_fail(ctx, KCF_ERR_NOMEM, "cudaMalloc(raw): %s", cudaGetErrorString(e)); }
-            ctx->d_raw_cap = padded + 16;
+        if (ctx->d_raw_cap[b] < padded + 16) {
+            cudaEventSynchronize(ctx->raw_free[b]); // the pack kernel that last read this buffer
+            if (ctx->d_raw[b]) cudaFree(ctx->d_raw[b]);
+            ctx->d_raw[b] = nullptr;
+            ctx->d_raw_cap[b] = 0;
+            const uint64_t cap = padded + padded / 16 + 16;
+            cudaError_t e = cudaMalloc(&ctx->d_raw[b], cap);
+            if (e != cudaSuccess) {
+                ctx->pool.push_back({s.codes, n_words * 8});
+                ctx->pool.push_back({s.valid, n_words * 4});
+                return kcf_fail(ctx, KCF_ERR_NOMEM, "cudaMalloc(raw): %s", cudaGetErrorString(e));
+            }
+            ctx->d_raw_cap[b] = cap;
         }
-        e = cudaMemcpyAsync(ctx->d_raw, bytes, n_bytes, cudaMemcpyHostToDevice, ctx->stream);
-        if (e != cudaSuccess) { cudaFree(s.codes); cudaFree(s.valid); return kcf_fail(ctx, KCF_ERR_CUDA, "H2D: %s", cudaGetErrorString(e)); }
+        cudaStreamWaitEvent(ctx->copy_stream, ctx->raw_free[b], 0);
+        cudaError_t e = cudaMemcpyAsync(ctx->d_raw[b], bytes, n_bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->h2d_done[b], ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->h2d_done[b], 0);
+        if (e != cudaSuccess) {
+            ctx->pool.push_back({s.codes, n_words * 8});
+            ctx->pool.push_back({s.valid, n_words * 4});
+            return kcf_fail(ctx, KCF_ERR_CUDA, "H2D: %s", cudaGetErrorString(e));
+        }
         // shared bytes: the raw span of PACK_BASES bases plus alignment slack
         const uint64_t lines = PACK_BASES / line_bases + 2;
         uint64_t smem = PACK_BASES + lines * (line_width - line_bases) + 48;
         smem = (smem + 15) & ~15ULL;
-        if (smem > 200 * 1024) { cudaFree(s.codes); cudaFree(s.valid); return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "line geometry needs %llu B of shared memory", (unsigned long long)smem); }
+        if (smem > 200 * 1024) {
+            ctx->pool.push_back({s.codes, n_words * 8});
+            ctx->pool.push_back({s.valid, n_words * 4});
+            return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "line geometry needs %llu B of shared memory", (unsigned long long)smem);
+        }
         if (smem > 48 * 1024) cudaFuncSetAttribute(kcf_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const unsigned grid = (unsigned)((seq_len + PACK_BASES - 1) / PACK_BASES);
-        kcf_pack_kernel<<<grid, PACK_THREADS, smem, ctx->stream>>>(ctx->d_raw, padded, line_bases, line_width, seq_len,
+        kcf_pack_kernel<<<grid, PACK_THREADS, smem, ctx->stream>>>(ctx->d_raw[b], padded, line_bases, line_width, seq_len,
                                                                    s.codes, s.valid, (uint32_t)smem);
         e = cudaGetLastError();
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); // the caller may reuse `bytes` after return
-        if (e != cudaSuccess) { cudaFree(s.codes); cudaFree(s.valid); return kcf_fail(ctx, KCF_ERR_CUDA, "pack kernel: %s", cudaGetErrorString(e)); }
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->raw_free[b], ctx->stream);
+        if (e != cudaSuccess) {
+            cudaStreamSynchronize(ctx->stream);
+            ctx->pool.push_back({s.codes, n_words * 8});
+            ctx->pool.push_back({s.valid, n_words * 4});
+            return kcf_fail(ctx, KCF_ERR_CUDA, "pack kernel: %s", cudaGetErrorString(e));
+        }
     }
     ctx->seqs.push_back(s);
     ctx->seqs_dirty = true;
     if (seq_id_out) *seq_id_out = (int)ctx->seqs.size() - 1;
     return KCF_OK;
+}
+
+extern "C" int kcf_ref_sync(kcf_ctx *ctx)
+{
+    if (!ctx) return KCF_ERR_ARG;
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    KCF_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    KCF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KCF_OK;
+}
+
+extern "C" int kcf_ref_add(kcf_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes, uint32_t line_bases, uint32_t line_width,
+                           uint64_t seq_len, int *seq_id_out)
+{
+    int rc = kcf_ref_add_async(ctx, bytes, n_bytes, line_bases, line_width, seq_len, seq_id_out);
+    if (rc != KCF_OK) return rc;
+    return kcf_ref_sync(ctx); // the caller may reuse `bytes` after return
 }

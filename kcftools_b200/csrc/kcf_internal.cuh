@@ -129,10 +129,24 @@ struct kcf_ctx {
     std::string err;
     std::vector<KcfSeqHost> seqs;
     KcfSeqDev *d_seqs = nullptr; // mirror of seqs on the device
+    KcfSeqDev *h_seqs = nullptr; // pinned staging of the same (entries are append-only between two kcf_ref_clear calls)
     size_t d_seqs_cap = 0;
+    size_t seqs_uploaded = 0;
     bool seqs_dirty = false;
-    uint8_t *d_raw = nullptr;    // staging for raw FASTA bytes
-    size_t d_raw_cap = 0;
+    // raw FASTA bytes are staged through two device buffers: the H2D copy of one sequence (copy stream) overlaps the
+    // 2-bit packing of the previous one and whatever screening is queued on the main stream
+    cudaStream_t copy_stream = nullptr;
+    uint8_t *d_raw[2] = {nullptr, nullptr};
+    size_t d_raw_cap[2] = {0, 0};
+    cudaEvent_t raw_free[2] = {nullptr, nullptr}; // pack kernel done: staging buffer reusable
+    cudaEvent_t h2d_done[2] = {nullptr, nullptr};
+    cudaEvent_t plan_ready = nullptr;             // window descriptors uploaded on the copy stream
+    int raw_next = 0;
+    struct PoolBlock {
+        void *p;
+        size_t bytes;
+    };
+    std::vector<PoolBlock> pool; // device blocks of cleared sequences, reused by later kcf_ref_add calls
     double load_factor = 0.4;
     int minimizer_len = 0;       // 0 = chosen from the database size
     int sm_count = 148;

@@ -576,28 +576,36 @@ extern "C" int kcf_measure_random_sector_gbps(kcf_ctx *ctx, uint64_t n_bytes, ui
 }
 
 // ---- host side: plans ---------------------------------------------------------------------------
+// bring the device-side sequence table up to date, stream-ordered and without a host synchronisation (a host that
+// uploads one chromosome after the other and screens each as it arrives must not stall on earlier work)
 static int kcf_sync_seqs(kcf_ctx *ctx)
 {
-    if (!ctx->seqs_dirty && ctx->d_seqs) return KCF_OK;
-    const size_t n = std::max<size_t>(ctx->seqs.size(), 1);
-    if (ctx->d_seqs_cap < n) {
-        if (ctx->d_seqs) {
-            cudaStreamSynchronize(ctx->stream);
-            cudaFree(ctx->d_seqs);
-            ctx->d_seqs = nullptr;
+    const size_t n = ctx->seqs.size();
+    if (ctx->d_seqs_cap < std::max<size_t>(n, 1)) {
+        const size_t cap = std::max<size_t>(4096, 2 * n);
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->d_seqs) cudaFree(ctx->d_seqs);
+        if (ctx->h_seqs) cudaFreeHost(ctx->h_seqs);
+        ctx->d_seqs = nullptr;
+        ctx->h_seqs = nullptr;
+        ctx->d_seqs_cap = 0;
+        KCF_CUDA(ctx, cudaMalloc(&ctx->d_seqs, cap * sizeof(KcfSeqDev)));
+        KCF_CUDA(ctx, cudaHostAlloc(&ctx->h_seqs, cap * sizeof(KcfSeqDev), cudaHostAllocDefault));
+        ctx->d_seqs_cap = cap;
+        ctx->seqs_uploaded = 0;
+    }
+    if (n < ctx->seqs_uploaded) ctx->seqs_uploaded = 0; // cleared since (kcf_ref_clear synchronises)
+    if (n > ctx->seqs_uploaded) {
+        for (size_t i = ctx->seqs_uploaded; i < n; ++i) {
+            ctx->h_seqs[i].codes = ctx->seqs[i].codes;
+            ctx->h_seqs[i].valid = ctx->seqs[i].valid;
+            ctx->h_seqs[i].len = (uint32_t)ctx->seqs[i].len;
+            ctx->h_seqs[i]._pad = 0;
         }
-        KCF_CUDA(ctx, cudaMalloc(&ctx->d_seqs, n * sizeof(KcfSeqDev)));
-        ctx->d_seqs_cap = n;
+        KCF_CUDA(ctx, cudaMemcpyAsync(ctx->d_seqs + ctx->seqs_uploaded, ctx->h_seqs + ctx->seqs_uploaded,
+                                      (n - ctx->seqs_uploaded) * sizeof(KcfSeqDev), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->seqs_uploaded = n;
     }
-    std::vector<KcfSeqDev> h(n);
-    for (size_t i = 0; i < ctx->seqs.size(); ++i) {
-        h[i].codes = ctx->seqs[i].codes;
-        h[i].valid = ctx->seqs[i].valid;
-        h[i].len = (uint32_t)ctx->seqs[i].len;
-        h[i]._pad = 0;
-    }
-    KCF_CUDA(ctx, cudaMemcpyAsync(ctx->d_seqs, h.data(), n * sizeof(KcfSeqDev), cudaMemcpyHostToDevice, ctx->stream));
-    KCF_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // h goes out of scope
     ctx->seqs_dirty = false;
     return KCF_OK;
 }
@@ -680,13 +688,14 @@ extern "C" int kcf_plan_create(kcf_ctx *ctx, int32_t kmer_length, const kcf_wind
     PL_CUDA(cudaMalloc(&plan->d_tile_sum, std::max<uint64_t>(tiles, 1) * sizeof(KcfGap) + 8)); // +8: the tile counter lives at the end
     PL_CUDA(cudaMalloc(&plan->d_out, std::max<uint64_t>(n_wins, 1) * sizeof(kcf_result_t)));
     if (rc == KCF_OK && n_wins) {
-        PL_CUDA(cudaMemcpyAsync(plan->d_wins, wins, n_wins * sizeof(kcf_window_t), cudaMemcpyHostToDevice, ctx->stream));
-        PL_CUDA(cudaMemcpyAsync(plan->d_segs, segs, n_segs * sizeof(kcf_segment_t), cudaMemcpyHostToDevice, ctx->stream));
-        PL_CUDA(cudaMemcpyAsync(plan->d_seg_off, seg_off.data(), n_segs * 4, cudaMemcpyHostToDevice, ctx->stream));
-        PL_CUDA(cudaMemcpyAsync(plan->d_win_len, win_len.data(), n_wins * 4, cudaMemcpyHostToDevice, ctx->stream));
+        // descriptors travel on the copy stream: creating a plan never waits for kernels queued on the main stream
+        PL_CUDA(cudaMemcpyAsync(plan->d_wins, wins, n_wins * sizeof(kcf_window_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+        PL_CUDA(cudaMemcpyAsync(plan->d_segs, segs, n_segs * sizeof(kcf_segment_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+        PL_CUDA(cudaMemcpyAsync(plan->d_seg_off, seg_off.data(), n_segs * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+        PL_CUDA(cudaMemcpyAsync(plan->d_win_len, win_len.data(), n_wins * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
     }
-    if (rc == KCF_OK) PL_CUDA(cudaMemcpyAsync(plan->d_tile_first, tile_first.data(), (n_wins + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    if (rc == KCF_OK) PL_CUDA(cudaStreamSynchronize(ctx->stream)); // host vectors go out of scope; caller may free wins/segs
+    if (rc == KCF_OK) PL_CUDA(cudaMemcpyAsync(plan->d_tile_first, tile_first.data(), (n_wins + 1) * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (rc == KCF_OK) PL_CUDA(cudaStreamSynchronize(ctx->copy_stream)); // host vectors go out of scope; caller may free wins/segs
 #undef PL_CUDA
     if (rc != KCF_OK) {
         kcf_plan_destroy(plan);
