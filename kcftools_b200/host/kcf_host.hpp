@@ -8,7 +8,6 @@
 //   KCF text      Data/KCFHeader.java:291-330, Data/Window.java:125-214, Data/Data.java:120-132, Utils/Configs.java:14-37
 #pragma once
 #include <cstdint>
-#include <map>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -21,18 +20,22 @@ namespace kcfh {
 struct FatalError : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
+// picocli usage errors (unknown / missing option): message + usage on stderr, exit status 2
+struct UsageError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
 
 namespace Logger {
 void info(const std::string &cls, const std::string &msg);
 void warning(const std::string &cls, const std::string &msg);
 [[noreturn]] void error(const std::string &cls, const std::string &msg);
-void set_quiet(bool q);
 } // namespace Logger
 
 // ---- Java text formatting ----------------------------------------------------------------------
 std::string java_double_to_string(double v); // Double.toString
 std::string java_float_to_string(float v);   // Float.toString
 std::string java_format_2f(double v);        // String.format("%.2f", v): HALF_UP on the shortest decimal digits
+int32_t java_string_hash(const std::string &s); // String.hashCode (ASCII / Latin-1 input)
 
 // ---- FastaIndex -------------------------------------------------------------------------------------
 struct FastaIndexEntry {
@@ -48,6 +51,7 @@ class FastaIndex {
     explicit FastaIndex(const std::string &fastaPath); // builds <fasta>.faidx when missing or older, then mmaps the file
     ~FastaIndex();
     FastaIndex(const FastaIndex &) = delete;
+    FastaIndex &operator=(const FastaIndex &) = delete;
     const std::vector<FastaIndexEntry> &entries() const { return entries_; }
     const FastaIndexEntry *getEntry(const std::string &name) const;
     int getSequenceLength(const std::string &name) const; // Logger.error when absent
@@ -81,7 +85,9 @@ class GTF {
     Loci getLoci(const std::string &featureID) const; // Logger.error when unknown
     // the merged, sorted loci GTF.getFasta concatenates; empty => the reference returns null (fatal in processWindow)
     std::vector<Loci> mergedLoci(const std::string &featureID, bool isGene) const;
-    static std::vector<Loci> mergeOverlappingLoci(std::vector<Loci> loci);
+    static std::vector<Loci> mergeOverlappingLoci(std::vector<Loci> lociInHashSetOrder);
+    // iteration order of a java.util.HashSet<Loci> filled in the given order (ties of the stable sorts depend on it)
+    static std::vector<Loci> javaHashSetOrder(const std::vector<Loci> &insertionOrder);
 
   private:
     struct Feature {
@@ -91,7 +97,7 @@ class GTF {
         std::string type, id;
     };
     std::vector<std::string> getChildren(const std::string &parent) const;
-    void addVertex(const std::string &v);
+    int addVertex(const std::string &v);
     void addEdge(const std::string &from, const std::string &to);
     std::unordered_map<std::string, int> vertices_;                // id -> index
     std::vector<std::vector<std::string>> children_;               // outgoing edges in insertion order
@@ -104,18 +110,20 @@ struct Window {
     std::string windowId, sequenceName;
     int start = 0, end = 0;
     std::vector<kcf_segment_t> segments; // what Window.getFasta / GTF.getFasta would concatenate
+    bool noFasta = false;                 // GTF.getFasta returned null: fatal when the window is processed
 };
 
 // ---- the plugin -------------------------------------------------------------------------------------
 struct GetVariantsOptions {             // GetVariants.java:21-61, same names and defaults
     std::string refFasta, kmcDBprefix, outFile, sampleName, featureType, gtfFile;
+    bool hasGtf = false;
     int nThreads = 2;
     bool loadMemory = false;
     double innerDistanceWeight = 0.3, tailDistanceWeight = 0.3, kmerRatioWeight = 0.4;
     int windowSize = 0;
     int minKmerCount = 1;
     int stepSize = 0;
-    int device = 0;                     // extension: CUDA ordinal
+    int device = 0;                     // extension: CUDA ordinal (--device)
     std::string commandLine;            // for ##CMD
 };
 
@@ -123,11 +131,11 @@ std::vector<Window> getWindows(const GetVariantsOptions &o, const FastaIndex &in
                                const std::string &sequenceName, int kmerSize); // GetVariants.java:278-352
 void validateCMD(const GetVariantsOptions &o);                                 // GetVariants.java:357-386
 std::string cleanSampleName(const std::string &s);                             // GetVariants.java:392-401
-std::string kcfHeaderText(const GetVariantsOptions &o, const FastaIndex &index, int kmerSize, int totalWindows,
-                          const std::string &date);                            // KCFHeader.java:291-330
+std::string kcfHeaderText(const GetVariantsOptions &o, const std::string &sample, const FastaIndex &index, int kmerSize,
+                          int totalWindows, const std::string &date);          // KCFHeader.java:291-330
 std::string kcfRowText(const Window &w, const kcf_result_t &r, const double weights[3]); // Window.java:125-138, Data.java:120-132
 double computeScore(const kcf_result_t &r, const double weights[3]);          // Data.java:95-107
-int getVariations(GetVariantsOptions o);                                       // GetVariants.java:92-183; returns 0 or throws FatalError
-int cliMain(int argc, const char *const *argv);                                // KCFTOOLS.main + picocli parsing for getVariations
+int getVariations(GetVariantsOptions o);                                       // GetVariants.java:92-183; 0 or throws
+int cliMain(int argc, const char *const *argv);                                // KCFTOOLS.main + picocli parsing
 
 } // namespace kcfh

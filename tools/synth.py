@@ -94,7 +94,7 @@ def fasta_record(codes: torch.Tensor, name: str, line: int = 60, lower: list[tup
     dev = codes.device
     seq = _ASCII.to(dev)[codes.long()]
     for (s, l) in (lower or []):
-        seq[s:s + l] += 32
+        seq[s:s + l] |= 32  # overlapping intervals must not shift a byte twice
     for (s, l) in (n_runs or []):
         seq[s:s + l] = 78
     for (s, l) in (other or []):
