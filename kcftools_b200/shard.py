@@ -1,0 +1,74 @@
+"""Multi-GPU host logic: one process per GPU, windows sharded, database replicated.
+
+Windows are the reference's unit of parallelism (one pool task per window, Plugins/GetVariants.java:138-150); they
+share bases (k-1 at tiling boundaries) but never results, so the path shards without a data-path collective: every
+rank screens a contiguous range of the window list, balanced on the number of positions, and the per-window rows are
+concatenated in window order (the KCF writer wants .faidx order, GetVariants.java:169-179).  The only communication
+is the gather of the 48-byte result rows.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ._lib import RESULT_DTYPE, SEGMENT_DTYPE, WINDOW_DTYPE
+
+
+def window_lengths(wins: np.ndarray, segs: np.ndarray) -> np.ndarray:
+    """positions per window = Σ segment lengths (what the screening kernel walks)"""
+    seg_len = segs["len"].astype(np.int64)
+    csum = np.concatenate([[0], np.cumsum(seg_len)])
+    first = wins["first_seg"].astype(np.int64)
+    return csum[first + wins["n_segs"].astype(np.int64)] - csum[first]
+
+
+def partition(lengths: np.ndarray, world: int) -> list[tuple[int, int]]:
+    """contiguous window ranges [begin, end) per rank with near-equal Σ length; every window in exactly one range"""
+    n = int(lengths.size)
+    csum = np.concatenate([[0], np.cumsum(lengths.astype(np.int64))])
+    total = int(csum[-1])
+    cuts = [0]
+    for r in range(1, world):
+        target = total * r // world
+        c = int(np.searchsorted(csum, target, side="left"))
+        cuts.append(min(max(c, cuts[-1]), n))
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def local_slice(wins: np.ndarray, segs: np.ndarray, begin: int, end: int) -> tuple[np.ndarray, np.ndarray]:
+    """window / segment arrays of one rank's range, segment indices re-based"""
+    w = np.ascontiguousarray(wins[begin:end]).astype(WINDOW_DTYPE, copy=True)
+    if w.size == 0:
+        return w, np.zeros(0, SEGMENT_DTYPE)
+    s0 = int(w["first_seg"][0])
+    s1 = int(w["first_seg"][-1]) + int(w["n_segs"][-1])
+    w["first_seg"] -= np.uint32(s0)
+    return w, np.ascontiguousarray(segs[s0:s1])
+
+
+def screen_sharded(screen_fn, wins: np.ndarray, segs: np.ndarray, group=None) -> np.ndarray:
+    """screen_fn(wins, segs) -> RESULT_DTYPE rows for the given windows (Context.screen bound to a database on this
+    rank's GPU).  Returns all rows, in window order, on every rank."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return screen_fn(wins, segs)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    ranges = partition(window_lengths(wins, segs), world)
+    b, e = ranges[rank]
+    lw, ls = local_slice(wins, segs, b, e)
+    mine = screen_fn(lw, ls) if lw.size else np.zeros(0, RESULT_DTYPE)
+    assert mine.dtype == RESULT_DTYPE and mine.size == e - b
+    # rows are plain bytes: gather them as uint8 tensors of the (known) per-rank sizes
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    parts = [torch.empty((re - rb) * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev) for (rb, re) in ranges]
+    src = torch.from_numpy(mine.view(np.uint8).copy()).to(dev)
+    most = max(p.numel() for p in parts)
+    # all_gather wants equal shapes: pad to the largest shard
+    padded = torch.zeros(most, dtype=torch.uint8, device=dev)
+    padded[:src.numel()] = src
+    bufs = [torch.empty(most, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(bufs, padded, group=group)
+    out = np.concatenate([bufs[r][:parts[r].numel()].cpu().numpy() for r in range(world)]).view(RESULT_DTYPE)
+    return out

@@ -1,0 +1,69 @@
+"""N > 1 host logic on CPU: 2-rank gloo job, windows sharded, rows gathered in window order.  The per-rank compute is
+the CPU oracle here (no GPU in this test); on the GPU box the same function wraps Context.screen (bench.py, test_gpu_*)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from common import Scenario, assert_results_equal
+from kcftools_b200 import shard
+from kcftools_b200.api import fixed_windows
+
+
+def test_partition_is_contiguous_balanced_and_complete():
+    rng = np.random.default_rng(3)
+    for n, world in [(0, 2), (1, 4), (7, 8), (1000, 2), (1000, 3), (18012, 8)]:
+        lengths = rng.integers(31, 50_001, n)
+        ranges = shard.partition(lengths, world)
+        assert len(ranges) == world and ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:])) and all(b <= e for b, e in ranges)
+        if n >= 100 * world:
+            sums = [int(lengths[b:e].sum()) for b, e in ranges]
+            assert max(sums) - min(sums) <= 2 * int(lengths.max())
+
+
+def test_local_slice_rebases_segments():
+    from common import windows_from_lists
+    wins, segs = windows_from_lists([[(0, 0, 10)], [(0, 5, 7), (1, 0, 9)], [(1, 3, 4)], [(0, 1, 2), (0, 9, 2), (1, 1, 1)]])
+    assert list(shard.window_lengths(wins, segs)) == [10, 16, 4, 5]
+    w, s = shard.local_slice(wins, segs, 1, 3)
+    assert list(w["first_seg"]) == [0, 2] and list(w["n_segs"]) == [2, 1] and s.size == 3 and tuple(s[0]) == (0, 5, 7)
+    w, s = shard.local_slice(wins, segs, 2, 2)
+    assert w.size == 0 and s.size == 0
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from oracle import binding as ob
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sc = Scenario(seq_lens=(60_000, 23_457, 40), seed=4, n_bins=16)
+    wins, segs, *_ = fixed_windows(sc.seq_lens, 3000, 0, 31)
+    odb = ob.OracleKMC(sc.kmc.pre, sc.kmc.suf)
+    calls = []
+
+    def screen(w, s):
+        calls.append(int(w.size))
+        rc, res = odb.screen(sc.seqs(), w, s, threads=2)
+        assert rc == 0
+        return res
+    got = shard.screen_sharded(screen, wins, segs)
+    rc, want = odb.screen(sc.seqs(), wins, segs, threads=2)
+    assert_results_equal(got, want)
+    assert len(calls) == 1 and 0 < calls[0] < wins.size  # this rank screened only its share
+    np.save(os.path.join(out_dir, f"rank{rank}.npy"), got.view(np.uint8))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharded_screen(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a = np.load(tmp_path / "rank0.npy")
+    b = np.load(tmp_path / "rank1.npy")
+    assert (a == b).all() and a.size > 0
