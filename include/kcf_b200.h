@@ -95,6 +95,7 @@ typedef struct kcf_db_info_t {
     int64_t table_bytes;        /* HBM bytes of the lookup structure */
     int64_t n_buckets;          /* 128-byte table lines */
     double load_seconds;        /* wall time of the open call */
+    int64_t elsewhere_kmers;    /* placement 1: reachable records whose home line belongs to another rank's slice */
 } kcf_db_info_t;
 
 /* ---- context ------------------------------------------------------------------------- */
@@ -111,8 +112,8 @@ void kcf_host_free(kcf_ctx *ctx, void *p);
 
 /* ---- database: replaces `new KMC(prefix, inMemory)` (KMC.java:56-78) ------------------- */
 /* placement: 0 = whole database resident on this context's GPU (replicated across contexts);
- *            1 = this context keeps only the slice rank/world of the mixed-key space
- *                (prefix partition; see kcf_db_open_part). */
+ *            1 = this context keeps only its slice of the table's line space (kcf_set_partition; screened through
+ *                the kcf_xchg_* calls below). */
 int kcf_db_open(kcf_ctx *ctx, const char *kmc_prefix, int placement, kcf_db **out);
 /* Same, from the byte images of the two files (what the reference mmaps, KMC.java:112, 173-189). */
 int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_len, const uint8_t *suf, uint64_t suf_len,
@@ -163,6 +164,29 @@ int kcf_plan_stats(kcf_plan *plan, uint64_t *n_tiles, uint64_t *n_positions, uin
 /* Per-valid-k-mer counts of one window of the last run (debug / parity; runs a separate pass). */
 int kcf_window_counts(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, uint64_t window, int32_t *counts_out, uint64_t cap,
                       uint64_t *n_out);
+
+/* ---- partitioned database (placement 1): for a database beyond one GPU's HBM ---------------------------------------
+ * The line space of the table is cut in `world` equal ranges; the context opened after kcf_set_partition(rank, world)
+ * keeps the records whose home line falls in range `rank` (kcf_db_info_t.elsewhere_kmers counts the others).  A rank
+ * can then not answer its own k-mers: screening becomes extract -> all-to-all -> lookup -> all-to-all -> fold, with
+ * the two all-to-all steps done by the HOST over caller-owned device buffers (NCCL; kcftools_b200/partitioned.py).
+ * This is the one place where the getVariations path has a real exchange step; the reference has no
+ * counterpart (its database always lives in one JVM, KMC.java:56-78). */
+int kcf_set_partition(kcf_ctx *ctx, int rank, int world);
+/* Requester, step 1: canonical k-mers of tiles [tile_begin, tile_end) of the plan (a tile = 2048 window positions,
+ * kcf_plan_stats), grouped by owning rank.  d_keys_out (uint64), d_homes_out (uint32: global home line), d_src_out
+ * (uint32: position inside the batch) are DEVICE buffers of `cap` entries (cap >= positions of the batch is always
+ * enough); send_counts[world] (host) receives how many consecutive entries go to each rank. */
+int kcf_xchg_extract(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, uint64_t tile_begin, uint64_t tile_end, int world,
+                     void *d_keys_out, void *d_homes_out, void *d_src_out, uint64_t cap, uint64_t *send_counts);
+/* Owner, step 2: KMC.getCount (KMC.java:292-326) of n received k-mers against this rank's slice -> uint32 counts (device). */
+int kcf_xchg_lookup(kcf_ctx *ctx, kcf_db *db, const void *d_keys, const void *d_homes, uint64_t n, void *d_counts_out);
+/* Requester, step 3: the counts of the n entries sent in step 1 (same order; d_src = step 1's d_src_out) -> gap
+ * summaries of tiles [tile_begin, tile_end) (GetVariants.java:217-252). */
+int kcf_xchg_fold(kcf_ctx *ctx, kcf_plan *plan, uint64_t tile_begin, uint64_t tile_end, const void *d_counts_back,
+                  const void *d_src, uint64_t n, int32_t min_count);
+/* Requester, last: scores and rows from the tile summaries (Data.java:70-107); then kcf_plan_fetch. */
+int kcf_plan_finalize(kcf_ctx *ctx, kcf_plan *plan, const double w[3]);
 
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* Random 32-byte-sector gather bandwidth of this GPU (the random-access roofline of SURVEY §8(d)):

@@ -30,7 +30,8 @@ class DbInfo(C.Structure):
                 ("counter_size", C.c_int32), ("both_strands", C.c_int32), ("min_count", C.c_int32),
                 ("max_count", C.c_int32), ("n_bins", C.c_int32), ("total_kmers", C.c_int64),
                 ("resident_kmers", C.c_int64), ("unreachable_kmers", C.c_int64), ("stash_kmers", C.c_int64),
-                ("table_bytes", C.c_int64), ("n_buckets", C.c_int64), ("load_seconds", C.c_double)]
+                ("table_bytes", C.c_int64), ("n_buckets", C.c_int64), ("load_seconds", C.c_double),
+                ("elsewhere_kmers", C.c_int64)]
 
 
 # every symbol include/kcf_b200.h declares: name -> (restype, argtypes)
@@ -60,6 +61,11 @@ SYMBOLS = {
     "kcf_plan_destroy": (None, [_P]),
     "kcf_plan_stats": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "kcf_window_counts": (C.c_int, [_P, _P, _P, C.c_uint64, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "kcf_set_partition": (C.c_int, [_P, C.c_int, C.c_int]),
+    "kcf_xchg_extract": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_int, _P, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "kcf_xchg_lookup": (C.c_int, [_P, _P, _P, _P, C.c_uint64, _P]),
+    "kcf_xchg_fold": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P, _P, C.c_uint64, C.c_int32]),
+    "kcf_plan_finalize": (C.c_int, [_P, _P, C.POINTER(C.c_double)]),
     "kcf_measure_random_sector_gbps": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
     "kcf_set_profiling": (C.c_int, [_P, C.c_int]),
     "kcf_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

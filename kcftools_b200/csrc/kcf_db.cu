@@ -76,7 +76,8 @@ struct KcfIngestParams {
     uint8_t *table;
     KcfStashEntry *ovf;      // overflow list
     uint64_t ovf_cap;
-    unsigned long long *counters; // [0] inserted, [1] unreachable, [2] overflow
+    unsigned long long *counters; // [0] inserted, [1] unreachable, [2] overflow, [3] owned by another rank
+    uint32_t part_rank, part_world;
     uint32_t *flags;
 };
 
@@ -151,7 +152,12 @@ __global__ void __launch_bounds__(256) kcf_ingest_kernel(KcfIngestParams p, KcfT
         return;
     }
     const uint32_t home = kcf_home_line(kcf_minimizer_of_key(kmer, g), g);
-    uint32_t *home_w31 = reinterpret_cast<uint32_t *>(p.table + (uint64_t)home * KCF_LINE_BYTES) + 31;
+    if (p.part_world > 1 && kcf_line_owner(home, g.n_lines, p.part_world) != p.part_rank) { // another rank's slice
+        atomicAdd(&p.counters[3], 1ULL);
+        return;
+    }
+    uint8_t *home_line = p.table + (uint64_t)kcf_line_wrap(home, 0, g) * KCF_LINE_BYTES;
+    uint32_t *home_w31 = reinterpret_cast<uint32_t *>(home_line) + 31;
     if (KCF_KEY_IN_LINES(kmer)) {
         const uint32_t lo = (uint32_t)kmer, hi = (uint32_t)(kmer >> 32);
         for (uint32_t d = 0; d <= KCF_MAX_DISP; ++d) {
@@ -171,7 +177,7 @@ __global__ void __launch_bounds__(256) kcf_ingest_kernel(KcfIngestParams p, KcfT
                         const uint32_t field = g.cw == 4 ? 0xFFFFFFFFu : (((1u << (8 * g.cw)) - 1u) << sh);
                         atomicAnd(w + (off >> 2), ~field | (count << sh));
                         atomicAnd(home_w31, ~(1u << (16 + d)));
-                        if (d > 0) kcf_filter_add(p.table + (uint64_t)home * KCF_LINE_BYTES, kmer, g);
+                        if (d > 0) kcf_filter_add(home_line, kmer, g);
                         atomicAdd(&p.counters[0], 1ULL);
                         placed = true;
                         break;
@@ -185,7 +191,7 @@ __global__ void __launch_bounds__(256) kcf_ingest_kernel(KcfIngestParams p, KcfT
         }
     }
     atomicAnd(home_w31, ~(1u << (16 + KCF_STASH_BIT)));
-    kcf_filter_add(p.table + (uint64_t)home * KCF_LINE_BYTES, kmer, g);
+    kcf_filter_add(home_line, kmer, g);
     unsigned long long pos = atomicAdd(&p.counters[2], 1ULL);
     if (pos < p.ovf_cap) {
         p.ovf[pos].key = kmer;
@@ -261,12 +267,22 @@ extern "C" int kcf_set_minimizer_length(kcf_ctx *ctx, int m)
     return KCF_OK;
 }
 
+extern "C" int kcf_set_partition(kcf_ctx *ctx, int rank, int world)
+{
+    if (!ctx) return KCF_ERR_ARG;
+    if (world < 1 || rank < 0 || rank >= world) return kcf_fail(ctx, KCF_ERR_ARG, "partition %d of %d", rank, world);
+    ctx->part_rank = rank;
+    ctx->part_world = world;
+    return KCF_OK;
+}
+
 extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_len, const uint8_t *suf, uint64_t suf_len,
                                int placement, kcf_db **out)
 {
     if (!ctx || !pre || !suf || !out) return KCF_ERR_ARG;
     *out = nullptr;
-    if (placement != 0) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "placement %d: use kcf_db_open_part for a partitioned database", placement);
+    if (placement != 0 && placement != 1) return kcf_fail(ctx, KCF_ERR_ARG, "placement %d (0 = whole database, 1 = this context's slice)", placement);
+    const uint32_t part_world = placement == 1 ? (uint32_t)ctx->part_world : 1u, part_rank = placement == 1 ? (uint32_t)ctx->part_rank : 0u;
     auto t0 = std::chrono::steady_clock::now();
     KCF_CUDA(ctx, cudaSetDevice(ctx->device));
     // --- KMC.java:107-168 readPrefixFile ---
@@ -344,6 +360,14 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     nb = std::max<uint64_t>(nb, cs == 0 ? 1 : 64);
     if (nb >= 0xFFFFFFFFULL) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "%llu records need more than 2^32 table lines; partition the database", (unsigned long long)N);
     g.n_lines = nb;
+    g.line_lo = 0;
+    g.n_local = nb;
+    if (part_world > 1) { // lines [lo, hi) of the global line space + spill lines for keys displaced past hi
+        const uint64_t lo = (nb * part_rank + part_world - 1) / part_world, hi = (nb * (part_rank + 1) + part_world - 1) / part_world;
+        g.line_lo = lo;
+        g.n_local = hi - lo + KCF_MAX_DISP;
+        nb = g.n_local; // lines allocated below
+    }
     g.stash_mask = 0;
 
     kcf_db *db = new kcf_db();
@@ -359,7 +383,7 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     const uint64_t chunk_rec = std::max<uint64_t>(1, (64ULL << 20) / std::max<uint32_t>(rec_size, 1));
     const uint64_t chunk_bytes = chunk_rec * std::max<uint32_t>(rec_size, 1);
     uint64_t ovf_cap = N / 16 + 4096;
-    unsigned long long counters[3] = {0, 0, 0};
+    unsigned long long counters[4] = {0, 0, 0, 0};
     uint32_t flags[FLAG_COUNT] = {0};
 
 #define DB_CUDA(call)                                                                                         \
@@ -377,8 +401,8 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     DB_CUDA(cudaMalloc(&d_lut, std::max<uint64_t>(lut_len, 1) * 8));
     DB_CUDA(cudaMalloc(&d_sigmap, sig_map_size * 4));
     DB_CUDA(cudaMalloc(&d_norm, (1ULL << (2 * L)) * 4));
-    DB_CUDA(cudaMalloc(&d_counters, 3 * sizeof(unsigned long long)));
-    DB_CUDA(cudaMemsetAsync(d_counters, 0, 3 * sizeof(unsigned long long), ctx->stream));
+    DB_CUDA(cudaMalloc(&d_counters, 4 * sizeof(unsigned long long)));
+    DB_CUDA(cudaMemsetAsync(d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
     DB_CUDA(cudaMemsetAsync(ctx->d_flags, 0, FLAG_COUNT * sizeof(uint32_t), ctx->stream));
     DB_CUDA(cudaMalloc(&d_ovf, ovf_cap * sizeof(KcfStashEntry)));
     if (lut_len) DB_CUDA(cudaMemcpyAsync(d_lut, pre + 4, lut_len * 8, cudaMemcpyHostToDevice, ctx->stream)); // KMC.java:153,159-163
@@ -403,7 +427,7 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
             ovf_cap = counters[2] + counters[2] / 8 + 4096; // placement races make the count vary a little between passes
             DB_CUDA(cudaMalloc(&d_ovf, ovf_cap * sizeof(KcfStashEntry)));
             DB_CUDA(cudaMemsetAsync(db->table, 0xFF, nb * KCF_LINE_BYTES, ctx->stream));
-            DB_CUDA(cudaMemsetAsync(d_counters, 0, 3 * sizeof(unsigned long long), ctx->stream));
+            DB_CUDA(cudaMemsetAsync(d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
         }
         const uint8_t *recs = suf + 4; // KMC.java:94 — skip the KMCS marker
         int j = 0;
@@ -431,6 +455,8 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
             p.ovf = d_ovf;
             p.ovf_cap = ovf_cap;
             p.counters = d_counters;
+            p.part_rank = part_rank;
+            p.part_world = part_world;
             p.flags = ctx->d_flags;
             kcf_ingest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(p, g);
             DB_CUDA(cudaGetLastError());
@@ -458,6 +484,9 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     info.unreachable_kmers = (int64_t)counters[1];
     info.stash_kmers = (int64_t)counters[2];
     info.n_buckets = (int64_t)nb;
+    info.elsewhere_kmers = (int64_t)counters[3];
+    db->part_rank = (int)part_rank;
+    db->part_world = (int)part_world;
     info.table_bytes = (int64_t)(nb * KCF_LINE_BYTES + (db->stash ? (g.stash_mask + 1) * sizeof(KcfStashEntry) : 0));
     info.load_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     db->info = info;

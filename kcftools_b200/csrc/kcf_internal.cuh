@@ -39,7 +39,9 @@
 #define KCF_KEY_IN_LINES(key) ((uint32_t)(key) != KCF_EMPTY_LO)
 
 struct KcfTableGeom {
-    uint64_t n_lines;    // < 2^32 - 1
+    uint64_t n_lines;    // < 2^32 - 1; the GLOBAL number of lines (home lines are computed against it)
+    uint64_t line_lo;    // global index of local line 0 (0 unless the database is partitioned)
+    uint64_t n_local;    // lines held by this table (== n_lines unless partitioned: own range + 14 spill lines)
     uint64_t kmask;      // 2k one-bits
     uint64_t stash_mask; // stash capacity - 1 (power of two), 0 when the stash is empty
     uint32_t k;
@@ -149,6 +151,7 @@ struct kcf_ctx {
     std::vector<PoolBlock> pool; // device blocks of cleared sequences, reused by later kcf_ref_add calls
     double load_factor = 0.4;
     int minimizer_len = 0;       // 0 = chosen from the database size
+    int part_rank = 0, part_world = 1; // slice kept by databases opened with placement 1 (kcf_set_partition)
     int sm_count = 148;
     int profiling = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -159,6 +162,7 @@ struct kcf_ctx {
 
 struct kcf_db {
     kcf_ctx *ctx = nullptr;
+    int part_rank = 0, part_world = 1; // > 1: this table holds one slice of the line space (placement 1)
     kcf_db_info_t info{};
     KcfTableGeom geom{};
     uint8_t *table = nullptr;        // n_lines * 128 bytes
@@ -180,6 +184,13 @@ struct kcf_plan {
     std::vector<uint64_t> h_tile_first;
     bool ran = false;
     double weights[3] = {0, 0, 0};
+    // scratch of the exchange path (partitioned databases), sized for one batch of tiles
+    uint64_t x_cap = 0;                    // positions
+    unsigned long long *x_keys = nullptr;  // canonical k-mer of every position of the batch
+    uint32_t *x_homes = nullptr;           // its global home line (0xFFFFFFFF: no k-mer ends here)
+    uint32_t *x_okw = nullptr, *x_start = nullptr; // validity / stretch-start bitmaps, one word per 32 positions
+    uint32_t *x_cnt = nullptr;             // counts returned by the owners, by position
+    unsigned long long *x_cursor = nullptr; // per-owner counters (device)
 };
 
 #define KCF_TILE 2048          // positions per tile = the unit of work one warp takes
@@ -189,6 +200,8 @@ struct kcf_plan {
 enum { FLAG_LUT_BAD = 0, FLAG_ORDER_BAD = 1, FLAG_SCORE_USED = 2, FLAG_COUNT = 8 };
 
 int kcf_fail(kcf_ctx *ctx, int code, const char *fmt, ...);
+int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t min_count, uint64_t tile_begin, uint64_t tile_end,
+                      int32_t *d_counts, bool extract);
 #define KCF_CUDA(ctx, call)                                                                        \
     do {                                                                                           \
         cudaError_t e__ = (call);                                                                  \

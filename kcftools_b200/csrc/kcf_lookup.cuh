@@ -49,11 +49,18 @@ __device__ __forceinline__ uint32_t kcf_minimizer_of_key(uint64_t key, const Kcf
     return mu;
 }
 
+// local index of global line home + d (wraps around the table; a partitioned table keeps 14 spill lines instead)
 __device__ __forceinline__ uint32_t kcf_line_wrap(uint32_t home, uint32_t d, const KcfTableGeom &g)
 {
-    uint64_t l = (uint64_t)home + d;
-    if (l >= g.n_lines) l -= g.n_lines;
+    uint64_t l = (uint64_t)home - g.line_lo + d;
+    if (l >= g.n_local) l -= g.n_local;
     return (uint32_t)l;
+}
+
+// rank that owns a home line when the line space is cut in `world` equal ranges
+__host__ __device__ __forceinline__ uint32_t kcf_line_owner(uint32_t home, uint64_t n_lines, uint32_t world)
+{
+    return (uint32_t)(((uint64_t)home * world) / n_lines);
 }
 
 // the 16-bit mask of a home line (stored inverted so that the table can be initialised with 0xFF bytes)
@@ -131,15 +138,21 @@ static __device__ __noinline__ uint32_t kcf_probe_lines(const uint8_t *__restric
     return 0;
 }
 
-// Full lookup of one canonical k-mer value (count kernel and slow paths).
-__device__ __forceinline__ uint32_t kcf_lookup(const uint8_t *__restrict__ table, const KcfStashEntry *__restrict__ stash,
-                                               const KcfTableGeom &g, uint64_t key)
+// Lookup of one canonical k-mer value whose (global) home line is known.
+__device__ __forceinline__ uint32_t kcf_lookup_at(const uint8_t *__restrict__ table, const KcfStashEntry *__restrict__ stash,
+                                                  const KcfTableGeom &g, uint64_t key, uint32_t home)
 {
-    const uint32_t home = kcf_home_line(kcf_minimizer_of_key(key, g), g);
-    const uint8_t *L = table + (uint64_t)home * KCF_LINE_BYTES;
+    const uint8_t *L = table + (uint64_t)kcf_line_wrap(home, 0, g) * KCF_LINE_BYTES;
     uint32_t c;
     if (KCF_KEY_IN_LINES(key) && kcf_line_find(L, key, g, c)) return c;
     if (!kcf_filter_pass(L, key, g)) return 0; // no key homed here that lives elsewhere looks like this one
     const uint32_t w31 = __ldg(reinterpret_cast<const uint32_t *>(L) + 31);
     return kcf_probe_lines(table, stash, g, key, home, kcf_mask_from_word31(w31), 1);
+}
+
+// Full lookup of one canonical k-mer value (count kernel and slow paths).
+__device__ __forceinline__ uint32_t kcf_lookup(const uint8_t *__restrict__ table, const KcfStashEntry *__restrict__ stash,
+                                               const KcfTableGeom &g, uint64_t key)
+{
+    return kcf_lookup_at(table, stash, g, key, kcf_home_line(kcf_minimizer_of_key(key, g), g));
 }

@@ -1,0 +1,305 @@
+// kcf_part.cu — screening against a database that is partitioned over several GPUs (placement 1, SURVEY §8e: a
+// database beyond one GPU's HBM is cut by home line, 1/world per rank).
+//
+// A rank cannot answer its own k-mers any more, so the hot path splits at the probe:
+//
+//   requester   kcf_xchg_extract   screening front half (stage, canonical k-mer, minimizer -> global home line) for a
+//                                  batch of tiles, then the k-mers grouped by the rank that owns their home line
+//   host        all-to-all of the (key, home) arrays        <- the one real exchange step of this path (NCCL)
+//   owner       kcf_xchg_lookup    probe of the local slice for every received k-mer (consecutive k-mers of a sender
+//                                  stay consecutive, so neighbours still share their line requests)
+//   host        all-to-all of the counts back
+//   requester   kcf_xchg_fold      counts back to positions, hit bitmaps, gap summaries per tile
+//   requester   kcf_plan_finalize  K5 as in the replicated path
+//
+// The host moves caller-owned device buffers between ranks (torch.distributed / NCCL in kcftools_b200/partitioned.py);
+// this file neither knows nor links a communication library.
+#include <algorithm>
+#include <vector>
+#include "kcf_internal.cuh"
+#include "kcf_lookup.cuh"
+
+#define KCF_MAX_WORLD 64
+
+// ---- requester: group the extracted k-mers by owner -------------------------------------------------------------
+__global__ void __launch_bounds__(256) kcf_part_count_kernel(const uint32_t *__restrict__ homes, uint64_t n, uint64_t n_lines, uint32_t world,
+                                                             unsigned long long *__restrict__ counts)
+{
+    __shared__ unsigned int s_cnt[KCF_MAX_WORLD];
+    if (threadIdx.x < KCF_MAX_WORLD) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t h = homes[i];
+        if (h != 0xFFFFFFFFu) atomicAdd(&s_cnt[kcf_line_owner(h, n_lines, world)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < world && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+}
+
+// One warp moves 32 consecutive positions at a time: the lanes bound for the same owner take consecutive slots of that
+// owner's range (one atomic per owner and warp step), so neighbouring k-mers stay neighbours on the owner's side.
+__global__ void __launch_bounds__(256) kcf_part_scatter_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ homes,
+                                                               uint64_t n, uint64_t n_lines, uint32_t world, unsigned long long *__restrict__ cursor,
+                                                               unsigned long long *__restrict__ keys_out, uint32_t *__restrict__ homes_out,
+                                                               uint32_t *__restrict__ src_out)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t i0 = warp * 32; i0 < n; i0 += n_warps * 32) {
+        const uint64_t i = i0 + lane;
+        const uint32_t h = i < n ? homes[i] : 0xFFFFFFFFu;
+        const uint32_t owner = h != 0xFFFFFFFFu ? kcf_line_owner(h, n_lines, world) : 0xFFFFFFFFu;
+        uint32_t todo = __ballot_sync(0xffffffffu, owner != 0xFFFFFFFFu);
+        while (todo) {
+            const uint32_t leader = __ffs(todo) - 1;
+            const uint32_t o = __shfl_sync(0xffffffffu, owner, leader);
+            const uint32_t same = __ballot_sync(0xffffffffu, owner == o);
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(&cursor[o], (unsigned long long)__popc(same));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (owner == o) {
+                const uint64_t dst = base + __popc(same & ((1u << lane) - 1u));
+                keys_out[dst] = keys[i];
+                homes_out[dst] = h;
+                src_out[dst] = (uint32_t)i;
+            }
+            todo &= ~same;
+        }
+    }
+}
+
+// ---- owner: probe the local slice -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kcf_part_lookup_kernel(const uint8_t *__restrict__ table, const KcfStashEntry *__restrict__ stash,
+                                                              KcfTableGeom g, const unsigned long long *__restrict__ keys,
+                                                              const uint32_t *__restrict__ homes, uint64_t n, uint32_t *__restrict__ counts)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    counts[i] = kcf_lookup_at(table, stash, g, keys[i], homes[i]);
+}
+
+// ---- requester: counts back to positions, then the gap summaries -----------------------------------------------------
+__global__ void __launch_bounds__(256) kcf_part_unscatter_kernel(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ src, uint64_t n,
+                                                                 uint32_t *__restrict__ cnt_by_pos)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cnt_by_pos[src[i]] = counts[i];
+}
+
+__device__ __forceinline__ uint32_t kcf_gap_distance_p(uint32_t gap, uint32_t k)
+{
+    int32_t d = (int32_t)gap - ((int32_t)k - 1);
+    if (d <= 0) d = abs(d + 1);
+    return (uint32_t)d;
+}
+
+// summary of 32 positions from their bitmaps (same function as in kcf_screen.cu; restated here to keep that file's
+// kernel self-contained)
+__device__ __forceinline__ KcfGap kcf_gap_bits_p(uint32_t hw, uint32_t vw, uint32_t sw, uint32_t k)
+{
+    KcfGap a;
+    a.n = __popc(vw);
+    a.obs = __popc(hw);
+    a.starts = __popc(sw);
+    a.sum = 0;
+    a.vin = a.inner = 0;
+    a.has = hw != 0;
+    if (!hw) {
+        a.lead = a.trail = a.n;
+        return a;
+    }
+    const uint32_t first = __ffs(hw) - 1, last = 31 - __clz(hw);
+    a.lead = __popc(vw & ((1u << first) - 1u));
+    a.trail = __popc(vw & ~(0xFFFFFFFFu >> (31 - last)));
+    uint32_t zr = ~hw & (0xFFFFFFFFu >> (31 - last)) & ~((1u << first) - 1u);
+    while (zr) {
+        const uint32_t s = __ffs(zr) - 1;
+        const uint32_t e = __ffs(~(zr >> s)) - 1;
+        const uint32_t gm = ((1u << e) - 1u) << s;
+        const uint32_t glen = __popc(vw & gm);
+        if (glen) {
+            a.vin += 1;
+            a.inner += kcf_gap_distance_p(glen, k);
+        }
+        zr &= ~gm;
+    }
+    return a;
+}
+
+__device__ __forceinline__ KcfGap kcf_gap_combine_p(const KcfGap &a, const KcfGap &b, uint32_t k)
+{
+    if (b.n == 0) return a;
+    if (a.n == 0) return b;
+    KcfGap r;
+    r.n = a.n + b.n;
+    r.obs = a.obs + b.obs;
+    r.sum = a.sum + b.sum;
+    r.starts = a.starts + b.starts;
+    r.vin = a.vin + b.vin;
+    r.inner = a.inner + b.inner;
+    r.has = a.has | b.has;
+    if (a.has && b.has) {
+        const uint32_t gp = a.trail + b.lead;
+        if (gp > 0) {
+            r.vin += 1;
+            r.inner += kcf_gap_distance_p(gp, k);
+        }
+        r.lead = a.lead;
+        r.trail = b.trail;
+    } else if (a.has) {
+        r.lead = a.lead;
+        r.trail = a.trail + b.n;
+    } else if (b.has) {
+        r.lead = a.n + b.lead;
+        r.trail = b.trail;
+    } else {
+        r.lead = r.n;
+        r.trail = r.n;
+    }
+    return r;
+}
+
+// one warp per tile of KCF_TILE positions: 64 words of 32 positions, two per lane, reduced in order
+__global__ void __launch_bounds__(128) kcf_part_fold_kernel(const uint32_t *__restrict__ cnt_by_pos, const uint32_t *__restrict__ okw,
+                                                            const uint32_t *__restrict__ start, uint64_t n_tiles, uint32_t k, int32_t min_count,
+                                                            KcfGap *__restrict__ tile_sum)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= n_tiles) return;
+    constexpr int WORDS = KCF_TILE / 32; // 64
+    unsigned long long sum = 0;
+    uint32_t hw0 = 0, hw1 = 0;
+    for (int wd = 0; wd < WORDS; ++wd) {
+        const uint64_t pos = t * KCF_TILE + 32ULL * wd + lane;
+        const uint32_t vw = okw[t * WORDS + wd];
+        const bool ok = (vw >> lane) & 1u;
+        const uint32_t c = ok ? cnt_by_pos[pos] : 0u;
+        const bool hit = ok && (int32_t)c >= min_count; // Java int compare (GetVariants.java:224)
+        if (hit) sum += c;
+        const uint32_t hb = __ballot_sync(0xffffffffu, hit);
+        if ((uint32_t)(wd & 31) == lane) {
+            if (wd < 32) hw0 = hb;
+            else hw1 = hb;
+        }
+    }
+    KcfGap a = kcf_gap_bits_p(hw0, okw[t * WORDS + lane], start[t * WORDS + lane], k);
+    KcfGap b = kcf_gap_bits_p(hw1, okw[t * WORDS + 32 + lane], start[t * WORDS + 32 + lane], k);
+    for (int d = 1; d < 32; d <<= 1) {
+        KcfGap a2, b2;
+#define SHF(dst, srcv, f) dst.f = __shfl_down_sync(0xffffffffu, srcv.f, d)
+        SHF(a2, a, n); SHF(a2, a, obs); SHF(a2, a, lead); SHF(a2, a, trail); SHF(a2, a, vin); SHF(a2, a, inner); SHF(a2, a, has); SHF(a2, a, starts);
+        SHF(b2, b, n); SHF(b2, b, obs); SHF(b2, b, lead); SHF(b2, b, trail); SHF(b2, b, vin); SHF(b2, b, inner); SHF(b2, b, has); SHF(b2, b, starts);
+#undef SHF
+        a2.sum = b2.sum = 0;
+        if (lane + d < 32) {
+            a = kcf_gap_combine_p(a, a2, k);
+            b = kcf_gap_combine_p(b, b2, k);
+        }
+        sum += __shfl_down_sync(0xffffffffu, sum, d);
+    }
+    if (lane == 0) {
+        KcfGap r = kcf_gap_combine_p(a, b, k);
+        r.sum = sum;
+        tile_sum[t] = r;
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------------
+static int kcf_xchg_reserve(kcf_ctx *ctx, kcf_plan *plan, uint64_t positions)
+{
+    if (plan->x_cap >= positions && plan->x_keys) return KCF_OK;
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(plan->x_keys);
+    cudaFree(plan->x_homes);
+    cudaFree(plan->x_okw);
+    cudaFree(plan->x_start);
+    cudaFree(plan->x_cnt);
+    plan->x_keys = nullptr;
+    plan->x_homes = plan->x_okw = plan->x_start = plan->x_cnt = nullptr;
+    plan->x_cap = 0;
+    KCF_CUDA(ctx, cudaMalloc(&plan->x_keys, positions * 8));
+    KCF_CUDA(ctx, cudaMalloc(&plan->x_homes, positions * 4));
+    KCF_CUDA(ctx, cudaMalloc(&plan->x_okw, positions / 32 * 4 + 4));
+    KCF_CUDA(ctx, cudaMalloc(&plan->x_start, positions / 32 * 4 + 4));
+    KCF_CUDA(ctx, cudaMalloc(&plan->x_cnt, positions * 4));
+    if (!plan->x_cursor) KCF_CUDA(ctx, cudaMalloc(&plan->x_cursor, 2 * KCF_MAX_WORLD * sizeof(unsigned long long)));
+    plan->x_cap = positions;
+    return KCF_OK;
+}
+
+extern "C" int kcf_xchg_extract(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, uint64_t tile_begin, uint64_t tile_end, int world,
+                                void *d_keys_out, void *d_homes_out, void *d_src_out, uint64_t cap, uint64_t *send_counts)
+{
+    if (!ctx || !db || !plan || !send_counts || plan->ctx != ctx || db->ctx != ctx) return KCF_ERR_ARG;
+    if (world < 1 || world > KCF_MAX_WORLD) return kcf_fail(ctx, KCF_ERR_ARG, "world %d outside 1..%d", world, KCF_MAX_WORLD);
+    if (world != db->part_world) return kcf_fail(ctx, KCF_ERR_ARG, "database was opened as slice %d of %d, not of %d", db->part_rank, db->part_world, world);
+    if (plan->k != db->info.kmer_length) return kcf_fail(ctx, KCF_ERR_ARG, "plan built for k=%d, database has k=%d", plan->k, db->info.kmer_length);
+    tile_end = std::min<uint64_t>(tile_end, plan->n_tiles);
+    for (int r = 0; r < world; ++r) send_counts[r] = 0;
+    if (tile_begin >= tile_end) return KCF_OK;
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t npos = (tile_end - tile_begin) * KCF_TILE;
+    if (npos >= (1ULL << 32)) return kcf_fail(ctx, KCF_ERR_ARG, "batch of %llu positions: keep batches below 2^32", (unsigned long long)npos);
+    int rc = kcf_xchg_reserve(ctx, plan, npos);
+    if (rc != KCF_OK) return rc;
+    KCF_CUDA(ctx, cudaMemsetAsync(plan->x_homes, 0xFF, npos * 4, ctx->stream));
+    KCF_CUDA(ctx, cudaMemsetAsync(plan->x_okw, 0, npos / 32 * 4, ctx->stream));
+    KCF_CUDA(ctx, cudaMemsetAsync(plan->x_start, 0, npos / 32 * 4, ctx->stream));
+    KCF_CUDA(ctx, cudaMemsetAsync(plan->x_cursor, 0, 2 * KCF_MAX_WORLD * sizeof(unsigned long long), ctx->stream));
+    rc = kcf_launch_screen(ctx, db, plan, 1, tile_begin, tile_end, nullptr, true);
+    if (rc != KCF_OK) return rc;
+    const unsigned grid = (unsigned)std::min<uint64_t>((npos + 255) / 256, (uint64_t)ctx->sm_count * 8);
+    kcf_part_count_kernel<<<grid, 256, 0, ctx->stream>>>(plan->x_homes, npos, db->geom.n_lines, (uint32_t)world, plan->x_cursor);
+    unsigned long long h_counts[KCF_MAX_WORLD];
+    KCF_CUDA(ctx, cudaMemcpyAsync(h_counts, plan->x_cursor, world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    KCF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned long long offs[KCF_MAX_WORLD], total = 0;
+    for (int r = 0; r < world; ++r) {
+        offs[r] = total;
+        total += h_counts[r];
+        send_counts[r] = h_counts[r];
+    }
+    if (total > cap) return kcf_fail(ctx, KCF_ERR_ARG, "send buffers hold %llu records, the batch has %llu", (unsigned long long)cap, total);
+    if (total && (!d_keys_out || !d_homes_out || !d_src_out)) return KCF_ERR_ARG;
+    // the scatter cursors start at each owner's offset (second half of x_cursor)
+    KCF_CUDA(ctx, cudaMemcpyAsync(plan->x_cursor + KCF_MAX_WORLD, offs, world * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+    if (total)
+        kcf_part_scatter_kernel<<<grid, 256, 0, ctx->stream>>>(plan->x_keys, plan->x_homes, npos, db->geom.n_lines, (uint32_t)world,
+                                                               plan->x_cursor + KCF_MAX_WORLD, (unsigned long long *)d_keys_out,
+                                                               (uint32_t *)d_homes_out, (uint32_t *)d_src_out);
+    KCF_CUDA(ctx, cudaGetLastError());
+    KCF_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // offs[] leaves scope; the caller hands the buffers to its communication library
+    return KCF_OK;
+}
+
+extern "C" int kcf_xchg_lookup(kcf_ctx *ctx, kcf_db *db, const void *d_keys, const void *d_homes, uint64_t n, void *d_counts_out)
+{
+    if (!ctx || !db || db->ctx != ctx || (n && (!d_keys || !d_homes || !d_counts_out))) return KCF_ERR_ARG;
+    if (n == 0) return KCF_OK;
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    kcf_part_lookup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(db->table, db->stash, db->geom, (const unsigned long long *)d_keys,
+                                                                                 (const uint32_t *)d_homes, n, (uint32_t *)d_counts_out);
+    KCF_CUDA(ctx, cudaGetLastError());
+    KCF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KCF_OK;
+}
+
+extern "C" int kcf_xchg_fold(kcf_ctx *ctx, kcf_plan *plan, uint64_t tile_begin, uint64_t tile_end, const void *d_counts_back, const void *d_src,
+                             uint64_t n, int32_t min_count)
+{
+    if (!ctx || !plan || plan->ctx != ctx || (n && (!d_counts_back || !d_src))) return KCF_ERR_ARG;
+    if (min_count < 1) return kcf_fail(ctx, KCF_ERR_ARG, "Minimum kmer count should be at least 1");
+    tile_end = std::min<uint64_t>(tile_end, plan->n_tiles);
+    if (tile_begin >= tile_end) return KCF_OK;
+    const uint64_t npos = (tile_end - tile_begin) * KCF_TILE;
+    if (!plan->x_cnt || plan->x_cap < npos) return kcf_fail(ctx, KCF_ERR_ARG, "kcf_xchg_fold without the matching kcf_xchg_extract");
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n) kcf_part_unscatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t *)d_counts_back, (const uint32_t *)d_src, n, plan->x_cnt);
+    const uint64_t nt = tile_end - tile_begin;
+    kcf_part_fold_kernel<<<(unsigned)((nt * 32 + 127) / 128), 128, 0, ctx->stream>>>(plan->x_cnt, plan->x_okw, plan->x_start, nt, (uint32_t)plan->k,
+                                                                                    min_count, plan->d_tile_sum + tile_begin);
+    KCF_CUDA(ctx, cudaGetLastError());
+    KCF_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // the caller may reuse its buffers
+    return KCF_OK;
+}

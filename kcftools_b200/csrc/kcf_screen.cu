@@ -32,6 +32,10 @@ struct KcfScreenParams {
     int32_t min_count;
     int32_t *counts_out;   // optional: per position count of the tiles processed (-1 = no k-mer ends here)
     uint64_t counts_tile0; // tile whose position 0 maps to counts_out[0]
+    // EXTRACT mode (partitioned databases): instead of probing, write every position's canonical k-mer, global home
+    // line (0xFFFFFFFF where no k-mer ends) and the validity / stretch-start bitmaps, indexed from tile_begin
+    unsigned long long *x_keys;
+    uint32_t *x_homes, *x_okw, *x_start;
 };
 
 // GetVariants.java:267-273 getDistance
@@ -271,6 +275,40 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
         }                                                                                                              \
     } while (0)
 
+// EXTRACT mode: the front half of a probe only — canonical k-mer, validity, home line — written out for the exchange
+#define KCF_EXTRACT(JJ)                                                                                                \
+    do {                                                                                                               \
+        const uint32_t cpos = 32 * (JJ) + lane;                                                                        \
+        const uint32_t q = KCF_HALO + cpos;                                                                            \
+        const uint32_t b0 = q - k + 1;                                                                                 \
+        bool ok, ok_prev;                                                                                              \
+        {                                                                                                              \
+            const uint32_t vb = b0 - 1, vi = vb >> 5;                                                                  \
+            const uint64_t vwin = ((((uint64_t)W.valid[vi + 1] << 32) | W.valid[vi]) >> (vb & 31u));                   \
+            ok_prev = (vwin & km1) == km1;                                                                             \
+            ok = ((vwin >> 1) & km1) == km1;                                                                           \
+        }                                                                                                              \
+        uint64_t key;                                                                                                  \
+        {                                                                                                              \
+            const uint32_t wi = b0 >> 4, sh = (b0 & 15u) * 2u;                                                         \
+            const uint64_t lo = ((uint64_t)W.codes[wi + 1] << 32) | W.codes[wi];                                       \
+            const uint64_t X = (sh ? ((lo >> sh) | ((uint64_t)W.codes[wi + 2] << (64 - sh))) : lo) & g.kmask;          \
+            const uint64_t fw = kcf_pair_reverse(X, g.kshift);                                                         \
+            const uint64_t rc = (~X) & g.kmask;                                                                        \
+            key = (g.both_strands && rc < fw) ? rc : fw;                                                               \
+        }                                                                                                              \
+        const uint32_t h0 = q - g.w + 1;                                                                               \
+        const uint32_t home = kcf_home_line(min(W.hash[h0], W.hash[h0 + g.w - P2]), g);                                \
+        p.x_keys[base + cpos] = key;                                                                                   \
+        p.x_homes[base + cpos] = ok ? home : 0xFFFFFFFFu;                                                              \
+        const uint32_t vb2 = __ballot_sync(0xffffffffu, ok);                                                           \
+        const uint32_t sb2 = __ballot_sync(0xffffffffu, ok && !ok_prev);                                               \
+        if (lane == 0) {                                                                                               \
+            p.x_okw[(base >> 5) + (JJ)] = vb2;                                                                         \
+            p.x_start[(base >> 5) + (JJ)] = sb2;                                                                       \
+        }                                                                                                              \
+    } while (0)
+
 // search the queued k-mers in the lines their home masks name; one item per lane
 #define KCF_FLUSH_QUEUE()                                                                                              \
     do {                                                                                                               \
@@ -297,7 +335,7 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
         __syncwarp();                                                                                                  \
     } while (0)
 
-template <int S, bool COUNTS>
+template <int S, bool COUNTS, bool EXTRACT>
 __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_screen_kernel(KcfScreenParams p, KcfTableGeom g)
 {
     extern __shared__ __align__(16) uint8_t kcf_smem_raw[];
@@ -441,6 +479,13 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
             for (uint32_t j = lane; j < KCF_CHUNK / 32; j += 32) W.hit[j] = W.okw[j] = W.start[j] = 0;
             __syncwarp();
 
+            if (EXTRACT) {
+                const uint64_t base = (tile - p.tile_begin) * KCF_TILE + (uint64_t)chunk * KCF_CHUNK;
+                const uint32_t np = (uint32_t)min((int64_t)KCF_CHUNK, (int64_t)wlen - o);
+#pragma unroll 1
+                for (uint32_t j = 0; 32 * j < np; ++j) KCF_EXTRACT(j);
+                continue;
+            }
             // ---- probe: lanes own consecutive positions ----
             uint64_t sum = 0;  // Σ count over this lane's observed k-mers
             uint32_t qn = 0;   // queue length (warp uniform)
@@ -464,7 +509,7 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
             acc = kcf_gap_combine(acc, a, k);
             __syncwarp(); // the bitmaps are rewritten by the next chunk
         }
-        if (lane == 0) p.tile_sum[tile] = acc;
+        if (!EXTRACT && lane == 0) p.tile_sum[tile] = acc;
     }
 }
 
@@ -622,6 +667,12 @@ extern "C" void kcf_plan_destroy(kcf_plan *plan)
     cudaFree(plan->d_tile_first);
     cudaFree(plan->d_tile_sum);
     cudaFree(plan->d_out);
+    cudaFree(plan->x_keys);
+    cudaFree(plan->x_homes);
+    cudaFree(plan->x_okw);
+    cudaFree(plan->x_start);
+    cudaFree(plan->x_cnt);
+    cudaFree(plan->x_cursor);
     delete plan;
 }
 
@@ -707,9 +758,11 @@ extern "C" int kcf_plan_create(kcf_ctx *ctx, int32_t kmer_length, const kcf_wind
     return KCF_OK;
 }
 
-static int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t min_count, uint64_t tile_begin, uint64_t tile_end,
-                             int32_t *d_counts)
+int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t min_count, uint64_t tile_begin, uint64_t tile_end,
+                      int32_t *d_counts, bool extract)
 {
+    if (!extract && db->part_world > 1)
+        return kcf_fail(ctx, KCF_ERR_ARG, "this database holds slice %d of %d: screen it through the exchange calls (kcf_xchg_*)", db->part_rank, db->part_world);
     int rc = kcf_sync_seqs(ctx);
     if (rc != KCF_OK) return rc;
     unsigned long long *d_counter = reinterpret_cast<unsigned long long *>(
@@ -732,10 +785,16 @@ static int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t m
     p.min_count = min_count;
     p.counts_out = d_counts;
     p.counts_tile0 = tile_begin;
+    p.x_keys = plan->x_keys;
+    p.x_homes = plan->x_homes;
+    p.x_okw = plan->x_okw;
+    p.x_start = plan->x_start;
     const size_t smem = KCF_WPC * sizeof(KcfWarpSmem);
     void (*kern)(KcfScreenParams, KcfTableGeom);
-    if (d_counts) kern = db->geom.S == 13 ? kcf_screen_kernel<13, true> : (db->geom.S == 12 ? kcf_screen_kernel<12, true> : kcf_screen_kernel<10, true>);
-    else kern = db->geom.S == 13 ? kcf_screen_kernel<13, false> : (db->geom.S == 12 ? kcf_screen_kernel<12, false> : kcf_screen_kernel<10, false>);
+    const int S = (int)db->geom.S;
+    if (extract) kern = S == 13 ? kcf_screen_kernel<13, false, true> : (S == 12 ? kcf_screen_kernel<12, false, true> : kcf_screen_kernel<10, false, true>);
+    else if (d_counts) kern = S == 13 ? kcf_screen_kernel<13, true, false> : (S == 12 ? kcf_screen_kernel<12, true, false> : kcf_screen_kernel<10, true, false>);
+    else kern = S == 13 ? kcf_screen_kernel<13, false, false> : (S == 12 ? kcf_screen_kernel<12, false, false> : kcf_screen_kernel<10, false, false>);
     KCF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     KCF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * KCF_WPC, smem));
@@ -755,7 +814,7 @@ extern "C" int kcf_plan_run(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t mi
     KCF_CUDA(ctx, cudaSetDevice(ctx->device));
     KCF_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, FLAG_COUNT * sizeof(uint32_t), ctx->stream));
     if (ctx->profiling) cudaEventRecord(ctx->ev[0], ctx->stream);
-    int rc = kcf_launch_screen(ctx, db, plan, min_count, 0, plan->n_tiles, nullptr);
+    int rc = kcf_launch_screen(ctx, db, plan, min_count, 0, plan->n_tiles, nullptr, false);
     if (rc != KCF_OK) return rc;
     if (ctx->profiling) cudaEventRecord(ctx->ev[1], ctx->stream);
     if (plan->n_wins) {
@@ -766,6 +825,24 @@ extern "C" int kcf_plan_run(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t mi
     if (ctx->profiling) {
         cudaEventRecord(ctx->ev[2], ctx->stream);
         ctx->ev_valid = true;
+    }
+    plan->weights[0] = w[0];
+    plan->weights[1] = w[1];
+    plan->weights[2] = w[2];
+    plan->ran = true;
+    return KCF_OK;
+}
+
+// K5 alone, over tile summaries that were produced by kcf_xchg_fold (partitioned databases)
+extern "C" int kcf_plan_finalize(kcf_ctx *ctx, kcf_plan *plan, const double w[3])
+{
+    if (!ctx || !plan || !w || plan->ctx != ctx) return KCF_ERR_ARG;
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    KCF_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, FLAG_COUNT * sizeof(uint32_t), ctx->stream));
+    if (plan->n_wins) {
+        kcf_finalize_kernel<<<(unsigned)((plan->n_wins + 127) / 128), 128, 0, ctx->stream>>>(
+            plan->d_tile_sum, plan->d_tile_first, plan->n_wins, (uint32_t)plan->k, w[0], w[1], w[2], plan->d_out, ctx->d_flags);
+        KCF_CUDA(ctx, cudaGetLastError());
     }
     plan->weights[0] = w[0];
     plan->weights[1] = w[1];
@@ -821,7 +898,7 @@ extern "C" int kcf_window_counts(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, uint6
     const uint64_t npos = (t1 - t0) * KCF_TILE;
     int32_t *d = nullptr;
     KCF_CUDA(ctx, cudaMalloc(&d, std::max<uint64_t>(npos, 1) * 4));
-    int rc = kcf_launch_screen(ctx, db, plan, 1, t0, t1, d);
+    int rc = kcf_launch_screen(ctx, db, plan, 1, t0, t1, d, false);
     std::vector<int32_t> h(npos);
     if (rc == KCF_OK) {
         cudaMemcpyAsync(h.data(), d, npos * 4, cudaMemcpyDeviceToHost, ctx->stream);

@@ -1,0 +1,101 @@
+"""Screening against a database that is partitioned over the GPUs of one node (placement 1).
+
+Each rank holds 1/world of the table (cut by home line) and a shard of the windows.  A rank can no longer answer its
+own k-mers, so the path gets its one real exchange step: per batch of tiles the k-mers are grouped by owning rank
+(kcf_xchg_extract), moved with an all-to-all, looked up by their owners (kcf_xchg_lookup), and the counts travel back
+with a second all-to-all before the per-window statistics are folded (kcf_xchg_fold, kcf_plan_finalize).
+
+`Exchange` is the communication seam: `DistExchange` = torch.distributed (NCCL over NVLink / NVSwitch on the GPU box,
+one process per GPU); `screen_partitioned_local` drives several contexts of ONE process in lockstep and moves the
+buffers by slicing — the single-GPU test of exactly the same library calls.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import RESULT_DTYPE
+
+BATCH_TILES = 1 << 16  # 2048 positions each: 1.3e8 positions, ~2 GB of exchange buffers per rank and batch
+
+
+def _extract(ctx, db, plan, t0, t1, world, torch, dev):
+    npos = max(0, min(t1, plan.n_tiles) - t0) * 2048
+    keys = torch.empty(max(npos, 1), dtype=torch.int64, device=dev)
+    homes = torch.empty(max(npos, 1), dtype=torch.int32, device=dev)
+    src = torch.empty(max(npos, 1), dtype=torch.int32, device=dev)
+    counts = (C.c_uint64 * world)()
+    ctx._check(ctx._lib.kcf_xchg_extract(ctx._h, db._h, plan._h, t0, t1, world, keys.data_ptr(), homes.data_ptr(), src.data_ptr(), npos, counts))
+    sc = [int(c) for c in counts]
+    n = sum(sc)
+    return keys[:n], homes[:n], src[:n], sc
+
+
+def _lookup(ctx, db, keys, homes, torch, dev):
+    out = torch.empty(max(keys.numel(), 1), dtype=torch.int32, device=dev)
+    ctx._check(ctx._lib.kcf_xchg_lookup(ctx._h, db._h, keys.data_ptr(), homes.data_ptr(), keys.numel(), out.data_ptr()))
+    return out[:keys.numel()]
+
+
+def _fold(ctx, plan, t0, t1, counts_back, src, min_count):
+    ctx._check(ctx._lib.kcf_xchg_fold(ctx._h, plan._h, t0, t1, counts_back.data_ptr(), src.data_ptr(), src.numel(), min_count))
+
+
+def _finish(ctx, plan, weights):
+    w = (C.c_double * 3)(*weights)
+    ctx._check(ctx._lib.kcf_plan_finalize(ctx._h, plan._h, w))
+    return plan.fetch()
+
+
+def screen_partitioned(ctx, db, plan, group=None, min_count: int = 1, weights=(0.3, 0.3, 0.4), batch_tiles: int = BATCH_TILES) -> np.ndarray:
+    """one rank of a torch.distributed job: `db` was opened with placement=1 after ctx.set_partition(rank, world), `plan`
+    holds THIS rank's windows.  Returns this rank's rows."""
+    import torch
+    import torch.distributed as dist
+    world, dev = dist.get_world_size(group), torch.device("cuda", ctx.device)
+    # every rank takes part in every all-to-all: loop over the largest batch count
+    nb = torch.tensor([(plan.n_tiles + batch_tiles - 1) // batch_tiles], device=dev)
+    dist.all_reduce(nb, op=dist.ReduceOp.MAX, group=group)
+    for b in range(int(nb.item())):
+        t0, t1 = b * batch_tiles, (b + 1) * batch_tiles
+        keys, homes, src, sc = _extract(ctx, db, plan, t0, t1, world, torch, dev)
+        send = torch.tensor(sc, dtype=torch.int64, device=dev)
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=group)
+        rc = [int(x) for x in recv.tolist()]
+        rkeys = torch.empty(sum(rc), dtype=torch.int64, device=dev)
+        rhomes = torch.empty(sum(rc), dtype=torch.int32, device=dev)
+        dist.all_to_all_single(rkeys, keys, rc, sc, group=group)
+        dist.all_to_all_single(rhomes, homes, rc, sc, group=group)
+        rcounts = _lookup(ctx, db, rkeys, rhomes, torch, dev)
+        back = torch.empty(sum(sc), dtype=torch.int32, device=dev)
+        dist.all_to_all_single(back, rcounts, sc, rc, group=group)
+        _fold(ctx, plan, t0, t1, back, src, min_count)
+    return _finish(ctx, plan, weights)
+
+
+def screen_partitioned_local(ranks, min_count: int = 1, weights=(0.3, 0.3, 0.4), batch_tiles: int = BATCH_TILES) -> list[np.ndarray]:
+    """`ranks` = [(ctx, db, plan), ...]: every slice of one database, each with its own window shard, all on GPUs this
+    process can see (typically the same one).  Runs the ranks in lockstep; the all-to-all is done by slicing."""
+    import torch
+    world = len(ranks)
+    devs = [torch.device("cuda", r[0].device) for r in ranks]
+    nb = max((r[2].n_tiles + batch_tiles - 1) // batch_tiles for r in ranks)
+    for b in range(nb):
+        t0, t1 = b * batch_tiles, (b + 1) * batch_tiles
+        ext = [_extract(ctx, db, plan, t0, t1, world, torch, devs[i]) for i, (ctx, db, plan) in enumerate(ranks)]
+        offs = [np.concatenate([[0], np.cumsum(e[3])]) for e in ext]
+        looked = []
+        for o, (ctx, db, plan) in enumerate(ranks):  # owner o receives from every sender s
+            rk = torch.cat([ext[s][0][offs[s][o]:offs[s][o + 1]].to(devs[o]) for s in range(world)])
+            rh = torch.cat([ext[s][1][offs[s][o]:offs[s][o + 1]].to(devs[o]) for s in range(world)])
+            looked.append(_lookup(ctx, db, rk, rh, torch, devs[o]))
+        for s, (ctx, db, plan) in enumerate(ranks):  # counts travel back in the order they were sent
+            parts = []
+            for o in range(world):
+                before = sum(ext[q][3][o] for q in range(s))
+                parts.append(looked[o][before:before + ext[s][3][o]].to(devs[s]))
+            back = torch.cat(parts) if parts else torch.empty(0, dtype=torch.int32, device=devs[s])
+            _fold(ctx, plan, t0, t1, back, ext[s][2], min_count)
+    return [_finish(ctx, plan, weights) for (ctx, db, plan) in ranks]

@@ -265,3 +265,42 @@ def test_empty_inputs(ctx, sc_main):
     got = ctx.screen(db, wins, segs)
     assert (got["obs"] == 0).all() and (got["right"] == got["total_kmers"]).all()
     db.close()
+
+
+@pytest.mark.parametrize("world,batch_tiles", [(1, 1 << 16), (2, 1 << 16), (3, 7)])
+def test_partitioned_database_exchange_path(sc_main, world, batch_tiles):
+    """placement 1: every rank holds 1/world of the table and a shard of the windows; k-mers travel to their owners and
+    the counts come back (here all ranks live on cuda:0 and the all-to-all is done by slicing — the library calls are
+    the ones the NCCL job makes)."""
+    from kcftools_b200 import shard
+    from kcftools_b200.api import Context
+    from kcftools_b200.partitioned import screen_partitioned_local
+    sc = sc_main
+    wins, segs, *_ = fixed_windows(sc.seq_lens, 20_000, 0, 31)
+    rc, want = _oracle_screen(sc, wins, segs, min_count=2, w=(0.2, 0.3, 0.5))
+    ranges = shard.partition(shard.window_lengths(wins, segs), world)
+    ranks, ctxs = [], []
+    total_resident = 0
+    for r in range(world):
+        c = Context(0)
+        ctxs.append(c)
+        sc.add_to(c)
+        c.set_partition(r, world)
+        db = KMC(c, pre=sc.kmc.pre, suf=sc.kmc.suf, placement=1)
+        total_resident += db.info.resident_kmers
+        assert db.info.resident_kmers + db.info.elsewhere_kmers == sc.kmc.total
+        lw, ls = shard.local_slice(wins, segs, *ranges[r])
+        ranks.append((c, db, c.plan(31, lw, ls)))
+    assert total_resident == sc.kmc.total  # every record lives on exactly one rank
+    if world > 1:
+        assert all(r[1].info.resident_kmers > 0 for r in ranks)
+        with pytest.raises(KcfError):  # a slice cannot be screened alone
+            ranks[0][2].run(ranks[0][1])
+    parts = screen_partitioned_local(ranks, min_count=2, weights=(0.2, 0.3, 0.5), batch_tiles=batch_tiles)
+    got = np.concatenate(parts)
+    assert_results_equal(got, want)
+    for (c, db, plan) in ranks:
+        plan.close()
+        db.close()
+    for c in ctxs:
+        c.close()
