@@ -153,6 +153,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-windows", type=int, default=0, help="windows in the CPU baseline sample (0 = auto, ~15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--placement", default="replicated", choices=["replicated", "partitioned"],
+                    help="partitioned: every rank keeps 1/N of the table, k-mers are routed by NCCL all-to-all (needs --gpus > 1)")
     ap.add_argument("--lf", type=float, default=0.0, help="table load factor (0 = library default)")
     ap.add_argument("--m", type=int, default=0, help="minimizer length (0 = automatic)")
     args = ap.parse_args()
@@ -217,7 +219,11 @@ def main():
         ctx.set_minimizer_length(args.m)
     stream = torch.cuda.ExternalStream(ctx.stream, device=device)
     t0 = time.time()
-    db = KMC(ctx, pre=kmc.pre, suf=kmc.suf)
+    partitioned = args.placement == "partitioned" and world > 1
+    if partitioned:
+        ctx.set_partition(rank, world)
+        config["db_placement"] = f"partitioned by home line, 1/{world} per GPU, k-mers routed by NCCL all-to-all"
+    db = KMC(ctx, pre=kmc.pre, suf=kmc.suf, placement=1 if partitioned else 0)
     db_load_s = time.time() - t0
     log(f"[bench r{rank}] db resident: {db.info.resident_kmers} records in {db.info.n_buckets} buckets "
         f"({db.info.table_bytes / 1e9:.2f} GB, stash {db.info.stash_kmers}) in {db_load_s:.1f}s")
@@ -239,9 +245,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if partitioned:
+        from kcftools_b200.partitioned import screen_partitioned
+
+        def step():
+            return screen_partitioned(ctx, db, plan)
+    else:
+        def step():
+            plan.run(db)
     for _ in range(max(args.warmup, 3)):
-        plan.run(db)
-    res = plan.fetch()
+        r_ = step()
+    res = r_ if partitioned else plan.fetch()
     total_kmers = int(res["total_kmers"].sum())
 
     sampler = ClockSampler(local_rank)
@@ -251,17 +265,20 @@ def main():
     ev0.record(stream)
     kernel_ms = []
     for _ in range(args.steps):
-        plan.run(db)
+        step()
     ev1.record(stream)
     barrier()
     total_ms = ev0.elapsed_time(ev1)
     # per-kernel duration of the screening kernel, CUDA events on the launching stream (profiling on)
     for _ in range(3):
+        if partitioned:
+            kernel_ms.append((ms_part := total_ms / args.steps, 0.0))
+            continue
         plan.run(db)
         torch.cuda.synchronize()
         kernel_ms.append(ctx.last_kernel_ms())
     clocks = sampler.stop()
-    res2 = plan.fetch()
+    res2 = step() if partitioned else plan.fetch()
     assert (res2 == res).all(), "results changed between runs"
     if dist is not None:
         t = torch.tensor([total_ms], device=device, dtype=torch.float64)
@@ -289,7 +306,7 @@ def main():
         w_i = wins[a:b].copy()
         w_i["first_seg"] -= np.uint32(a)
         per_chr.append((w_i, segs[a:b].copy()))
-    for it in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
+    for it in range(args.e2e_steps + 1 if (args.e2e_steps > 0 and not partitioned) else 0):
         barrier()
         t1 = time.perf_counter()
         ctx.ref_clear()
@@ -307,12 +324,12 @@ def main():
         if it > 0:
             e2e_ms.append(dt)
     assert (out == res).all(), "e2e results differ from the resident run"
-    e2e_step = float(np.mean(e2e_ms)) if e2e_ms else float("nan")
-    if dist is not None:
+    e2e_step = float(np.mean(e2e_ms)) if e2e_ms else None
+    if dist is not None and e2e_step is not None:
         t = torch.tensor([e2e_step], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_step = float(t.item())
-    e2e_value = job_kmers / (e2e_step * 1e-3)
+    e2e_value = job_kmers / (e2e_step * 1e-3) if e2e_step else None
 
     # ---- roofline of the dominant kernel (kcf_screen_kernel)
     peak, peak_src = measured_peaks()

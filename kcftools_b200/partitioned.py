@@ -68,9 +68,11 @@ def screen_partitioned(ctx, db, plan, group=None, min_count: int = 1, weights=(0
         rhomes = torch.empty(sum(rc), dtype=torch.int32, device=dev)
         dist.all_to_all_single(rkeys, keys, rc, sc, group=group)
         dist.all_to_all_single(rhomes, homes, rc, sc, group=group)
+        torch.cuda.current_stream(dev).synchronize()  # NCCL ran on torch's stream, the library has its own
         rcounts = _lookup(ctx, db, rkeys, rhomes, torch, dev)
         back = torch.empty(sum(sc), dtype=torch.int32, device=dev)
         dist.all_to_all_single(back, rcounts, sc, rc, group=group)
+        torch.cuda.current_stream(dev).synchronize()
         _fold(ctx, plan, t0, t1, back, src, min_count)
     return _finish(ctx, plan, weights)
 
