@@ -214,13 +214,7 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
         const uint32_t cpos = 32 * (JJ) + lane;     /* chunk position of this lane's k-mer end */                      \
         const uint32_t q = KCF_HALO + cpos;         /* the same in staged coordinates */                               \
         const uint32_t b0 = q - k + 1;              /* first base */                                                   \
-        bool ok, ok_prev; /* validity of this k-mer and of the one ending one position earlier (Fasta.java:99-104) */  \
-        {                                                                                                              \
-            const uint32_t vb = b0 - 1, vi = vb >> 5;                                                                  \
-            const uint64_t vwin = ((((uint64_t)W.valid[vi + 1] << 32) | W.valid[vi]) >> (vb & 31u));                   \
-            ok_prev = (vwin & km1) == km1;                                                                             \
-            ok = ((vwin >> 1) & km1) == km1;                                                                           \
-        }                                                                                                              \
+        const bool ok = (W.okw[JJ] >> lane) & 1u; /* a k-mer ends here (bitmap built once per chunk) */                \
         uint64_t key; /* canonical k-mer (Kmer.java:57-79, 232-252, 300-338) */                                        \
         {                                                                                                              \
             const uint32_t wi = b0 >> 4, sh = (b0 & 15u) * 2u;                                                         \
@@ -253,14 +247,8 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
         const bool hit = ok && (int32_t)cnt >= p.min_count; /* Java int compare (GetVariants.java:224) */              \
         if (hit) sum += cnt;                                                                                           \
         const uint32_t hb = __ballot_sync(0xffffffffu, hit);                                                           \
-        const uint32_t vb = __ballot_sync(0xffffffffu, ok);                                                            \
-        const uint32_t sb = __ballot_sync(0xffffffffu, ok && !ok_prev);                                                \
         const uint32_t pb = __ballot_sync(0xffffffffu, pending);                                                       \
-        if (lane == 0) {                                                                                               \
-            atomicOr(&W.hit[JJ], hb);                                                                                  \
-            W.okw[JJ] = vb;                                                                                            \
-            W.start[JJ] = sb;                                                                                          \
-        }                                                                                                              \
+        if (lane == 0) atomicOr(&W.hit[JJ], hb);                                                                       \
         if (COUNTS) p.counts_out[(tile - p.counts_tile0) * KCF_TILE + chunk * KCF_CHUNK + cpos] = ok ? (int32_t)cnt : -1; \
         if (pb) {                                                                                                      \
             if (pending) {                                                                                             \
@@ -281,13 +269,7 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
         const uint32_t cpos = 32 * (JJ) + lane;                                                                        \
         const uint32_t q = KCF_HALO + cpos;                                                                            \
         const uint32_t b0 = q - k + 1;                                                                                 \
-        bool ok, ok_prev;                                                                                              \
-        {                                                                                                              \
-            const uint32_t vb = b0 - 1, vi = vb >> 5;                                                                  \
-            const uint64_t vwin = ((((uint64_t)W.valid[vi + 1] << 32) | W.valid[vi]) >> (vb & 31u));                   \
-            ok_prev = (vwin & km1) == km1;                                                                             \
-            ok = ((vwin >> 1) & km1) == km1;                                                                           \
-        }                                                                                                              \
+        const bool ok = (W.okw[JJ] >> lane) & 1u;                                                                      \
         uint64_t key;                                                                                                  \
         {                                                                                                              \
             const uint32_t wi = b0 >> 4, sh = (b0 & 15u) * 2u;                                                         \
@@ -301,11 +283,9 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
         const uint32_t home = kcf_home_line(min(W.hash[h0], W.hash[h0 + g.w - P2]), g);                                \
         p.x_keys[base + cpos] = key;                                                                                   \
         p.x_homes[base + cpos] = ok ? home : 0xFFFFFFFFu;                                                              \
-        const uint32_t vb2 = __ballot_sync(0xffffffffu, ok);                                                           \
-        const uint32_t sb2 = __ballot_sync(0xffffffffu, ok && !ok_prev);                                               \
         if (lane == 0) {                                                                                               \
-            p.x_okw[(base >> 5) + (JJ)] = vb2;                                                                         \
-            p.x_start[(base >> 5) + (JJ)] = sb2;                                                                       \
+            p.x_okw[(base >> 5) + (JJ)] = W.okw[JJ];                                                                   \
+            p.x_start[(base >> 5) + (JJ)] = W.start[JJ];                                                               \
         }                                                                                                              \
     } while (0)
 
@@ -343,7 +323,6 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
 
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t k = g.k;
-    const uint64_t km1 = (k == 32) ? 0xFFFFFFFFULL : ((1ULL << k) - 1ULL);
     uint32_t P2 = 1; // largest power of two <= w: the sliding minimum is built by doubling up to it
     while (2 * P2 <= g.w) P2 *= 2;
 
@@ -476,7 +455,25 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
                     sd *= four ? 4 : 2;
                 }
             }
-            for (uint32_t j = lane; j < KCF_CHUNK / 32; j += 32) W.hit[j] = W.okw[j] = W.start[j] = 0;
+            // validity of every k-mer of the chunk, 32 positions per lane: bit q of `run` is set iff the k staged validity
+            // bits q-k+1 .. q are all set (Fasta.java:99-104), built from runs of 1, 2, 4, .. bits; a k-mer opens a valid
+            // stretch when the one ending one position earlier is not valid (EFFLEN, Fasta.java:140-167)
+            if (lane < KCF_CHUNK / 32) {
+                const uint64_t v64 = ((uint64_t)W.valid[lane + 1] << 32) | W.valid[lane]; // top half = this lane's 32 positions
+                uint64_t a = v64, run = ~0ULL;
+                uint32_t pos = 0;
+#pragma unroll
+                for (uint32_t b = 0; b < 6; ++b) {
+                    if ((k >> b) & 1u) {
+                        run &= a << pos;
+                        pos += 1u << b;
+                    }
+                    a &= a << (1u << b);
+                }
+                W.okw[lane] = (uint32_t)(run >> 32);
+                W.start[lane] = (uint32_t)((run & ~(run << 1)) >> 32);
+                W.hit[lane] = 0;
+            }
             __syncwarp();
 
             if (EXTRACT) {
