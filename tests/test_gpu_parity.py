@@ -153,7 +153,7 @@ def test_high_load_factor_uses_displacement_and_stash(ctx, sc_main):
     try:
         db = KMC(ctx, pre=sc.kmc.pre, suf=sc.kmc.suf)
     finally:
-        ctx.set_load_factor(0.4)
+        ctx.set_load_factor(0.0)
     assert db.info.resident_kmers == sc.kmc.total
     wins, segs, *_ = fixed_windows(sc.seq_lens, 20_000, 0, 31)
     rc, want = _oracle_screen(sc, wins, segs)
@@ -174,7 +174,7 @@ def test_minimizer_length_and_load_factor_never_change_results(ctx, sc_main, m, 
         db = KMC(ctx, pre=sc.kmc.pre, suf=sc.kmc.suf)
     finally:
         ctx.set_minimizer_length(0)
-        ctx.set_load_factor(0.4)
+        ctx.set_load_factor(0.0)
     assert db.info.resident_kmers == sc.kmc.total
     if m <= 4:
         assert db.info.stash_kmers > 0
