@@ -39,7 +39,38 @@ WORKLOADS = {
     "c2": (12, 75_000_000, 50_000, "configs[1]: synthetic 900 Mb / 12 chr reference, k=31, 50 kb tiling windows, KMC DB of a mutated copy (~8x)"),
     "c2s": (12, 7_500_000, 50_000, "configs[1] / 10: synthetic 90 Mb / 12 chr"),
     "c1": (1, 10_000_000, 50_000, "configs[0]: synthetic 10 Mb single chromosome, k=31, 50 kb tiling windows"),
+    # gene / transcript windows (configs[2] scaled down): window size 0 = windows come from a synthetic GTF
+    "c3s": (9, 10_000_000, 0, "configs[2] / 28: synthetic 90 Mb / 9 chr reference + GTF (1,500 genes per chromosome), gene windows"),
+    "c3st": (9, 10_000_000, -1, "configs[2] / 28: synthetic 90 Mb / 9 chr reference + GTF (1,500 genes per chromosome), transcript windows"),
 }
+
+
+def gtf_windows(fasta, feature: str, seed: int = 31337):
+    """gene / transcript window and segment arrays from the C++ host (kcftools_b200/host `_windows` hook: the
+    product's own GTF logic), for a synthetic GTF over the workload's chromosomes"""
+    from tools import synth
+    from kcftools_b200._lib import SEGMENT_DTYPE, WINDOW_DTYPE
+    cli = os.path.join(ROOT, "kcftools_b200", "host", "kcftools_b200")
+    if not os.path.exists(cli):
+        subprocess.check_call(["make", "-C", os.path.dirname(cli)], stdout=subprocess.DEVNULL)
+    d = tempfile.mkdtemp(prefix="kcfbench")
+    fa, gtf = os.path.join(d, "ref.fa"), os.path.join(d, "ann.gtf")
+    fasta.write(fa)
+    open(gtf, "w").write(synth.synthetic_gtf(list(zip(fasta.names, fasta.lengths)), 1500, seed, max_tx=3, max_exons=12))
+    out = subprocess.run([cli, "_windows", "-r", fa, "-f", feature, "-g", gtf, "--kmer-size", "31"], capture_output=True, text=True, check=True).stdout
+    wl, sl = [], []
+    for line in out.split("\n"):
+        if not line.startswith("W\t"):
+            continue
+        f = line.split("\t")
+        wl.append((len(sl), len(f) - 6))
+        sl.extend(tuple(int(x) for x in t.split(":")) for t in f[6:])
+    for f_ in (fa, fa + ".faidx", gtf):
+        os.unlink(f_)
+    os.rmdir(d)
+    wins = np.array(wl, dtype=WINDOW_DTYPE)
+    segs = np.array(sl, dtype=SEGMENT_DTYPE)
+    return wins, segs
 
 
 def log(*a):
@@ -181,7 +212,11 @@ def main():
 
     fasta, kmc, window, desc = build_workload(args.workload, device, rank)
     from kcftools_b200.api import fixed_windows
-    wins, segs, starts, ends, sids = fixed_windows(fasta.lengths, window, 0, 31)
+    if window > 0:
+        wins, segs, starts, ends, sids = fixed_windows(fasta.lengths, window, 0, 31)
+    else:
+        wins, segs = gtf_windows(fasta, "gene" if window == 0 else "transcript")
+        sids = segs["seq_id"][wins["first_seg"]]  # every locus of a synthetic gene lies on the gene's chromosome
     n_wins = wins.size
     config = {"workload": f"{args.workload}: {desc}", "k": 31, "window": window, "windows": int(n_wins),
               "db_records": int(kmc.total), "reference_bp": int(sum(fasta.lengths)), "db_placement": "replicated",
@@ -302,10 +337,8 @@ def main():
     bounds = np.searchsorted(sids, np.arange(len(pinned) + 1))
     per_chr = []
     for i in range(len(pinned)):
-        a, b = int(bounds[i]), int(bounds[i + 1])
-        w_i = wins[a:b].copy()
-        w_i["first_seg"] -= np.uint32(a)
-        per_chr.append((w_i, segs[a:b].copy()))
+        from kcftools_b200 import shard
+        per_chr.append(shard.local_slice(wins, segs, int(bounds[i]), int(bounds[i + 1])))
     for it in range(args.e2e_steps + 1 if (args.e2e_steps > 0 and not partitioned) else 0):
         barrier()
         t1 = time.perf_counter()

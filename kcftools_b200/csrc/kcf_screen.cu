@@ -377,16 +377,30 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
                 const int64_t pos0 = o - KCF_HALO + 8 * (int64_t)u;
                 uint32_t c16 = 0, v8 = 0;
                 if (pos0 + 8 > 0 && pos0 < (int64_t)wlen) {
-                    if (win.n_segs == 1 && pos0 >= 0 && pos0 + 8 <= (int64_t)wlen) {
-                        // fixed / sliding window, fully inside: two funnel shifts over the packed words
-                        const kcf_segment_t sg = p.segs[win.first_seg];
+                    // the segment holding pos0 (a fixed / sliding window has one; a gene / transcript window one per merged locus)
+                    uint32_t s0 = 0;
+                    bool inside = pos0 >= 0 && pos0 + 8 <= (int64_t)wlen;
+                    if (inside && win.n_segs > 1) {
+                        uint32_t lo = 0, hi = win.n_segs; // last segment with seg_off <= pos0
+                        while (lo < hi) {
+                            uint32_t mid = (lo + hi) >> 1;
+                            if (p.seg_off[win.first_seg + mid] <= (uint32_t)pos0) lo = mid + 1;
+                            else hi = mid;
+                        }
+                        s0 = lo - 1;
+                        const uint32_t seg_end = s0 + 1 < win.n_segs ? p.seg_off[win.first_seg + s0 + 1] : wlen;
+                        inside = (uint32_t)pos0 + 8 <= seg_end;
+                    }
+                    if (inside) {
+                        // all 8 positions inside one segment: two funnel shifts over the packed words
+                        const kcf_segment_t sg = p.segs[win.first_seg + s0];
                         const KcfSeqDev sq = p.seqs[sg.seq_id];
-                        const uint32_t sp = (uint32_t)(sg.start0 + pos0);
+                        const uint32_t sp = (uint32_t)sg.start0 + ((uint32_t)pos0 - (win.n_segs > 1 ? p.seg_off[win.first_seg + s0] : 0u));
                         const uint32_t wi = sp >> 4, vi = sp >> 5;
                         c16 = __funnelshift_r(__ldg(sq.codes + wi), __ldg(sq.codes + wi + 1), (sp & 15u) * 2u) & 0xFFFFu;
                         v8 = __funnelshift_r(__ldg(sq.valid + vi), __ldg(sq.valid + vi + 1), sp & 31u) & 0xFFu;
                     } else {
-                        // window edges and multi-segment (gene / transcript) windows: base by base
+                        // window edges and segment junctions: base by base
                         uint32_t s = 0;
                         bool have = false;
                         for (int j = 0; j < 8; ++j) {
