@@ -318,8 +318,8 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
 template <int S, bool COUNTS, bool EXTRACT>
 __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_screen_kernel(KcfScreenParams p, KcfTableGeom g)
 {
-    extern __shared__ __align__(16) uint8_t kcf_smem_raw[];
-    KcfWarpSmem &W = reinterpret_cast<KcfWarpSmem *>(kcf_smem_raw)[threadIdx.x >> 5]; // the warps of a CTA share nothing
+    __shared__ __align__(16) KcfWarpSmem kcf_warp_smem[KCF_WPC];
+    KcfWarpSmem &W = kcf_warp_smem[threadIdx.x >> 5]; // the warps of a CTA share nothing
 
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t k = g.k;
@@ -800,13 +800,12 @@ int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t min_coun
     p.x_homes = plan->x_homes;
     p.x_okw = plan->x_okw;
     p.x_start = plan->x_start;
-    const size_t smem = KCF_WPC * sizeof(KcfWarpSmem);
+    const size_t smem = 0; // the per-warp buffers are static shared memory
     void (*kern)(KcfScreenParams, KcfTableGeom);
     const int S = (int)db->geom.S;
     if (extract) kern = S == 13 ? kcf_screen_kernel<13, false, true> : (S == 12 ? kcf_screen_kernel<12, false, true> : kcf_screen_kernel<10, false, true>);
     else if (d_counts) kern = S == 13 ? kcf_screen_kernel<13, true, false> : (S == 12 ? kcf_screen_kernel<12, true, false> : kcf_screen_kernel<10, true, false>);
     else kern = S == 13 ? kcf_screen_kernel<13, false, false> : (S == 12 ? kcf_screen_kernel<12, false, false> : kcf_screen_kernel<10, false, false>);
-    KCF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     KCF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * KCF_WPC, smem));
     const uint64_t n = tile_end - tile_begin;
