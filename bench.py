@@ -184,6 +184,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-windows", type=int, default=0, help="windows in the CPU baseline sample (0 = auto, ~15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cli", action="store_true",
+                    help="also time the getVariations command line end to end on files (FASTA + KMC database written to a "
+                         "temporary directory): BASELINE.json's second metric, wall time vs the host CPU")
     ap.add_argument("--placement", default="replicated", choices=["replicated", "partitioned"],
                     help="partitioned: every rank keeps 1/N of the table, k-mers are routed by NCCL all-to-all (needs --gpus > 1)")
     ap.add_argument("--lf", type=float, default=0.0, help="table load factor (0 = library default)")
@@ -399,6 +402,33 @@ def main():
             "gpu_launches": int(args.steps * plan.kernels_per_run),
             "roofline": roof, "clocks": clocks, "db_load_s": db_load_s,
             "kmers_per_step_per_gpu": total_kmers, "obs_fraction": float(res["obs"].sum() / max(total_kmers, 1))}
+
+    # ---- getVariations wall time through the command line, files to KCF (opt-in: writes the workload to disk)
+    if args.cli and rank == 0 and world == 1 and window > 0:
+        d = tempfile.mkdtemp(prefix="kcfcli")
+        try:
+            fa, pref, outp = os.path.join(d, "ref.fa"), os.path.join(d, "sample"), os.path.join(d, "out.kcf")
+            fasta.write(fa)
+            kmc.write(pref)
+            cli = os.path.join(ROOT, "kcftools_b200", "host", "kcftools_b200")
+            if not os.path.exists(cli):
+                subprocess.check_call(["make", "-C", os.path.dirname(cli)], stdout=subprocess.DEVNULL)
+            walls = []
+            for _ in range(2):  # first run also builds the .faidx; both runs read the files from the page cache
+                t1 = time.perf_counter()
+                subprocess.run([cli, "getVariations", "-r", fa, "-k", pref, "-o", outp, "-s", "bench", "-f", "window", "-w", str(window),
+                                "--device", str(local_rank)], check=True, stdout=subprocess.DEVNULL)
+                walls.append(time.perf_counter() - t1)
+            rows = [l.split("\t") for l in open(outp) if not l.startswith("#")]
+            ok = len(rows) == n_wins and all(int(r[4]) == int(res["total_kmers"][i]) and r[7].split(":")[2] == str(int(res["obs"][i]))
+                                              for i, r in enumerate(rows))
+            line["cli"] = {"wall_s_first_run": walls[0], "wall_s": walls[1], "kmers_per_s": total_kmers / walls[1],
+                           "rows_match_library": bool(ok), "input_bytes": int(fasta.data.size + kmc.pre.size + kmc.suf.size),
+                           "what": "kcftools_b200 getVariations on files in the page cache: mmap + KMC ingest (H2D, table build), .faidx, "
+                                   "FASTA H2D + pack, screening, KCF text; process start to exit"}
+        finally:
+            import shutil
+            shutil.rmtree(d, ignore_errors=True)
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
