@@ -36,46 +36,75 @@ __global__ void __launch_bounds__(256) kcf_part_count_kernel(const uint32_t *__r
     if (threadIdx.x < world && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
 }
 
-// One warp moves 32 consecutive positions at a time: the lanes bound for the same owner take consecutive slots of that
-// owner's range (one atomic per owner and warp step), so neighbouring k-mers stay neighbours on the owner's side.
+// A CTA moves KCF_SCATTER_CHUNK consecutive positions: it counts them per owner in shared memory, reserves one range per
+// owner with ONE global atomic each, and then every warp step places its lanes (the lanes bound for the same owner take
+// consecutive slots), so neighbouring k-mers stay neighbours on the owner's side and the global cursors see two
+// atomics per 4096 positions instead of one per warp step.
+#define KCF_SCATTER_CHUNK 4096
 __global__ void __launch_bounds__(256) kcf_part_scatter_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ homes,
                                                                uint64_t n, uint64_t n_lines, uint32_t world, unsigned long long *__restrict__ cursor,
                                                                unsigned long long *__restrict__ keys_out, uint32_t *__restrict__ homes_out,
                                                                uint32_t *__restrict__ src_out)
 {
+    __shared__ unsigned int s_cnt[KCF_MAX_WORLD], s_off[KCF_MAX_WORLD];
+    __shared__ unsigned long long s_base[KCF_MAX_WORLD];
     const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t i0 = warp * 32; i0 < n; i0 += n_warps * 32) {
-        const uint64_t i = i0 + lane;
-        const uint32_t h = i < n ? homes[i] : 0xFFFFFFFFu;
-        const uint32_t owner = h != 0xFFFFFFFFu ? kcf_line_owner(h, n_lines, world) : 0xFFFFFFFFu;
-        uint32_t todo = __ballot_sync(0xffffffffu, owner != 0xFFFFFFFFu);
-        while (todo) {
-            const uint32_t leader = __ffs(todo) - 1;
-            const uint32_t o = __shfl_sync(0xffffffffu, owner, leader);
-            const uint32_t same = __ballot_sync(0xffffffffu, owner == o);
-            unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(&cursor[o], (unsigned long long)__popc(same));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (owner == o) {
-                const uint64_t dst = base + __popc(same & ((1u << lane) - 1u));
-                keys_out[dst] = keys[i];
-                homes_out[dst] = h;
-                src_out[dst] = (uint32_t)i;
-            }
-            todo &= ~same;
+    for (uint64_t c0 = (uint64_t)blockIdx.x * KCF_SCATTER_CHUNK; c0 < n; c0 += (uint64_t)gridDim.x * KCF_SCATTER_CHUNK) {
+        if (threadIdx.x < KCF_MAX_WORLD) s_cnt[threadIdx.x] = s_off[threadIdx.x] = 0;
+        __syncthreads();
+        const uint64_t c1 = min(c0 + (uint64_t)KCF_SCATTER_CHUNK, n);
+        for (uint64_t i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+            const uint32_t h = homes[i];
+            if (h != 0xFFFFFFFFu) atomicAdd(&s_cnt[kcf_line_owner(h, n_lines, world)], 1u);
         }
+        __syncthreads();
+        if (threadIdx.x < world && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+        __syncthreads();
+        for (uint64_t i0 = c0 + (threadIdx.x & ~31u); i0 < c1; i0 += blockDim.x) {
+            const uint64_t i = i0 + lane;
+            const uint32_t h = i < c1 ? homes[i] : 0xFFFFFFFFu;
+            const uint32_t owner = h != 0xFFFFFFFFu ? kcf_line_owner(h, n_lines, world) : 0xFFFFFFFFu;
+            uint32_t todo = __ballot_sync(0xffffffffu, owner != 0xFFFFFFFFu);
+            while (todo) {
+                const uint32_t leader = __ffs(todo) - 1;
+                const uint32_t o = __shfl_sync(0xffffffffu, owner, leader);
+                const uint32_t same = __ballot_sync(0xffffffffu, owner == o);
+                unsigned int off = 0;
+                if (lane == leader) off = atomicAdd(&s_off[o], (unsigned int)__popc(same));
+                off = __shfl_sync(0xffffffffu, off, leader);
+                if (owner == o) {
+                    const uint64_t dst = s_base[o] + off + __popc(same & ((1u << lane) - 1u));
+                    keys_out[dst] = keys[i];
+                    homes_out[dst] = h;
+                    src_out[dst] = (uint32_t)i;
+                }
+                todo &= ~same;
+            }
+        }
+        __syncthreads();
     }
 }
 
 // ---- owner: probe the local slice -----------------------------------------------------------------------------------
+// Threads own consecutive received k-mers = consecutive k-mers of the sender, so the lanes of a warp mostly ask for the
+// same few home lines and the coalescer merges them, as in the replicated kernel.
+template <int S>
 __global__ void __launch_bounds__(256) kcf_part_lookup_kernel(const uint8_t *__restrict__ table, const KcfStashEntry *__restrict__ stash,
                                                               KcfTableGeom g, const unsigned long long *__restrict__ keys,
                                                               const uint32_t *__restrict__ homes, uint64_t n, uint32_t *__restrict__ counts)
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    counts[i] = kcf_lookup_at(table, stash, g, keys[i], homes[i]);
+    const uint64_t key = keys[i];
+    const uint32_t home = homes[i];
+    const uint8_t *L = table + (uint64_t)kcf_line_wrap(home, 0, g) * KCF_LINE_BYTES;
+    uint32_t c = 0;
+    if (!(KCF_KEY_IN_LINES(key) && kcf_probe_line<S>(L, key, c))) {
+        c = 0;
+        if (kcf_filter_pass(L, key, g))
+            c = kcf_probe_lines(table, stash, g, key, home, kcf_mask_from_word31(__ldg(reinterpret_cast<const uint32_t *>(L) + 31)), 1);
+    }
+    counts[i] = c;
 }
 
 // ---- requester: counts back to positions, then the gap summaries -----------------------------------------------------
@@ -278,8 +307,12 @@ extern "C" int kcf_xchg_lookup(kcf_ctx *ctx, kcf_db *db, const void *d_keys, con
     if (!ctx || !db || db->ctx != ctx || (n && (!d_keys || !d_homes || !d_counts_out))) return KCF_ERR_ARG;
     if (n == 0) return KCF_OK;
     KCF_CUDA(ctx, cudaSetDevice(ctx->device));
-    kcf_part_lookup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(db->table, db->stash, db->geom, (const unsigned long long *)d_keys,
-                                                                                 (const uint32_t *)d_homes, n, (uint32_t *)d_counts_out);
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    const unsigned long long *kp = (const unsigned long long *)d_keys;
+    const uint32_t *hp = (const uint32_t *)d_homes;
+    if (db->geom.S == 13) kcf_part_lookup_kernel<13><<<grid, 256, 0, ctx->stream>>>(db->table, db->stash, db->geom, kp, hp, n, (uint32_t *)d_counts_out);
+    else if (db->geom.S == 12) kcf_part_lookup_kernel<12><<<grid, 256, 0, ctx->stream>>>(db->table, db->stash, db->geom, kp, hp, n, (uint32_t *)d_counts_out);
+    else kcf_part_lookup_kernel<10><<<grid, 256, 0, ctx->stream>>>(db->table, db->stash, db->geom, kp, hp, n, (uint32_t *)d_counts_out);
     KCF_CUDA(ctx, cudaGetLastError());
     KCF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return KCF_OK;

@@ -141,38 +141,6 @@ struct KcfWarpSmem {
 };
 
 
-// Probe one table line for `key`: the S low key words sit in the line's first two 32-byte sectors (4 x 16-byte loads);
-// live low words of a line are distinct, so the low-word match is the only candidate and is confirmed on the high word.
-// The loads allocate in L1: the high word, the count, the filter and the mask of the same line are read right after.
-template <int S>
-__device__ __forceinline__ bool kcf_probe_line(const uint8_t *line, uint64_t key, uint32_t &count)
-{
-    const uint4 *q = reinterpret_cast<const uint4 *>(line);
-    const uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
-    const uint32_t lo = (uint32_t)key;
-    int idx = -1;
-    if (a.x == lo) idx = 0;
-    if (a.y == lo) idx = 1;
-    if (a.z == lo) idx = 2;
-    if (a.w == lo) idx = 3;
-    if (b.x == lo) idx = 4;
-    if (b.y == lo) idx = 5;
-    if (b.z == lo) idx = 6;
-    if (b.w == lo) idx = 7;
-    if (c.x == lo) idx = 8;
-    if (c.y == lo) idx = 9;
-    if (S > 10 && c.z == lo) idx = 10;
-    if (S > 11 && c.w == lo) idx = 11;
-    if (S > 12 && d.x == lo) idx = 12;
-    if (idx < 0) return false;
-    if (__ldg(reinterpret_cast<const uint32_t *>(line) + S + idx) != (uint32_t)(key >> 32)) return false;
-    constexpr int CW = S == 13 ? 1 : (S == 12 ? 2 : 4);
-    constexpr int COFF = S == 13 ? 112 : 8 * S;
-    const uint8_t *cp = line + COFF + CW * idx;
-    count = CW == 1 ? (uint32_t)__ldg(cp) : (CW == 2 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(cp)) : __ldg(reinterpret_cast<const uint32_t *>(cp)));
-    return true;
-}
-
 // gap summary of 32 consecutive positions from their bitmaps (bit i = position i): `vw` marks the positions where a
 // k-mer ends, `hw` (a subset) the observed ones.  Positions without a k-mer are transparent: a miss run continues
 // across them (GetVariants.java:217-245 runs over the compacted k-mer list).

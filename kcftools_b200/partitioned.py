@@ -55,11 +55,23 @@ def screen_partitioned(ctx, db, plan, group=None, min_count: int = 1, weights=(0
     import torch.distributed as dist
     world, dev = dist.get_world_size(group), torch.device("cuda", ctx.device)
     # every rank takes part in every all-to-all: loop over the largest batch count
+    import os
+    import time
+    trace = os.environ.get("KCF_PART_TRACE") and dist.get_rank(group) == 0
+    tt = {"extract": 0.0, "a2a_keys": 0.0, "lookup": 0.0, "a2a_counts": 0.0, "fold": 0.0}
+
+    def lap(name, t):
+        if trace:
+            torch.cuda.synchronize(dev)
+            tt[name] += time.perf_counter() - t
+        return time.perf_counter()
     nb = torch.tensor([(plan.n_tiles + batch_tiles - 1) // batch_tiles], device=dev)
     dist.all_reduce(nb, op=dist.ReduceOp.MAX, group=group)
     for b in range(int(nb.item())):
         t0, t1 = b * batch_tiles, (b + 1) * batch_tiles
+        t = time.perf_counter()
         keys, homes, src, sc = _extract(ctx, db, plan, t0, t1, world, torch, dev)
+        t = lap("extract", t)
         send = torch.tensor(sc, dtype=torch.int64, device=dev)
         recv = torch.empty_like(send)
         dist.all_to_all_single(recv, send, group=group)
@@ -69,11 +81,17 @@ def screen_partitioned(ctx, db, plan, group=None, min_count: int = 1, weights=(0
         dist.all_to_all_single(rkeys, keys, rc, sc, group=group)
         dist.all_to_all_single(rhomes, homes, rc, sc, group=group)
         torch.cuda.current_stream(dev).synchronize()  # NCCL ran on torch's stream, the library has its own
+        t = lap("a2a_keys", t)
         rcounts = _lookup(ctx, db, rkeys, rhomes, torch, dev)
+        t = lap("lookup", t)
         back = torch.empty(sum(sc), dtype=torch.int32, device=dev)
         dist.all_to_all_single(back, rcounts, sc, rc, group=group)
         torch.cuda.current_stream(dev).synchronize()
+        t = lap("a2a_counts", t)
         _fold(ctx, plan, t0, t1, back, src, min_count)
+        t = lap("fold", t)
+    if trace:
+        print("[partitioned] ms per phase:", {k: round(1e3 * v, 3) for k, v in tt.items()}, flush=True)
     return _finish(ctx, plan, weights)
 
 
