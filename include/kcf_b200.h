@@ -123,8 +123,8 @@ void kcf_db_close(kcf_db *db);
 /* Load-factor target for subsequently opened databases (0 < lf <= 0.9; 0 = automatic, the default: 0.3, denser when
  * the table would take more than 40 % of the device memory). */
 int kcf_set_load_factor(kcf_ctx *ctx, double lf);
-/* Minimizer length of the home-line function for subsequently opened databases (1..16; 0 = chosen from the
- * database size).  A tuning / test knob: results never depend on it. */
+/* Minimizer length of the home-line function for subsequently opened databases (1..24; 0 = chosen from the
+ * database size and k).  A tuning / test knob: results never depend on it. */
 int kcf_set_minimizer_length(kcf_ctx *ctx, int m);
 
 /* KMC.getCount for a batch of k-mers given as ASCII (n * k bytes, upper or lower case ACGT), canonicalised

@@ -262,7 +262,7 @@ extern "C" int kcf_set_load_factor(kcf_ctx *ctx, double lf)
 extern "C" int kcf_set_minimizer_length(kcf_ctx *ctx, int m)
 {
     if (!ctx) return KCF_ERR_ARG;
-    if (m < 0 || m > 16) return kcf_fail(ctx, KCF_ERR_ARG, "minimizer length must be 0 (auto) or 1..16");
+    if (m < 0 || m > 24) return kcf_fail(ctx, KCF_ERR_ARG, "minimizer length must be 0 (auto) or 1..24");
     ctx->minimizer_len = m;
     return KCF_OK;
 }
@@ -342,19 +342,21 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     g.fbits = g.cw == 1 ? 64u : 32u;
     g.both_strands = (uint32_t)info.both_strands;
     {
-        // minimizer length: long enough that one m-mer value rarely names more than one locus of the
-        // sampled genome (4^m >= 4 N), short enough that consecutive k-mers share it (w = k-m+1)
+        // minimizer length: long enough that one m-mer value rarely names more than one locus of the sampled genome
+        // (4^m >= 4 N) and that a run of k-mers sharing it fits one line (w = k-m+1 <= S: a group larger than a line always
+        // overflows), short enough that consecutive k-mers share it at all
         int m = ctx->minimizer_len;
         if (m <= 0) {
             m = 8;
             while (m < 16 && (1ULL << (2 * m)) < 4 * N) ++m;
+            m = std::max(m, k - (int)g.S + 1);
         }
-        m = std::min(std::min(m, 16), k);
+        m = std::min(std::min(m, 24), k);
         m = std::max(m, 1);
         if (k - m + 1 > 32) m = k - 31;
         g.m = (uint32_t)m;
         g.w = (uint32_t)(k - m + 1);
-        g.mmask = m == 16 ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
+        g.mmask = (1ULL << (2 * m)) - 1ULL;
     }
     double lf = ctx->load_factor;
     if (lf <= 0.0) { // automatic: 0.3 is the fastest measured (fewest displaced keys); give memory back when it is scarce
@@ -371,12 +373,14 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     g.n_lines = nb;
     g.line_lo = 0;
     g.n_local = nb;
-    if (part_world > 1) { // lines [lo, hi) of the global line space + spill lines for keys displaced past hi
+    if (part_world > 1) { // home lines [lo, hi) of the global line space
         const uint64_t lo = (nb * part_rank + part_world - 1) / part_world, hi = (nb * (part_rank + 1) + part_world - 1) / part_world;
         g.line_lo = lo;
-        g.n_local = hi - lo + KCF_MAX_DISP;
-        nb = g.n_local; // lines allocated below
+        g.n_local = hi - lo;
     }
+    g.n_ov = cs == 0 ? 1 : std::max<uint64_t>(g.n_local / 8, 32); // overflow region: 1/8 of the home lines
+    nb = g.n_local + g.n_ov;                                       // lines allocated below
+    if (nb >= 0xFFFFFFFFULL) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "%llu table lines do not fit a 32-bit line index; partition the database", (unsigned long long)nb);
     g.stash_mask = 0;
 
     kcf_db *db = new kcf_db();

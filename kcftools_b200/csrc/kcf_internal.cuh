@@ -23,10 +23,11 @@
 //            (S = 13 slots and a 64-bit filter for 1-byte counts; 12 / 10 slots and 32 bits for 2 / 4-byte counts;
 //             key = canonical k-mer value, stored in full; low word 0xFFFFFFFF = empty slot)
 //
-// A key lives in line home+d, 0 <= d <= 14, the first one with a free slot when it was inserted
-// (no deletions).  Bit d of the HOME line's mask says "some key homed here lives in home+d", bit 15
-// "some key homed here lives in the stash"; a lookup therefore knows after reading the home line
-// exactly which other lines (if any) can hold its key.  The filter is a 2-hash Bloom filter over the keys homed
+// A key lives in its home line or, when that was full at insertion time (no deletions), in one of 14 lines of a
+// separate OVERFLOW region starting at a hash of the home line — home lines only ever hold their own keys, so one
+// crowded line does not push its neighbours' keys out.  Bit 0 of the HOME line's mask says "a key homed here lives
+// here", bit d >= 1 "... in overflow line ov(home) + d - 1", bit 15 "... in the stash"; a lookup therefore knows after
+// reading the home line exactly which other lines (if any) can hold its key.  The filter is a 2-hash Bloom filter over the keys homed
 // here that live elsewhere: a k-mer that misses in its home line and fails the filter is absent, and no other line
 // is read for it (absent k-mers are a quarter of a typical reference scan).  Keys are stored in full: a probe is
 // exact; the filter can only cause extra probes, never a wrong answer.
@@ -39,16 +40,17 @@
 #define KCF_KEY_IN_LINES(key) ((uint32_t)(key) != KCF_EMPTY_LO)
 
 struct KcfTableGeom {
-    uint64_t n_lines;    // < 2^32 - 1; the GLOBAL number of lines (home lines are computed against it)
-    uint64_t line_lo;    // global index of local line 0 (0 unless the database is partitioned)
-    uint64_t n_local;    // lines held by this table (== n_lines unless partitioned: own range + 14 spill lines)
+    uint64_t n_lines;    // < 2^32 - 1; the GLOBAL number of home lines (home lines are computed against it)
+    uint64_t line_lo;    // global index of local home line 0 (0 unless the database is partitioned)
+    uint64_t n_local;    // home lines held by this table (== n_lines unless partitioned)
+    uint64_t n_ov;       // overflow lines, stored after the home lines: keys that do not fit their home line
     uint64_t kmask;      // 2k one-bits
     uint64_t stash_mask; // stash capacity - 1 (power of two), 0 when the stash is empty
     uint32_t k;
     uint32_t kshift;     // 64 - 2k
-    uint32_t m;          // minimizer length, 1..16, <= k
+    uint32_t m;          // minimizer length, 1..24, <= k
     uint32_t w;          // k - m + 1 (1..32)
-    uint32_t mmask;      // 2m one-bits
+    uint64_t mmask;      // 2m one-bits
     uint32_t S;          // slots per line: 13 / 12 / 10 for count width 1 / 2 / 4
     uint32_t cw;         // bytes per stored count: 1, 2 or 4 (0-byte counters store nothing)
     uint32_t coff;       // byte offset of the counts inside a line: 112 / 96 / 80

@@ -29,9 +29,10 @@ __device__ __forceinline__ uint64_t kcf_pair_reverse(uint64_t x, uint32_t kshift
 // and its reverse complement get the same value.
 __device__ __forceinline__ uint32_t kcf_mmer_order(uint64_t E, uint64_t R, uint32_t j, const KcfTableGeom &g)
 {
-    const uint32_t x = (uint32_t)(E >> (2 * j)) & g.mmask;
-    const uint32_t r = (uint32_t)(R >> (2 * (32 - g.m - j))) & g.mmask;
-    return kcf_mix32(min(x, r));
+    const uint64_t x = (E >> (2 * j)) & g.mmask;
+    const uint64_t r = (R >> (2 * (32 - g.m - j))) & g.mmask;
+    const uint64_t c = min(x, r);
+    return kcf_mix32((uint32_t)c ^ ((uint32_t)(c >> 32) * 0x9E3779B1u)); // m <= 16: the plain 32-bit value
 }
 
 __device__ __forceinline__ uint32_t kcf_home_line(uint32_t mu, const KcfTableGeom &g)
@@ -49,12 +50,14 @@ __device__ __forceinline__ uint32_t kcf_minimizer_of_key(uint64_t key, const Kcf
     return mu;
 }
 
-// local index of global line home + d (wraps around the table; a partitioned table keeps 14 spill lines instead)
+// local index of the line that mask bit d of home line `home` names: d = 0 the home line itself, d >= 1 the (d-1)-th
+// line of the home's probe sequence in the overflow region (stored after the local home lines)
 __device__ __forceinline__ uint32_t kcf_line_wrap(uint32_t home, uint32_t d, const KcfTableGeom &g)
 {
-    uint64_t l = (uint64_t)home - g.line_lo + d;
-    if (l >= g.n_local) l -= g.n_local;
-    return (uint32_t)l;
+    if (d == 0) return (uint32_t)(home - g.line_lo);
+    uint64_t o = __umulhi(kcf_mix32(home ^ 0x85EBCA6Bu), (uint32_t)g.n_ov) + (d - 1);
+    if (o >= g.n_ov) o -= g.n_ov;
+    return (uint32_t)(g.n_local + o);
 }
 
 // rank that owns a home line when the line space is cut in `world` equal ranges

@@ -162,7 +162,7 @@ def test_high_load_factor_uses_displacement_and_stash(ctx, sc_main):
     db.close()
 
 
-@pytest.mark.parametrize("m,lf", [(16, 0.5), (12, 0.3), (4, 0.5), (1, 0.9), (10, 0.9)])
+@pytest.mark.parametrize("m,lf", [(16, 0.5), (12, 0.3), (4, 0.5), (1, 0.9), (10, 0.9), (19, 0.3), (24, 0.6)])
 def test_minimizer_length_and_load_factor_never_change_results(ctx, sc_main, m, lf):
     """the home-line function (minimizer length) and the load factor are layout knobs only.  m = 4 / 1 pile thousands
     of keys onto few minimizers: displaced lines, continuation fetches and the stash all get exercised."""
