@@ -349,7 +349,7 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
         if (m <= 0) {
             m = 8;
             while (m < 16 && (1ULL << (2 * m)) < 4 * N) ++m;
-            m = std::max(m, k - (int)g.S + 1);
+            m = std::max(m, k - (int)g.S + 2);
         }
         m = std::min(std::min(m, 24), k);
         m = std::max(m, 1);
@@ -359,11 +359,12 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
         g.mmask = (1ULL << (2 * m)) - 1ULL;
     }
     double lf = ctx->load_factor;
-    if (lf <= 0.0) { // automatic: 0.3 is the fastest measured (fewest displaced keys); give memory back when it is scarce
+    if (lf <= 0.0) { // automatic: sparse tables are faster (fewer keys outside their home line: 60.7 / 64.8 / 68.6 G k-mers/s at
+                     // 0.4 / 0.3 / 0.2 on C2); start at 0.2 and give memory back when it is scarce
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         const double share = part_world > 1 ? 1.0 / part_world : 1.0;
-        lf = 0.3;
+        lf = 0.2;
         // against the device's TOTAL memory: every rank of a partitioned database must derive the same geometry
         while (lf < 0.6 && (double)N * share / (g.S * lf) * KCF_LINE_BYTES > 0.4 * (double)total_b) lf += 0.1;
     }
