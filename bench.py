@@ -187,8 +187,13 @@ def main():
     ap.add_argument("--cli", action="store_true",
                     help="also time the getVariations command line end to end on files (FASTA + KMC database written to a "
                          "temporary directory): BASELINE.json's second metric, wall time vs the host CPU")
-    ap.add_argument("--placement", default="replicated", choices=["replicated", "partitioned"],
-                    help="partitioned: every rank keeps 1/N of the table, k-mers are routed by NCCL all-to-all (needs --gpus > 1)")
+    ap.add_argument("--placement", default="replicated", choices=["replicated", "partitioned", "partitioned-scan"],
+                    help="partitioned: every rank keeps 1/N of the table, k-mers are routed by NCCL all-to-all (needs --gpus > 1); "
+                         "partitioned-scan: same table slices, every rank walks ALL windows and probes what it owns, hit bitmaps are "
+                         "all-reduced (total work fixed: strong scaling)")
+    ap.add_argument("--table-parts", type=int, default=0,
+                    help="partitioned-scan only: slices of the table (default = N); N / table-parts window shards, each screened by a "
+                         "group of table-parts GPUs (e.g. --gpus 8 --table-parts 2: half a table per GPU, 4 window shards)")
     ap.add_argument("--lf", type=float, default=0.0, help="table load factor (0 = library default)")
     ap.add_argument("--m", type=int, default=0, help="minimizer length (0 = automatic)")
     args = ap.parse_args()
@@ -257,10 +262,23 @@ def main():
         ctx.set_minimizer_length(args.m)
     stream = torch.cuda.ExternalStream(ctx.stream, device=device)
     t0 = time.time()
-    partitioned = args.placement == "partitioned" and world > 1
+    partitioned = args.placement.startswith("partitioned") and world > 1
+    scan = partitioned and args.placement == "partitioned-scan"
+    tparts = (args.table_parts or world) if scan else world
+    scan_group, scan_shard, n_shards = None, 0, 1
+    if scan:
+        from kcftools_b200 import shard as _shard
+        n_shards = world // tparts
+        for s_ in range(n_shards):  # every rank creates every group (torch.distributed rule)
+            g_ = dist.new_group(list(range(s_ * tparts, (s_ + 1) * tparts)))
+            if s_ == rank // tparts:
+                scan_group = g_
+        part_rank, scan_shard, _ = _shard.grid_layout(rank, world, tparts)
     if partitioned:
-        ctx.set_partition(rank, world)
-        config["db_placement"] = f"partitioned by home line, 1/{world} per GPU, k-mers routed by NCCL all-to-all"
+        ctx.set_partition(part_rank if scan else rank, tparts)
+        config["db_placement"] = (f"partitioned by home line, 1/{tparts} per GPU, {n_shards} window shard(s); every rank walks its shard's windows and "
+                                  "probes the k-mers it owns, hit bitmaps + count sums all-reduced inside the shard's group (NCCL)" if scan else
+                                  f"partitioned by home line, 1/{world} per GPU, k-mers routed by NCCL all-to-all")
     db = KMC(ctx, pre=kmc.pre, suf=kmc.suf, placement=1 if partitioned else 0)
     db_load_s = time.time() - t0
     log(f"[bench r{rank}] db resident: {db.info.resident_kmers} records in {db.info.n_buckets} buckets "
@@ -274,6 +292,10 @@ def main():
         pinned.append(pb)
     for i, pb in enumerate(pinned):
         ctx.ref_add(pb, fasta.line_bases[i], fasta.line_width[i], fasta.lengths[i])
+    all_wins = wins
+    if scan and n_shards > 1:  # this rank's group screens one contiguous shard of the window list
+        rng = _shard.partition(_shard.window_lengths(wins, segs), n_shards)[scan_shard]
+        wins, segs = _shard.local_slice(wins, segs, *rng)
     plan = ctx.plan(31, wins, segs)
     ctx.set_profiling(True)
 
@@ -284,10 +306,10 @@ def main():
         torch.cuda.synchronize()
 
     if partitioned:
-        from kcftools_b200.partitioned import screen_partitioned
+        from kcftools_b200.partitioned import screen_partitioned, screen_partitioned_scan
 
         def step():
-            return screen_partitioned(ctx, db, plan)
+            return screen_partitioned_scan(ctx, db, plan, group=scan_group) if scan else screen_partitioned(ctx, db, plan)
     else:
         def step():
             plan.run(db)
@@ -324,7 +346,8 @@ def main():
         total_ms = float(t.item())
         k_all = torch.tensor([total_kmers], device=device, dtype=torch.int64)
         dist.all_reduce(k_all, op=dist.ReduceOp.SUM)
-        job_kmers = int(k_all.item())
+        # scan placement: ONE copy of the workload screened by all ranks together (every rank of a group reports its shard)
+        job_kmers = int(k_all.item()) // tparts if scan else int(k_all.item())
     else:
         job_kmers = total_kmers
     ms_per_step = total_ms / args.steps
@@ -339,7 +362,7 @@ def main():
     out = res
     bounds = np.searchsorted(sids, np.arange(len(pinned) + 1))
     per_chr = []
-    for i in range(len(pinned)):
+    for i in range(len(pinned) if not partitioned else 0):
         from kcftools_b200 import shard
         per_chr.append(shard.local_slice(wins, segs, int(bounds[i]), int(bounds[i + 1])))
     for it in range(args.e2e_steps + 1 if (args.e2e_steps > 0 and not partitioned) else 0):
@@ -394,7 +417,7 @@ def main():
             pass
 
     line = {"metric": "ref k-mers screened/s", "value": value, "unit": "kmers/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if scan else "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "kmers/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_step, "what": "per chromosome: kcf_ref_add_async (pinned FASTA bytes -> H2D -> 2-bit pack) + kcf_plan_create (window "

@@ -189,6 +189,54 @@ int kcf_xchg_fold(kcf_ctx *ctx, kcf_plan *plan, uint64_t tile_begin, uint64_t ti
 /* Requester, last: scores and rows from the tile summaries (Data.java:70-107); then kcf_plan_fetch. */
 int kcf_plan_finalize(kcf_ctx *ctx, kcf_plan *plan, const double w[3]);
 
+/* Scan placement — the second way to screen against a partitioned table, without moving k-mers: the plan holds ALL
+ * windows on every rank (the 2-bit reference is replicated; it is small next to the table), every rank runs
+ * Fasta.getKmersList (Fasta.java:90-127) over tiles [tile_begin, tile_end) but does KMC.getCount (KMC.java:292-326)
+ * only for the k-mers whose home line lies in its slice.  Output (device buffers of the caller): d_hit_out = one uint32
+ * per 32 positions (bit = k-mer observed with count >= min_count BY THIS RANK), d_sum_out = one uint64 per tile (Σcount
+ * of those hits).  The caller sum-reduces both over the ranks (the owners' bitmaps are disjoint: + is OR; NCCL
+ * all-reduce) and hands the totals to kcf_scan_fold, which rebuilds the gap summaries (GetVariants.java:217-252);
+ * then kcf_plan_finalize / kcf_plan_fetch as above. */
+int kcf_scan_owned(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, uint64_t tile_begin, uint64_t tile_end, int32_t min_count,
+                   void *d_hit_out, void *d_sum_out);
+int kcf_scan_fold(kcf_ctx *ctx, kcf_plan *plan, uint64_t tile_begin, uint64_t tile_end, const void *d_hit, const void *d_sum);
+
+/* ---- windows x samples matrix: cohort, findIBS, kcf2gt ---------------------------------------
+ * The consumers of getVariations output, kept on the device: a cohort is the matrix [sample][window] of the per-window
+ * integers, filled either straight from the rows of a kcf_plan (no KCF text in between; replaces writing and re-reading
+ * one file per sample before Plugins/Cohort.java:71-119) or from rows the host parsed out of KCF files
+ * (Data/KCFReader.java:31-105, Data/Window.java:42-83). */
+typedef struct kcf_cohort kcf_cohort;
+typedef struct kcf_cell_t {   /* one sample in one window = Data/Data.java:16-24; 40 bytes */
+    int32_t obs, variations, inner, left, right;
+    int32_t ibs;              /* -1 = "N" */
+    int64_t kmer_count;       /* Σ count (from a plan) or Math.round(KD * obs) (from a KCF row, Window.java:70) */
+    double score;
+} kcf_cell_t;
+/* total_kmers / eff_len: per window (host arrays), or both NULL when the first kcf_cohort_add_plan is to define them. */
+int kcf_cohort_create(kcf_ctx *ctx, uint64_t n_windows, uint32_t n_samples, const int32_t *total_kmers, const int32_t *eff_len,
+                      kcf_cohort **out);
+void kcf_cohort_destroy(kcf_cohort *c);
+/* Column `sample`, rows [window_offset, window_offset + plan windows) <- the results of a plan that has run (device to
+ * device, asynchronous).  A sample whose TOTAL_KMERS / EFFLEN differ from the cohort's is "Windows mismatch"
+ * (Cohort.java:92-94), reported by kcf_cohort_scores / kcf_cohort_fetch. */
+int kcf_cohort_add_plan(kcf_ctx *ctx, kcf_cohort *c, uint32_t sample, uint64_t window_offset, kcf_plan *plan);
+/* Column `sample` <- n_windows cells parsed by the host (needs the totals given to kcf_cohort_create). */
+int kcf_cohort_set_sample(kcf_ctx *ctx, kcf_cohort *c, uint32_t sample, const kcf_cell_t *cells);
+/* Every cell's score from its integers and the weights {wi, wt, wr}, as the reference does whenever it reads a KCF row
+ * (Window.java:42-83 -> Data.java:41-67, 95-107); KCF_ERR_WEIGHTS as in kcf_plan_fetch. */
+int kcf_cohort_scores(kcf_ctx *ctx, kcf_cohort *c, const double w[3]);
+/* FindIBS.java:118-158 for every sample: order[p] = window index at traversal position p (the reference walks a HashMap
+ * of chromosomes, windows in file order inside each), chrom[p] = ordinal of that window's chromosome; a window is IBS
+ * when score >= cutoff (detect_var: score < cutoff), blocks are numbered per sample; result in kcf_cell_t.ibs. */
+int kcf_cohort_find_ibs(kcf_ctx *ctx, kcf_cohort *c, const uint32_t *order, const uint32_t *chrom, uint64_t n, int detect_var,
+                        int32_t min_consecutive, float score_cutoff);
+/* KCFToGenotypeTable.java:116-133, 159-172: alleles_out[window][sample] in {0, 2, 1, -1}, bad_out[window] = badWindow(). */
+int kcf_cohort_genotypes(kcf_ctx *ctx, kcf_cohort *c, double score_a, double score_b, double score_n, double min_maf, double max_missing,
+                         int8_t *alleles_out, uint8_t *bad_out);
+/* Column `sample` (and the per-window totals; any pointer may be NULL) back to the host. */
+int kcf_cohort_fetch(kcf_ctx *ctx, kcf_cohort *c, uint32_t sample, kcf_cell_t *cells_out, int32_t *total_kmers_out, int32_t *eff_len_out);
+
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* Random 32-byte-sector gather bandwidth of this GPU (the random-access roofline of SURVEY §8(d)):
  * n_loads independent 32-B loads from uniformly random sector addresses of a buffer of n_bytes. */

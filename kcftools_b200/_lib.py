@@ -18,6 +18,9 @@ RESULT_DTYPE = np.dtype([("total_kmers", "<i4"), ("eff_len", "<i4"), ("obs", "<i
                          ("kmer_count_sum", "<i8"), ("score", "<f8")])
 WINDOW_DTYPE = np.dtype([("first_seg", "<u4"), ("n_segs", "<u4")])
 SEGMENT_DTYPE = np.dtype([("seq_id", "<i4"), ("start0", "<i4"), ("len", "<i4")])
+CELL_DTYPE = np.dtype([("obs", "<i4"), ("variations", "<i4"), ("inner", "<i4"), ("left", "<i4"), ("right", "<i4"), ("ibs", "<i4"),
+                       ("kmer_count", "<i8"), ("score", "<f8")])  # kcf_cell_t
+assert CELL_DTYPE.itemsize == 40
 assert RESULT_DTYPE.itemsize == 48 and WINDOW_DTYPE.itemsize == 8 and SEGMENT_DTYPE.itemsize == 12
 
 STATUS = {0: "KCF_OK", -1: "KCF_ERR_CUDA", -2: "KCF_ERR_IO", -3: "KCF_ERR_DB_FORMAT", -4: "KCF_ERR_UNSUPPORTED",
@@ -66,6 +69,16 @@ SYMBOLS = {
     "kcf_xchg_lookup": (C.c_int, [_P, _P, _P, _P, C.c_uint64, _P]),
     "kcf_xchg_fold": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P, _P, C.c_uint64, C.c_int32]),
     "kcf_plan_finalize": (C.c_int, [_P, _P, C.POINTER(C.c_double)]),
+    "kcf_cohort_create": (C.c_int, [_P, C.c_uint64, C.c_uint32, _P, _P, C.POINTER(_P)]),
+    "kcf_cohort_destroy": (None, [_P]),
+    "kcf_cohort_add_plan": (C.c_int, [_P, _P, C.c_uint32, C.c_uint64, _P]),
+    "kcf_cohort_set_sample": (C.c_int, [_P, _P, C.c_uint32, _P]),
+    "kcf_cohort_scores": (C.c_int, [_P, _P, C.POINTER(C.c_double)]),
+    "kcf_cohort_find_ibs": (C.c_int, [_P, _P, _P, _P, C.c_uint64, C.c_int, C.c_int32, C.c_float]),
+    "kcf_cohort_genotypes": (C.c_int, [_P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P]),
+    "kcf_cohort_fetch": (C.c_int, [_P, _P, C.c_uint32, _P, _P, _P]),
+    "kcf_scan_owned": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_int32, _P, _P]),
+    "kcf_scan_fold": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P, _P]),
     "kcf_measure_random_sector_gbps": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
     "kcf_set_profiling": (C.c_int, [_P, C.c_int]),
     "kcf_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

@@ -224,6 +224,57 @@ class Plan:
             self._h = C.c_void_p()
 
 
+class Cohort:
+    """windows x samples matrix resident on the device (Plugins/Cohort.java, FindIBS.java, KCFToGenotypeTable.java)."""
+
+    def __init__(self, ctx: Context, n_windows: int, n_samples: int, total_kmers: np.ndarray | None = None, eff_len: np.ndarray | None = None):
+        self.ctx, self._lib = ctx, ctx._lib
+        self.n_windows, self.n_samples = int(n_windows), int(n_samples)
+        self._h = C.c_void_p()
+        t = None if total_kmers is None else np.ascontiguousarray(total_kmers, np.int32)
+        e = None if eff_len is None else np.ascontiguousarray(eff_len, np.int32)
+        ctx._check(self._lib.kcf_cohort_create(ctx._h, self.n_windows, self.n_samples, None if t is None else _ptr(t), None if e is None else _ptr(e),
+                                               C.byref(self._h)))
+
+    def add_plan(self, sample: int, plan: "Plan", window_offset: int = 0):
+        self.ctx._check(self._lib.kcf_cohort_add_plan(self.ctx._h, self._h, sample, window_offset, plan._h))
+
+    def set_sample(self, sample: int, cells: np.ndarray):
+        from ._lib import CELL_DTYPE
+        cells = np.ascontiguousarray(cells, CELL_DTYPE)
+        assert cells.size == self.n_windows
+        self.ctx._check(self._lib.kcf_cohort_set_sample(self.ctx._h, self._h, sample, _ptr(cells)))
+
+    def scores(self, weights=(0.3, 0.3, 0.4)):
+        self.ctx._check(self._lib.kcf_cohort_scores(self.ctx._h, self._h, (C.c_double * 3)(*weights)))
+
+    def find_ibs(self, order: np.ndarray, chrom: np.ndarray, detect_var: bool = False, min_consecutive: int = 4, score_cutoff: float = 95.0):
+        order = np.ascontiguousarray(order, np.uint32)
+        chrom = np.ascontiguousarray(chrom, np.uint32)
+        assert order.size == chrom.size
+        self.ctx._check(self._lib.kcf_cohort_find_ibs(self.ctx._h, self._h, _ptr(order), _ptr(chrom), order.size, int(detect_var), min_consecutive,
+                                                      C.c_float(score_cutoff)))
+
+    def genotypes(self, score_a=95.0, score_b=60.0, score_n=30.0, min_maf=0.0, max_missing=1.0):
+        al = np.zeros((self.n_windows, self.n_samples), np.int8)
+        bad = np.zeros(self.n_windows, np.uint8)
+        self.ctx._check(self._lib.kcf_cohort_genotypes(self.ctx._h, self._h, score_a, score_b, score_n, min_maf, max_missing, _ptr(al), _ptr(bad)))
+        return al, bad
+
+    def fetch(self, sample: int):
+        from ._lib import CELL_DTYPE
+        cells = np.zeros(self.n_windows, CELL_DTYPE)
+        tot = np.zeros(self.n_windows, np.int32)
+        eff = np.zeros(self.n_windows, np.int32)
+        self.ctx._check(self._lib.kcf_cohort_fetch(self.ctx._h, self._h, sample, _ptr(cells), _ptr(tot), _ptr(eff)))
+        return cells, tot, eff
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.kcf_cohort_destroy(self._h)
+            self._h = C.c_void_p()
+
+
 def fixed_windows(seq_lens, window: int, step: int, k: int):
     """window / segment arrays of the `-f window` mode (GetVariants.java:292-320) for sequences 0..n-1.
     Returns (wins, segs, starts, ends, seq_ids)."""

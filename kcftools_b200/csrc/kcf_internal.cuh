@@ -193,6 +193,9 @@ struct kcf_plan {
     uint32_t *x_okw = nullptr, *x_start = nullptr; // validity / stretch-start bitmaps, one word per 32 positions
     uint32_t *x_cnt = nullptr;             // counts returned by the owners, by position
     unsigned long long *x_cursor = nullptr; // per-owner counters (device)
+    // scratch of the scan path (partitioned databases, every rank walks every tile): bitmaps, one word per 32 positions
+    uint64_t s_cap = 0; // words
+    uint32_t *s_okw = nullptr, *s_start = nullptr;
 };
 
 #define KCF_TILE 2048          // positions per tile = the unit of work one warp takes
@@ -203,7 +206,7 @@ enum { FLAG_LUT_BAD = 0, FLAG_ORDER_BAD = 1, FLAG_SCORE_USED = 2, FLAG_COUNT = 8
 
 int kcf_fail(kcf_ctx *ctx, int code, const char *fmt, ...);
 int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t min_count, uint64_t tile_begin, uint64_t tile_end,
-                      int32_t *d_counts, bool extract);
+                      int32_t *d_counts, bool extract, uint32_t *d_owned_hit, unsigned long long *d_owned_sum);
 #define KCF_CUDA(ctx, call)                                                                        \
     do {                                                                                           \
         cudaError_t e__ = (call);                                                                  \

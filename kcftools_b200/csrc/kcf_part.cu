@@ -276,7 +276,7 @@ extern "C" int kcf_xchg_extract(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, uint64
     KCF_CUDA(ctx, cudaMemsetAsync(plan->x_okw, 0, npos / 32 * 4, ctx->stream));
     KCF_CUDA(ctx, cudaMemsetAsync(plan->x_start, 0, npos / 32 * 4, ctx->stream));
     KCF_CUDA(ctx, cudaMemsetAsync(plan->x_cursor, 0, 2 * KCF_MAX_WORLD * sizeof(unsigned long long), ctx->stream));
-    rc = kcf_launch_screen(ctx, db, plan, 1, tile_begin, tile_end, nullptr, true);
+    rc = kcf_launch_screen(ctx, db, plan, 1, tile_begin, tile_end, nullptr, true, nullptr, nullptr);
     if (rc != KCF_OK) return rc;
     const unsigned grid = (unsigned)std::min<uint64_t>((npos + 255) / 256, (uint64_t)ctx->sm_count * 8);
     kcf_part_count_kernel<<<grid, 256, 0, ctx->stream>>>(plan->x_homes, npos, db->geom.n_lines, (uint32_t)world, plan->x_cursor);
@@ -332,6 +332,99 @@ extern "C" int kcf_xchg_fold(kcf_ctx *ctx, kcf_plan *plan, uint64_t tile_begin, 
     const uint64_t nt = tile_end - tile_begin;
     kcf_part_fold_kernel<<<(unsigned)((nt * 32 + 127) / 128), 128, 0, ctx->stream>>>(plan->x_cnt, plan->x_okw, plan->x_start, nt, (uint32_t)plan->k,
                                                                                     min_count, plan->d_tile_sum + tile_begin);
+    KCF_CUDA(ctx, cudaGetLastError());
+    KCF_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // the caller may reuse its buffers
+    return KCF_OK;
+}
+
+// ---- scan placement: every rank walks every tile, probes what it owns, bitmaps are reduced over ranks ------------------
+// The second way to screen against a partitioned table (the first is the k-mer exchange above).  The 2-bit reference is
+// small next to the table (0.375 B per base), so it is replicated; a rank runs the whole screening front half over ALL
+// tiles but probes only the k-mers whose home line lies in its slice (ownership goes by minimizer, so the owned k-mers
+// still come in runs that share a line).  What crosses NVLink is one hit BIT per position and one Σcount per tile —
+// a sum-reduction (the owners' bitmaps are disjoint, so + is OR) — instead of 12-16 bytes per k-mer each way.
+
+// one warp per tile: 64 words of 32 positions, two per lane, reduced in order
+__global__ void __launch_bounds__(128) kcf_scan_fold_kernel(const uint32_t *__restrict__ hit, const uint32_t *__restrict__ okw,
+                                                            const uint32_t *__restrict__ start, const unsigned long long *__restrict__ sums,
+                                                            uint64_t n_tiles, uint32_t k, KcfGap *__restrict__ tile_sum)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= n_tiles) return;
+    constexpr int WORDS = KCF_TILE / 32; // 64
+    const uint64_t w0 = t * WORDS + lane, w1 = w0 + 32;
+    // a hit bit is only ever set where a k-mer ends; the mask keeps a corrupted reduction from inventing k-mers
+    KcfGap a = kcf_gap_bits_p(hit[w0] & okw[w0], okw[w0], start[w0], k);
+    KcfGap b = kcf_gap_bits_p(hit[w1] & okw[w1], okw[w1], start[w1], k);
+    for (int d = 1; d < 32; d <<= 1) {
+        KcfGap a2, b2;
+#define SHF(dst, srcv, f) dst.f = __shfl_down_sync(0xffffffffu, srcv.f, d)
+        SHF(a2, a, n); SHF(a2, a, obs); SHF(a2, a, lead); SHF(a2, a, trail); SHF(a2, a, vin); SHF(a2, a, inner); SHF(a2, a, has); SHF(a2, a, starts);
+        SHF(b2, b, n); SHF(b2, b, obs); SHF(b2, b, lead); SHF(b2, b, trail); SHF(b2, b, vin); SHF(b2, b, inner); SHF(b2, b, has); SHF(b2, b, starts);
+#undef SHF
+        a2.sum = b2.sum = 0;
+        if (lane + d < 32) {
+            a = kcf_gap_combine_p(a, a2, k);
+            b = kcf_gap_combine_p(b, b2, k);
+        }
+    }
+    if (lane == 0) {
+        KcfGap r = kcf_gap_combine_p(a, b, k);
+        r.sum = sums[t];
+        tile_sum[t] = r;
+    }
+}
+
+static int kcf_scan_reserve(kcf_ctx *ctx, kcf_plan *plan, uint64_t words)
+{
+    if (plan->s_cap >= words && plan->s_okw) return KCF_OK;
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(plan->s_okw);
+    cudaFree(plan->s_start);
+    plan->s_okw = plan->s_start = nullptr;
+    plan->s_cap = 0;
+    KCF_CUDA(ctx, cudaMalloc(&plan->s_okw, words * 4));
+    KCF_CUDA(ctx, cudaMalloc(&plan->s_start, words * 4));
+    plan->s_cap = words;
+    return KCF_OK;
+}
+
+extern "C" int kcf_scan_owned(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, uint64_t tile_begin, uint64_t tile_end, int32_t min_count,
+                              void *d_hit_out, void *d_sum_out)
+{
+    if (!ctx || !db || !plan || plan->ctx != ctx || db->ctx != ctx) return KCF_ERR_ARG;
+    if (min_count < 1) return kcf_fail(ctx, KCF_ERR_ARG, "Minimum kmer count should be at least 1"); // GetVariants.java:383-385
+    if (plan->k != db->info.kmer_length) return kcf_fail(ctx, KCF_ERR_ARG, "plan built for k=%d, database has k=%d", plan->k, db->info.kmer_length);
+    tile_end = std::min<uint64_t>(tile_end, plan->n_tiles);
+    if (tile_begin >= tile_end) return KCF_OK;
+    if (!d_hit_out || !d_sum_out) return KCF_ERR_ARG;
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t nt = tile_end - tile_begin, words = nt * (KCF_TILE / 32);
+    int rc = kcf_scan_reserve(ctx, plan, words);
+    if (rc != KCF_OK) return rc;
+    // chunks past the end of a window are never visited: their words must read "no k-mer, no hit"
+    KCF_CUDA(ctx, cudaMemsetAsync(d_hit_out, 0, words * 4, ctx->stream));
+    KCF_CUDA(ctx, cudaMemsetAsync(plan->s_okw, 0, words * 4, ctx->stream));
+    KCF_CUDA(ctx, cudaMemsetAsync(plan->s_start, 0, words * 4, ctx->stream));
+    rc = kcf_launch_screen(ctx, db, plan, min_count, tile_begin, tile_end, nullptr, false, (uint32_t *)d_hit_out, (unsigned long long *)d_sum_out);
+    if (rc != KCF_OK) return rc;
+    KCF_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // the caller hands the buffers to its communication library
+    return KCF_OK;
+}
+
+extern "C" int kcf_scan_fold(kcf_ctx *ctx, kcf_plan *plan, uint64_t tile_begin, uint64_t tile_end, const void *d_hit, const void *d_sum)
+{
+    if (!ctx || !plan || plan->ctx != ctx) return KCF_ERR_ARG;
+    tile_end = std::min<uint64_t>(tile_end, plan->n_tiles);
+    if (tile_begin >= tile_end) return KCF_OK;
+    if (!d_hit || !d_sum) return KCF_ERR_ARG;
+    const uint64_t nt = tile_end - tile_begin;
+    if (!plan->s_okw || plan->s_cap < nt * (KCF_TILE / 32)) return kcf_fail(ctx, KCF_ERR_ARG, "kcf_scan_fold without the matching kcf_scan_owned");
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    kcf_scan_fold_kernel<<<(unsigned)((nt * 32 + 127) / 128), 128, 0, ctx->stream>>>((const uint32_t *)d_hit, plan->s_okw, plan->s_start,
+                                                                                    (const unsigned long long *)d_sum, nt, (uint32_t)plan->k,
+                                                                                    plan->d_tile_sum + tile_begin);
     KCF_CUDA(ctx, cudaGetLastError());
     KCF_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // the caller may reuse its buffers
     return KCF_OK;

@@ -36,7 +36,14 @@ struct KcfScreenParams {
     // line (0xFFFFFFFF where no k-mer ends) and the validity / stretch-start bitmaps, indexed from tile_begin
     unsigned long long *x_keys;
     uint32_t *x_homes, *x_okw, *x_start;
+    // OWNED mode (partitioned databases, scan placement): every rank walks every tile but probes only the k-mers whose
+    // home line it holds; the hit bitmap (one word per 32 positions) and the tile's Σcount go out for the reduction over
+    // ranks, next to the validity / stretch-start bitmaps (identical on every rank)
+    uint32_t *x_hit;
+    unsigned long long *x_sum;
 };
+
+enum { KCF_MODE_SCREEN = 0, KCF_MODE_COUNTS = 1, KCF_MODE_EXTRACT = 2, KCF_MODE_OWNED = 3 };
 
 // GetVariants.java:267-273 getDistance
 __device__ __forceinline__ uint32_t kcf_gap_distance(uint32_t gap, uint32_t k)
@@ -195,10 +202,12 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
         /* minimizer = min over the w m-mers ending at q-w+1 .. q -> home line */                                      \
         const uint32_t h0 = q - g.w + 1;                                                                               \
         const uint32_t home = kcf_home_line(min(W.hash[h0], W.hash[h0 + g.w - P2]), g);                                \
-        const uint8_t *L = p.table + (uint64_t)home * KCF_LINE_BYTES;                                                  \
+        const uint32_t lhome = OWNED ? home - (uint32_t)g.line_lo : home; /* local line index */                       \
+        const bool mine = !OWNED || lhome < (uint32_t)g.n_local;          /* this rank holds the k-mer's home line */  \
+        const uint8_t *L = p.table + (uint64_t)lhome * KCF_LINE_BYTES;                                                 \
         uint32_t cnt = 0, mask = 0;                                                                                    \
         bool pending = false;                                                                                          \
-        if (ok) {                                                                                                      \
+        if (ok && mine) {                                                                                              \
             const bool inl = KCF_KEY_IN_LINES(key);                                                                    \
             if (!(inl && kcf_probe_line<S>(L, key, cnt))) {                                                            \
                 cnt = 0;                                                                                               \
@@ -283,9 +292,10 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
         __syncwarp();                                                                                                  \
     } while (0)
 
-template <int S, bool COUNTS, bool EXTRACT>
+template <int S, int MODE>
 __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_screen_kernel(KcfScreenParams p, KcfTableGeom g)
 {
+    constexpr bool COUNTS = MODE == KCF_MODE_COUNTS, EXTRACT = MODE == KCF_MODE_EXTRACT, OWNED = MODE == KCF_MODE_OWNED;
     __shared__ __align__(16) KcfWarpSmem kcf_warp_smem[KCF_WPC];
     KcfWarpSmem &W = kcf_warp_smem[threadIdx.x >> 5]; // the warps of a CTA share nothing
 
@@ -321,6 +331,7 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
         acc.n = acc.obs = acc.lead = acc.trail = acc.vin = acc.inner = acc.has = acc.starts = 0;
         acc.sum = 0;
         uint32_t carry_hash = 0; // order hash of position KCF_CHUNK + lane of the previous chunk = position lane of this one
+        unsigned long long owned_sum = 0; // OWNED mode: Σcount of this rank's hits in the tile
 
         for (uint32_t chunk = 0; chunk < KCF_TILE / KCF_CHUNK; ++chunk) {
             const int64_t o = o_tile + (int64_t)chunk * KCF_CHUNK;
@@ -474,6 +485,21 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
             for (uint32_t j = 0; j < J; ++j) KCF_PROBE(j);
             if (qn) KCF_FLUSH_QUEUE();
             __syncwarp();
+            if (OWNED) {
+                // this rank's share of the chunk: bitmaps out, Σcount kept per tile; the gap summaries are folded after the
+                // reduction over ranks (kcf_scan_fold)
+                const uint64_t wbase = (tile - p.tile_begin) * (KCF_TILE / 32) + (uint64_t)chunk * (KCF_CHUNK / 32);
+                if (lane < KCF_CHUNK / 32) {
+                    p.x_hit[wbase + lane] = W.hit[lane];
+                    p.x_okw[wbase + lane] = W.okw[lane];
+                    p.x_start[wbase + lane] = W.start[lane];
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, d);
+                owned_sum += sum;
+                __syncwarp();
+                continue;
+            }
 
             // ---- fold: lane j summarises positions [32 j, 32 j + 32), one ordered shuffle reduction per chunk ----
             constexpr uint32_t NWORDS = KCF_CHUNK / 32;
@@ -488,7 +514,9 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
             acc = kcf_gap_combine(acc, a, k);
             __syncwarp(); // the bitmaps are rewritten by the next chunk
         }
-        if (!EXTRACT && lane == 0) p.tile_sum[tile] = acc;
+        if (OWNED) {
+            if (lane == 0) p.x_sum[tile - p.tile_begin] = owned_sum;
+        } else if (!EXTRACT && lane == 0) p.tile_sum[tile] = acc;
     }
 }
 
@@ -652,6 +680,8 @@ extern "C" void kcf_plan_destroy(kcf_plan *plan)
     cudaFree(plan->x_start);
     cudaFree(plan->x_cnt);
     cudaFree(plan->x_cursor);
+    cudaFree(plan->s_okw);
+    cudaFree(plan->s_start);
     delete plan;
 }
 
@@ -738,9 +768,10 @@ extern "C" int kcf_plan_create(kcf_ctx *ctx, int32_t kmer_length, const kcf_wind
 }
 
 int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t min_count, uint64_t tile_begin, uint64_t tile_end,
-                      int32_t *d_counts, bool extract)
+                      int32_t *d_counts, bool extract, uint32_t *d_owned_hit, unsigned long long *d_owned_sum)
 {
-    if (!extract && db->part_world > 1)
+    const bool owned = d_owned_hit != nullptr;
+    if (!extract && !owned && db->part_world > 1)
         return kcf_fail(ctx, KCF_ERR_ARG, "this database holds slice %d of %d: screen it through the exchange calls (kcf_xchg_*)", db->part_rank, db->part_world);
     int rc = kcf_sync_seqs(ctx);
     if (rc != KCF_OK) return rc;
@@ -768,12 +799,21 @@ int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t min_coun
     p.x_homes = plan->x_homes;
     p.x_okw = plan->x_okw;
     p.x_start = plan->x_start;
+    if (owned) {
+        p.x_okw = plan->s_okw;
+        p.x_start = plan->s_start;
+        p.x_hit = d_owned_hit;
+        p.x_sum = d_owned_sum;
+    }
     const size_t smem = 0; // the per-warp buffers are static shared memory
     void (*kern)(KcfScreenParams, KcfTableGeom);
     const int S = (int)db->geom.S;
-    if (extract) kern = S == 13 ? kcf_screen_kernel<13, false, true> : (S == 12 ? kcf_screen_kernel<12, false, true> : kcf_screen_kernel<10, false, true>);
-    else if (d_counts) kern = S == 13 ? kcf_screen_kernel<13, true, false> : (S == 12 ? kcf_screen_kernel<12, true, false> : kcf_screen_kernel<10, true, false>);
-    else kern = S == 13 ? kcf_screen_kernel<13, false, false> : (S == 12 ? kcf_screen_kernel<12, false, false> : kcf_screen_kernel<10, false, false>);
+#define KCF_PICK(MODE) (S == 13 ? kcf_screen_kernel<13, MODE> : (S == 12 ? kcf_screen_kernel<12, MODE> : kcf_screen_kernel<10, MODE>))
+    if (extract) kern = KCF_PICK(KCF_MODE_EXTRACT);
+    else if (owned) kern = KCF_PICK(KCF_MODE_OWNED);
+    else if (d_counts) kern = KCF_PICK(KCF_MODE_COUNTS);
+    else kern = KCF_PICK(KCF_MODE_SCREEN);
+#undef KCF_PICK
     int per_sm = 0;
     KCF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * KCF_WPC, smem));
     const uint64_t n = tile_end - tile_begin;
@@ -792,7 +832,7 @@ extern "C" int kcf_plan_run(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t mi
     KCF_CUDA(ctx, cudaSetDevice(ctx->device));
     KCF_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, FLAG_COUNT * sizeof(uint32_t), ctx->stream));
     if (ctx->profiling) cudaEventRecord(ctx->ev[0], ctx->stream);
-    int rc = kcf_launch_screen(ctx, db, plan, min_count, 0, plan->n_tiles, nullptr, false);
+    int rc = kcf_launch_screen(ctx, db, plan, min_count, 0, plan->n_tiles, nullptr, false, nullptr, nullptr);
     if (rc != KCF_OK) return rc;
     if (ctx->profiling) cudaEventRecord(ctx->ev[1], ctx->stream);
     if (plan->n_wins) {
@@ -876,7 +916,7 @@ extern "C" int kcf_window_counts(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, uint6
     const uint64_t npos = (t1 - t0) * KCF_TILE;
     int32_t *d = nullptr;
     KCF_CUDA(ctx, cudaMalloc(&d, std::max<uint64_t>(npos, 1) * 4));
-    int rc = kcf_launch_screen(ctx, db, plan, 1, t0, t1, d, false);
+    int rc = kcf_launch_screen(ctx, db, plan, 1, t0, t1, d, false, nullptr, nullptr);
     std::vector<int32_t> h(npos);
     if (rc == KCF_OK) {
         cudaMemcpyAsync(h.data(), d, npos * 4, cudaMemcpyDeviceToHost, ctx->stream);

@@ -1,6 +1,7 @@
 // kcf_host.cpp — see kcf_host.hpp.  Everything here is host-side control flow of `kcftools getVariations`; the
 // per-k-mer work is one call into libkcfgpu.so (include/kcf_b200.h).
 #include "kcf_host.hpp"
+#include "kcf_tools.hpp"
 
 #include <algorithm>
 #include <chrono>
@@ -190,6 +191,8 @@ struct LineReader {
     }
 };
 
+} // namespace
+
 bool read_file(const std::string &path, std::string &out)
 {
     std::ifstream f(path, std::ios::binary);
@@ -246,7 +249,15 @@ int java_parse_int(const std::string &s, const std::string &what)
         throw FatalError("java.lang.NumberFormatException: For input string: \"" + s + "\" (" + what + ")");
     return (int)v;
 }
-} // namespace
+
+std::vector<std::string> java_lines(const std::string &text)
+{
+    std::vector<std::string> out;
+    LineReader rd(text);
+    std::string line;
+    while (rd.next(line)) out.push_back(line);
+    return out;
+}
 
 // ================================================================================================ FastaIndex
 static const char *const FAI_CLASS = "FastaIndex";
@@ -715,7 +726,7 @@ double computeScore(const kcf_result_t &r, const double w[3])
            100.0;
 }
 
-static std::string today()
+std::string today()
 {
     std::time_t t = std::time(nullptr);
     std::tm tm{};
@@ -749,6 +760,15 @@ static const char *const KCF_FORMAT_LINES[] = {
 #ifndef KCF_FORMAT_VERSION
 #define KCF_FORMAT_VERSION "0.4.0" /* the reference's pom.xml version, filtered into version.properties at build time */
 #endif
+
+std::string kcfStaticHeaderLines() // ##INFO and ##FORMAT lines (Configs.java:14-37)
+{
+    std::string s;
+    for (const char *l : KCF_INFO_LINES) s += std::string("##INFO=") + l + "\n";
+    for (const char *l : KCF_FORMAT_LINES) s += std::string("##FORMAT=") + l + "\n";
+    return s;
+}
+const char *kcfFormatVersion() { return KCF_FORMAT_VERSION; }
 
 std::string kcfHeaderText(const GetVariantsOptions &o, const std::string &sample, const FastaIndex &index, int kmerSize,
                           int totalWindows, const std::string &date)
@@ -809,12 +829,40 @@ struct Device {
 };
 } // namespace
 
+// One database against every sequence: queue a plan per sequence.  Rows stay on the device until fetched.
+static void screenAllSequences(Device &dev, const std::vector<std::vector<Window>> &perSeq, int kmerSize, int minKmerCount, const double weights[3])
+{
+    for (kcf_plan *p : dev.plans) kcf_plan_destroy(p);
+    dev.plans.clear();
+    for (size_t s = 0; s < perSeq.size(); ++s) {
+        std::vector<kcf_window_t> wins;
+        std::vector<kcf_segment_t> segs;
+        for (const Window &w : perSeq[s]) {
+            wins.push_back(kcf_window_t{(uint32_t)segs.size(), (uint32_t)w.segments.size()});
+            segs.insert(segs.end(), w.segments.begin(), w.segments.end());
+        }
+        kcf_plan *plan = nullptr;
+        if (kcf_plan_create(dev.ctx, kmerSize, wins.data(), wins.size(), segs.data(), segs.size(), &plan) != KCF_OK) dev.fail(FAI_CLASS);
+        dev.plans.push_back(plan);
+        if (kcf_plan_run(dev.ctx, dev.db, plan, minKmerCount, weights) != KCF_OK) dev.fail(GV_CLASS);
+    }
+}
+
 int getVariations(GetVariantsOptions o)
 {
-    const std::string sample = cleanSampleName(o.sampleName);
+    // Extension: `-k a,b,c -s x,y,z` screens several databases against the same reference and writes
+    // the COHORT file directly — the text `kcftools cohort` would write from the per-sample files, without those files.
+    const std::vector<std::string> prefixes = java_split(o.kmcDBprefix, ',');
+    std::vector<std::string> sampleNames = java_split(o.sampleName, ',');
+    const bool multi = prefixes.size() > 1;
+    if (multi && sampleNames.size() != prefixes.size())
+        Logger::error(GV_CLASS, "Number of sample names (" + std::to_string(sampleNames.size()) + ") differs from the number of KMC databases (" +
+                                    std::to_string(prefixes.size()) + ")");
+    if (!multi) sampleNames = {o.sampleName};
+    for (std::string &s : sampleNames) s = cleanSampleName(s);
     Device dev;
     if (kcf_init(o.device, &dev.ctx) != KCF_OK) Logger::error("KMC", std::string(kcf_last_error(nullptr)));
-    if (kcf_db_open(dev.ctx, o.kmcDBprefix.c_str(), 0, &dev.db) != KCF_OK) dev.fail("KMC");
+    if (kcf_db_open(dev.ctx, prefixes[0].c_str(), 0, &dev.db) != KCF_OK) dev.fail("KMC");
     kcf_db_info_t info;
     kcf_db_info(dev.db, &info);
     const int kmerSize = info.kmer_length;
@@ -843,35 +891,84 @@ int getVariations(GetVariantsOptions o)
         if (kcf_ref_add_async(dev.ctx, bytes, n, (uint32_t)e.lineBases, (uint32_t)e.lineWidth, (uint64_t)e.length, &sid) != KCF_OK) dev.fail(FAI_CLASS);
     }
     const double weights[3] = {o.innerDistanceWeight, o.tailDistanceWeight, o.kmerRatioWeight}; // getWeights(), :388-390
-    std::vector<std::vector<kcf_result_t>> results(perSeq.size());
+    // per sequence: the order the reference writes (stable sort by start, GetVariants.java:169-171)
+    std::vector<std::vector<size_t>> sorted(perSeq.size());
     for (size_t s = 0; s < perSeq.size(); ++s) {
-        std::vector<kcf_window_t> wins;
-        std::vector<kcf_segment_t> segs;
-        for (const Window &w : perSeq[s]) {
-            wins.push_back(kcf_window_t{(uint32_t)segs.size(), (uint32_t)w.segments.size()});
-            segs.insert(segs.end(), w.segments.begin(), w.segments.end());
-        }
-        kcf_plan *plan = nullptr;
-        if (kcf_plan_create(dev.ctx, kmerSize, wins.data(), wins.size(), segs.data(), segs.size(), &plan) != KCF_OK) dev.fail(FAI_CLASS);
-        dev.plans.push_back(plan);
-        if (kcf_plan_run(dev.ctx, dev.db, plan, o.minKmerCount, weights) != KCF_OK) dev.fail(GV_CLASS);
+        sorted[s].resize(perSeq[s].size());
+        for (size_t i = 0; i < sorted[s].size(); ++i) sorted[s][i] = i;
+        std::stable_sort(sorted[s].begin(), sorted[s].end(), [&](size_t a, size_t b) { return perSeq[s][a].start < perSeq[s][b].start; });
     }
-    for (size_t s = 0; s < perSeq.size(); ++s) {
-        results[s].resize(perSeq[s].size());
-        const int rc = kcf_plan_fetch(dev.ctx, dev.plans[s], results[s].data());
-        if (rc == KCF_ERR_WEIGHTS) Logger::error("Data", "Weights should sum to 1.0");
-        if (rc != KCF_OK) dev.fail(GV_CLASS);
-    }
-
-    // sort each contig's windows by start (stable, GetVariants.java:169-171) and write
     std::ofstream out(o.outFile, std::ios::binary);
     if (!out) throw FatalError("java.io.FileNotFoundException: " + o.outFile + " (No such file or directory)");
-    out << kcfHeaderText(o, sample, index, kmerSize, (int)totalWindows, today());
-    for (size_t s = 0; s < perSeq.size(); ++s) {
-        std::vector<size_t> order(perSeq[s].size());
-        for (size_t i = 0; i < order.size(); ++i) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return perSeq[s][a].start < perSeq[s][b].start; });
-        for (size_t i : order) out << kcfRowText(perSeq[s][i], results[s][i], weights) << "\n";
+
+    if (!multi) {
+        screenAllSequences(dev, perSeq, kmerSize, o.minKmerCount, weights);
+        std::vector<std::vector<kcf_result_t>> results(perSeq.size());
+        for (size_t s = 0; s < perSeq.size(); ++s) {
+            results[s].resize(perSeq[s].size());
+            const int rc = kcf_plan_fetch(dev.ctx, dev.plans[s], results[s].data());
+            if (rc == KCF_ERR_WEIGHTS) Logger::error("Data", "Weights should sum to 1.0");
+            if (rc != KCF_OK) dev.fail(GV_CLASS);
+        }
+        out << kcfHeaderText(o, sampleNames[0], index, kmerSize, (int)totalWindows, today());
+        for (size_t s = 0; s < perSeq.size(); ++s)
+            for (size_t i : sorted[s]) out << kcfRowText(perSeq[s][i], results[s][i], weights) << "\n";
+    } else {
+        // every database in turn against the resident reference; its rows go device-to-device into the cohort matrix
+        std::vector<size_t> offset(perSeq.size() + 1, 0);
+        for (size_t s = 0; s < perSeq.size(); ++s) offset[s + 1] = offset[s] + perSeq[s].size();
+        kcf_cohort *co = nullptr;
+        if (kcf_cohort_create(dev.ctx, totalWindows, (uint32_t)prefixes.size(), nullptr, nullptr, &co) != KCF_OK) dev.fail("Cohort");
+        struct CoGuard {
+            kcf_cohort *c;
+            ~CoGuard() { kcf_cohort_destroy(c); }
+        } guard{co};
+        for (size_t d = 0; d < prefixes.size(); ++d) {
+            if (d > 0) {
+                for (kcf_plan *p : dev.plans) kcf_plan_destroy(p);
+                dev.plans.clear();
+                kcf_db_close(dev.db);
+                dev.db = nullptr;
+                if (kcf_db_open(dev.ctx, prefixes[d].c_str(), 0, &dev.db) != KCF_OK) dev.fail("KMC");
+                kcf_db_info_t inf;
+                kcf_db_info(dev.db, &inf);
+                if (inf.kmer_length != kmerSize) Logger::error("KCFHeader", "Kmer size mismatch between the KCFs");
+            }
+            screenAllSequences(dev, perSeq, kmerSize, o.minKmerCount, weights);
+            for (size_t s = 0; s < perSeq.size(); ++s)
+                if (kcf_cohort_add_plan(dev.ctx, co, (uint32_t)d, offset[s], dev.plans[s]) != KCF_OK) dev.fail("Cohort");
+        }
+        // what `cohort` does when it re-reads the per-sample files: the weights come back from their Double.toString text
+        // (the same doubles), every score is recomputed from the integers, and KD has been through "%.2f"
+        // (Window.java:70: kmerCount = Math.round(KD * OB))
+        const int rc = kcf_cohort_scores(dev.ctx, co, weights);
+        if (rc == KCF_ERR_WEIGHTS) Logger::error("Data", "Weights should sum to 1.0");
+        if (rc != KCF_OK) dev.fail("Cohort");
+        std::vector<std::vector<kcf_cell_t>> cols(prefixes.size(), std::vector<kcf_cell_t>(std::max<size_t>(totalWindows, 1)));
+        std::vector<int32_t> total(std::max<size_t>(totalWindows, 1)), eff(std::max<size_t>(totalWindows, 1));
+        for (size_t d = 0; d < prefixes.size(); ++d)
+            if (kcf_cohort_fetch(dev.ctx, co, (uint32_t)d, cols[d].data(), total.data(), eff.data()) != KCF_OK) dev.fail("Cohort");
+        std::string sampleCols = sampleNames[0];
+        for (size_t d = 1; d < sampleNames.size(); ++d) sampleCols += "\t" + sampleNames[d];
+        out << kcfHeaderText(o, sampleCols, index, kmerSize, (int)totalWindows, today());
+        for (size_t s = 0; s < perSeq.size(); ++s)
+            for (size_t i : sorted[s]) {
+                const Window &w = perSeq[s][i];
+                KcfRow row;
+                row.seq = w.sequenceName;
+                row.wid = w.windowId;
+                row.start = w.start;
+                row.end = w.end;
+                row.total = total[offset[s] + i];
+                row.eff = eff[offset[s] + i];
+                for (size_t d = 0; d < prefixes.size(); ++d) {
+                    kcf_cell_t c = cols[d][offset[s] + i];
+                    const double kd = c.obs > 0 ? (double)c.kmer_count / c.obs : 0.0;                       // Data.java:87, as written by getVariations
+                    c.kmer_count = java_round(std::strtod(java_format_2f(kd).c_str(), nullptr) * (double)c.obs); // as re-read by cohort
+                    row.cells.push_back(c);
+                }
+                out << kcfRowTextMulti(row) << "\n";
+            }
     }
     out.flush();
     if (!out) throw FatalError("Error writing KCF file window");
@@ -1036,6 +1133,15 @@ int cliMain(int argc, const char *const *argv)
             printCommandLine(ps.o);
             validateCMD(ps.o);
             return getVariations(ps.o);
+        }
+        if (cmd == "cohort") return cohortMain(argc, argv, cmdline);
+        if (cmd == "findIBS") return findIBSMain(argc, argv, cmdline);
+        if (cmd == "kcf2gt") return kcf2gtMain(argc, argv, cmdline);
+        if (cmd == "_kcfheader") { // test hook: parse a KCF file's header (and rows) on the host, print the header back
+            if (argc < 3) throw UsageError("_kcfheader <file.kcf>");
+            const KcfFile f = readKcf(argv[2]);
+            std::fputs(f.header.text(today()).c_str(), stdout);
+            return 0;
         }
         if (cmd == "_faidx") { // test hook: build / load <fasta>.faidx and print it
             if (argc < 3) throw UsageError("_faidx <fasta>");

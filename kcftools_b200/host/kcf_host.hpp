@@ -36,6 +36,14 @@ std::string java_double_to_string(double v); // Double.toString
 std::string java_float_to_string(float v);   // Float.toString
 std::string java_format_2f(double v);        // String.format("%.2f", v): HALF_UP on the shortest decimal digits
 int32_t java_string_hash(const std::string &s); // String.hashCode (ASCII / Latin-1 input)
+bool read_file(const std::string &path, std::string &out);
+std::vector<std::string> java_split(const std::string &s, char sep);  // String.split(one literal char)
+std::vector<std::string> java_lines(const std::string &text);         // BufferedReader.readLine over a whole file
+std::string java_trim(const std::string &s);
+int java_parse_int(const std::string &s, const std::string &what);    // Integer.parseInt; FatalError when malformed
+std::string today();                                                  // HelperFunctions.getTodayDate
+std::string kcfStaticHeaderLines();                                   // the ##INFO / ##FORMAT block (Configs.java:14-37)
+const char *kcfFormatVersion();
 
 // ---- FastaIndex -------------------------------------------------------------------------------------
 struct FastaIndexEntry {
@@ -135,6 +143,9 @@ std::string kcfHeaderText(const GetVariantsOptions &o, const std::string &sample
                           int totalWindows, const std::string &date);          // KCFHeader.java:291-330
 std::string kcfRowText(const Window &w, const kcf_result_t &r, const double weights[3]); // Window.java:125-138, Data.java:120-132
 double computeScore(const kcf_result_t &r, const double weights[3]);          // Data.java:95-107
+int cohortMain(int argc, const char *const *argv, const std::string &cmdline);   // Plugins/Cohort.java
+int findIBSMain(int argc, const char *const *argv, const std::string &cmdline);  // Plugins/FindIBS.java
+int kcf2gtMain(int argc, const char *const *argv, const std::string &cmdline);   // Plugins/KCFToGenotypeTable.java
 int getVariations(GetVariantsOptions o);                                       // GetVariants.java:92-183; 0 or throws
 int cliMain(int argc, const char *const *argv);                                // KCFTOOLS.main + picocli parsing
 

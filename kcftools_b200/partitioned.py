@@ -5,6 +5,11 @@ own k-mers, so the path gets its one real exchange step: per batch of tiles the 
 (kcf_xchg_extract), moved with an all-to-all, looked up by their owners (kcf_xchg_lookup), and the counts travel back
 with a second all-to-all before the per-window statistics are folded (kcf_xchg_fold, kcf_plan_finalize).
 
+Second strategy, `screen_partitioned_scan*` ("scan placement"): no k-mer leaves its GPU.  Every rank holds ALL windows,
+walks all of them, probes only the k-mers whose home line it owns (kcf_scan_owned) and the per-position hit bits and
+per-tile count sums are sum-reduced over the ranks (one bit per k-mer instead of 12-16 bytes each way), then folded
+(kcf_scan_fold, kcf_plan_finalize).  Every rank ends up with every row.
+
 `Exchange` is the communication seam: `DistExchange` = torch.distributed (NCCL over NVLink / NVSwitch on the GPU box,
 one process per GPU); `screen_partitioned_local` drives several contexts of ONE process in lockstep and moves the
 buffers by slicing — the single-GPU test of exactly the same library calls.
@@ -118,4 +123,51 @@ def screen_partitioned_local(ranks, min_count: int = 1, weights=(0.3, 0.3, 0.4),
                 parts.append(looked[o][before:before + ext[s][3][o]].to(devs[s]))
             back = torch.cat(parts) if parts else torch.empty(0, dtype=torch.int32, device=devs[s])
             _fold(ctx, plan, t0, t1, back, ext[s][2], min_count)
+    return [_finish(ctx, plan, weights) for (ctx, db, plan) in ranks]
+
+
+# ---- scan placement ---------------------------------------------------------------------------------------------------
+def _scan_owned(ctx, db, plan, t0, t1, min_count, torch, dev):
+    nt = max(0, min(t1, plan.n_tiles) - t0)
+    hit = torch.empty(max(nt * 64, 1), dtype=torch.int32, device=dev)  # one word per 32 positions
+    sums = torch.empty(max(nt, 1), dtype=torch.int64, device=dev)
+    ctx._check(ctx._lib.kcf_scan_owned(ctx._h, db._h, plan._h, t0, t1, min_count, hit.data_ptr(), sums.data_ptr()))
+    return hit[:nt * 64], sums[:nt]
+
+
+def _scan_fold(ctx, plan, t0, t1, hit, sums):
+    ctx._check(ctx._lib.kcf_scan_fold(ctx._h, plan._h, t0, t1, hit.data_ptr(), sums.data_ptr()))
+
+
+def screen_partitioned_scan(ctx, db, plan, group=None, min_count: int = 1, weights=(0.3, 0.3, 0.4), batch_tiles: int = 1 << 20) -> np.ndarray:
+    """one rank of a torch.distributed job: `db` was opened with placement=1 after ctx.set_partition(rank, world), `plan`
+    holds ALL windows (the same plan on every rank).  Returns all rows (identical on every rank)."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", ctx.device)
+    for t0 in range(0, plan.n_tiles, batch_tiles):
+        t1 = t0 + batch_tiles
+        hit, sums = _scan_owned(ctx, db, plan, t0, t1, min_count, torch, dev)
+        # the owners' bitmaps are disjoint, so the sum is the union (no carries; NCCL has no bitwise reduction)
+        dist.all_reduce(hit, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        torch.cuda.current_stream(dev).synchronize()  # NCCL ran on torch's stream, the library has its own
+        _scan_fold(ctx, plan, t0, t1, hit, sums)
+    return _finish(ctx, plan, weights)
+
+
+def screen_partitioned_scan_local(ranks, min_count: int = 1, weights=(0.3, 0.3, 0.4), batch_tiles: int = 1 << 20) -> list[np.ndarray]:
+    """`ranks` = [(ctx, db, plan), ...]: every slice of one database, every plan holding ALL windows, all on GPUs this
+    process can see.  Lockstep version of screen_partitioned_scan: the all-reduce is a sum of the ranks' tensors."""
+    import torch
+    devs = [torch.device("cuda", r[0].device) for r in ranks]
+    n_tiles = ranks[0][2].n_tiles
+    assert all(r[2].n_tiles == n_tiles for r in ranks), "scan placement: every rank plans the same windows"
+    for t0 in range(0, n_tiles, batch_tiles):
+        t1 = t0 + batch_tiles
+        parts = [_scan_owned(ctx, db, plan, t0, t1, min_count, torch, devs[i]) for i, (ctx, db, plan) in enumerate(ranks)]
+        for i, (ctx, db, plan) in enumerate(ranks):
+            hit = torch.stack([p[0].to(devs[i]) for p in parts]).sum(0, dtype=torch.int32)
+            sums = torch.stack([p[1].to(devs[i]) for p in parts]).sum(0)
+            _scan_fold(ctx, plan, t0, t1, hit, sums)
     return [_finish(ctx, plan, weights) for (ctx, db, plan) in ranks]

@@ -35,6 +35,16 @@ def partition(lengths: np.ndarray, world: int) -> list[tuple[int, int]]:
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+def grid_layout(rank: int, world: int, table_parts: int) -> tuple[int, int, list[int]]:
+    """scan placement on world = table_parts x window_shards ranks: rank r keeps table slice r % table_parts and screens
+    window shard r // table_parts; the ranks that share a window shard (consecutive ranks, so neighbours on the NVSwitch)
+    reduce their bitmaps among themselves.  Returns (slice, shard, ranks of this rank's reduction group)."""
+    if table_parts < 1 or world % table_parts:
+        raise ValueError(f"table_parts {table_parts} must divide the world size {world}")
+    shard_id = rank // table_parts
+    return rank % table_parts, shard_id, list(range(shard_id * table_parts, (shard_id + 1) * table_parts))
+
+
 def local_slice(wins: np.ndarray, segs: np.ndarray, begin: int, end: int) -> tuple[np.ndarray, np.ndarray]:
     """window / segment arrays of one rank's range, segment indices re-based"""
     w = np.ascontiguousarray(wins[begin:end]).astype(WINDOW_DTYPE, copy=True)

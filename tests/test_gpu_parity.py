@@ -304,3 +304,36 @@ def test_partitioned_database_exchange_path(sc_main, world, batch_tiles):
         db.close()
     for c in ctxs:
         c.close()
+
+
+@pytest.mark.parametrize("world,batch_tiles,kind", [(1, 1 << 20, "fixed"), (2, 1 << 20, "fixed"), (3, 5, "fixed"), (4, 1 << 20, "multi")])
+def test_partitioned_database_scan_path(sc_main, world, batch_tiles, kind):
+    """placement 1, scan strategy: every rank holds 1/world of the table and ALL windows, probes only the k-mers whose
+    home line it owns, and the hit bitmaps / count sums are summed over the ranks before the fold (here all ranks live
+    on cuda:0 and the all-reduce is a tensor sum — the library calls are the ones the NCCL job makes)."""
+    from kcftools_b200.api import Context
+    from kcftools_b200.partitioned import screen_partitioned_scan_local
+    sc = sc_main
+    if kind == "fixed":
+        wins, segs, *_ = fixed_windows(sc.seq_lens, 20_000, 0, 31)
+    else:  # multi-segment windows whose k-mers span junctions, one shorter than k, one crossing several tiles
+        wins, segs = windows_from_lists([[(0, 100, 500), (0, 5_000, 40), (1, 10, 3_000)], [(1, 0, 20)], [(0, 0, 30_000), (1, 2_000, 9_000)],
+                                         [(1, 100, 31)], [(0, 50_000, 2_048), (0, 60_000, 2_048)]])
+    rc, want = _oracle_screen(sc, wins, segs, min_count=2, w=(0.2, 0.3, 0.5))
+    assert rc == 0
+    ranks, ctxs = [], []
+    for r in range(world):
+        c = Context(0)
+        ctxs.append(c)
+        sc.add_to(c)
+        c.set_partition(r, world)
+        db = KMC(c, pre=sc.kmc.pre, suf=sc.kmc.suf, placement=1)
+        ranks.append((c, db, c.plan(31, wins, segs)))
+    parts = screen_partitioned_scan_local(ranks, min_count=2, weights=(0.2, 0.3, 0.5), batch_tiles=batch_tiles)
+    for got in parts:  # every rank ends up with every row
+        assert_results_equal(got, want)
+    for (c, db, plan) in ranks:
+        plan.close()
+        db.close()
+    for c in ctxs:
+        c.close()
