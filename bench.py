@@ -209,6 +209,7 @@ def main():
         if args.impl == "ours":
             import torch.distributed as dist
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line and nothing else
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     have_gpu = torch.cuda.is_available()
     if args.impl == "ours" and not have_gpu:

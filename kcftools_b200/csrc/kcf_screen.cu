@@ -126,7 +126,7 @@ __device__ __forceinline__ KcfGap kcf_gap_shfl_down(const KcfGap &a, int delta)
 #define KCF_WPC 2 // independent warps per CTA (an SM holds 32 CTAs at most)
 #define S_CODE_WORDS ((KCF_CHUNK + KCF_HALO) / 16 + 4)
 #define S_VALID_WORDS ((KCF_CHUNK + KCF_HALO) / 32 + 2)
-#define S_HASH_WORDS (KCF_CHUNK + KCF_HALO + 8)
+#define S_HASH_WORDS (((KCF_CHUNK + KCF_HALO + 127) / 128) * 128 + 16) // padded: the 4-wide sliding-minimum rounds read 16 words per lane
 #ifndef KCF_QCAP
 #define KCF_QCAP 64
 #endif
@@ -137,7 +137,7 @@ struct KcfQueueItem {
     uint32_t info;  // chunk position << 16 | home mask (bit 0 cleared)
 };
 
-struct KcfWarpSmem {
+struct __align__(16) KcfWarpSmem {
     KcfQueueItem queue[KCF_QCAP];
     uint32_t hash[S_HASH_WORDS];
     uint32_t codes[S_CODE_WORDS];
@@ -193,15 +193,15 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
         uint64_t key; /* canonical k-mer (Kmer.java:57-79, 232-252, 300-338) */                                        \
         {                                                                                                              \
             const uint32_t wi = b0 >> 4, sh = (b0 & 15u) * 2u;                                                         \
-            const uint64_t lo = ((uint64_t)W.codes[wi + 1] << 32) | W.codes[wi];                                       \
-            const uint64_t X = (sh ? ((lo >> sh) | ((uint64_t)W.codes[wi + 2] << (64 - sh))) : lo) & g.kmask;          \
+            const uint32_t c0 = W.codes[wi], c1 = W.codes[wi + 1], c2 = W.codes[wi + 2];                               \
+            const uint64_t X = (((uint64_t)__funnelshift_r(c1, c2, sh) << 32) | __funnelshift_r(c0, c1, sh)) & g.kmask; \
             const uint64_t fw = kcf_pair_reverse(X, g.kshift); /* first base most significant */                       \
             const uint64_t rc = (~X) & g.kmask;                /* reverse complement value */                          \
             key = (g.both_strands && rc < fw) ? rc : fw;       /* unsigned-smaller word, tie keeps forward */          \
         }                                                                                                              \
         /* minimizer = min over the w m-mers ending at q-w+1 .. q -> home line */                                      \
         const uint32_t h0 = q - g.w + 1;                                                                               \
-        const uint32_t home = kcf_home_line(min(W.hash[h0], W.hash[h0 + g.w - P2]), g);                                \
+        const uint32_t home = kcf_home_line(FASTMIN ? W.hash[h0] : min(W.hash[h0], W.hash[h0 + g.w - P2]), g);          \
         const uint32_t lhome = OWNED ? home - (uint32_t)g.line_lo : home; /* local line index */                       \
         const bool mine = !OWNED || lhome < (uint32_t)g.n_local;          /* this rank holds the k-mer's home line */  \
         const uint8_t *L = p.table + (uint64_t)lhome * KCF_LINE_BYTES;                                                 \
@@ -225,7 +225,7 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
         if (hit) sum += cnt;                                                                                           \
         const uint32_t hb = __ballot_sync(0xffffffffu, hit);                                                           \
         const uint32_t pb = __ballot_sync(0xffffffffu, pending);                                                       \
-        if (lane == 0) atomicOr(&W.hit[JJ], hb);                                                                       \
+        if (lane == 0) W.hit[JJ] = hb; /* the queue flush ORs late hits into it, after this store */                    \
         if (COUNTS) p.counts_out[(tile - p.counts_tile0) * KCF_TILE + chunk * KCF_CHUNK + cpos] = ok ? (int32_t)cnt : -1; \
         if (pb) {                                                                                                      \
             if (pending) {                                                                                             \
@@ -250,14 +250,14 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
         uint64_t key;                                                                                                  \
         {                                                                                                              \
             const uint32_t wi = b0 >> 4, sh = (b0 & 15u) * 2u;                                                         \
-            const uint64_t lo = ((uint64_t)W.codes[wi + 1] << 32) | W.codes[wi];                                       \
-            const uint64_t X = (sh ? ((lo >> sh) | ((uint64_t)W.codes[wi + 2] << (64 - sh))) : lo) & g.kmask;          \
+            const uint32_t c0 = W.codes[wi], c1 = W.codes[wi + 1], c2 = W.codes[wi + 2];                               \
+            const uint64_t X = (((uint64_t)__funnelshift_r(c1, c2, sh) << 32) | __funnelshift_r(c0, c1, sh)) & g.kmask; \
             const uint64_t fw = kcf_pair_reverse(X, g.kshift);                                                         \
             const uint64_t rc = (~X) & g.kmask;                                                                        \
             key = (g.both_strands && rc < fw) ? rc : fw;                                                               \
         }                                                                                                              \
         const uint32_t h0 = q - g.w + 1;                                                                               \
-        const uint32_t home = kcf_home_line(min(W.hash[h0], W.hash[h0 + g.w - P2]), g);                                \
+        const uint32_t home = kcf_home_line(FASTMIN ? W.hash[h0] : min(W.hash[h0], W.hash[h0 + g.w - P2]), g);          \
         p.x_keys[base + cpos] = key;                                                                                   \
         p.x_homes[base + cpos] = ok ? home : 0xFFFFFFFFu;                                                              \
         if (lane == 0) {                                                                                               \
@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
     const uint32_t k = g.k;
     uint32_t P2 = 1; // largest power of two <= w: the sliding minimum is built by doubling up to it
     while (2 * P2 <= g.w) P2 *= 2;
+    const bool FASTMIN = g.w >= 4 && g.w <= 13; // register sliding minimum (warp uniform)
 
     for (;;) {
         // ---- take a tile: KCF_TILE consecutive positions of one window ----
@@ -430,9 +431,42 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
             }
             __syncwarp();
             carry_hash = W.hash[KCF_CHUNK + lane];
-            // sliding minimum by doubling, in place: a pass with stride s turns "min over [q, q + s)" into "min over
-            // [q, q + 4 s)" (or 2 s for the last pass when log2(P2) is odd); ascending q only reads not-yet-updated entries
-            {
+            // sliding minimum over w consecutive order hashes, in place: afterwards hash[q] = min over [q, q + w) (fast path) or
+            // min over [q, q + P2) (general path; the probe then combines two of them)
+            if (FASTMIN) {
+                // 4 <= w <= 13 (the automatic choice w = S - 1 always is): a lane produces 4 consecutive minima per round from
+                // the 13 hashes it holds in registers plus 3 more; the part common to the four windows is reduced once.
+                // A round rewrites [128 r, 128 r + 128) after every lane has read what it needs from it; later rounds only
+                // read higher positions.
+                const uint32_t wv = g.w;
+#pragma unroll 1
+                for (uint32_t r0 = 0; r0 < KCF_CHUNK + KCF_HALO; r0 += 128) {
+                    const uint32_t base = r0 + 4 * lane;
+                    const uint4 va = *reinterpret_cast<const uint4 *>(&W.hash[base]);
+                    const uint4 vb = *reinterpret_cast<const uint4 *>(&W.hash[base + 4]);
+                    const uint4 vc = *reinterpret_cast<const uint4 *>(&W.hash[base + 8]);
+                    const uint32_t v12 = W.hash[base + 12];
+                    const uint32_t t0 = W.hash[base + wv], t1 = W.hash[base + wv + 1], t2 = W.hash[base + wv + 2];
+                    uint32_t core = va.w; // positions 3 .. w-1 belong to all four windows
+                    if (wv > 4) core = min(core, vb.x);
+                    if (wv > 5) core = min(core, vb.y);
+                    if (wv > 6) core = min(core, vb.z);
+                    if (wv > 7) core = min(core, vb.w);
+                    if (wv > 8) core = min(core, vc.x);
+                    if (wv > 9) core = min(core, vc.y);
+                    if (wv > 10) core = min(core, vc.z);
+                    if (wv > 11) core = min(core, vc.w);
+                    if (wv > 12) core = min(core, v12);
+                    uint4 o;
+                    o.x = min(min(core, va.x), min(va.y, va.z));
+                    o.y = min(min(core, va.y), min(va.z, t0));
+                    o.z = min(min(core, va.z), min(t0, t1));
+                    o.w = min(min(core, t0), min(t1, t2));
+                    __syncwarp();
+                    *reinterpret_cast<uint4 *>(&W.hash[base]) = o;
+                    __syncwarp();
+                }
+            } else {
                 uint32_t sd = 1;
                 while (sd < P2) {
                     const bool four = 4 * sd <= P2;
