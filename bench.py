@@ -174,7 +174,27 @@ def cpu_leg(fasta, kmc, wins, segs, n_windows: int, threads: int):
     return int(res["total_kmers"].sum()), dt, res
 
 
+_STDOUT_FD = None
+
+
+def quiet_stdout():
+    """everything libraries print to fd 1 (NCCL's version banner, ...) goes to stderr: stdout carries the one JSON line"""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
@@ -251,7 +271,7 @@ def main():
                                            "(oracle/kcf_oracle.c, pthreads over windows like GetVariants.java:129-151); the Java reference cannot run (no JDK)"},
                 "e2e": {"value": v, "unit": "kmers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ our arm (GPU)
@@ -440,14 +460,15 @@ def main():
             walls = []
             for _ in range(2):  # first run also builds the .faidx; both runs read the files from the page cache
                 t1 = time.perf_counter()
-                subprocess.run([cli, "getVariations", "-r", fa, "-k", pref, "-o", outp, "-s", "bench", "-f", "window", "-w", str(window),
-                                "--device", str(local_rank)], check=True, stdout=subprocess.DEVNULL)
+                pr = subprocess.run([cli, "getVariations", "-r", fa, "-k", pref, "-o", outp, "-s", "bench", "-f", "window", "-w", str(window),
+                                     "--device", str(local_rank)], check=True, capture_output=True, text=True)
                 walls.append(time.perf_counter() - t1)
+                cli_log = [l[11:23] + l[33:] for l in pr.stdout.split("\n") if " - INFO " in l and "CMD" not in l and "--" not in l][-12:]
             rows = [l.split("\t") for l in open(outp) if not l.startswith("#")]
             ok = len(rows) == n_wins and all(int(r[4]) == int(res["total_kmers"][i]) and r[7].split(":")[2] == str(int(res["obs"][i]))
                                               for i, r in enumerate(rows))
             line["cli"] = {"wall_s_first_run": walls[0], "wall_s": walls[1], "kmers_per_s": total_kmers / walls[1],
-                           "rows_match_library": bool(ok), "input_bytes": int(fasta.data.size + kmc.pre.size + kmc.suf.size),
+                           "rows_match_library": bool(ok), "log": cli_log, "input_bytes": int(fasta.data.size + kmc.pre.size + kmc.suf.size),
                            "what": "kcftools_b200 getVariations on files in the page cache: mmap + KMC ingest (H2D, table build), .faidx, "
                                    "FASTA H2D + pack, screening, KCF text; process start to exit"}
         finally:
@@ -463,13 +484,13 @@ def main():
                                 "sample": f"first {nwin} windows ({kmers} k-mers) of the same workload, {dt:.1f} s; CPU restatement of the reference "
                                           "algorithm (oracle/kcf_oracle.c), pthreads over windows; Java reference not runnable (no JDK)",
                                 "gpu_matches_cpu_on_sample": bool(same)}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
     plan.close()
     db.close()
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
+    if rank == 0:
+        emit(line)  # last: nothing may follow the JSON line on stdout
     return 0
 
 

@@ -19,6 +19,26 @@
 #include <unistd.h>
 #include "kcf_internal.cuh"
 #include "kcf_lookup.cuh"
+#include <thread>
+
+// The records reach the device through two pinned staging buffers; filling them is a host memcpy out of the page cache
+// (or the caller's array), and one thread doing it (~11 GB/s) was slower than the ingest kernel it feeds.
+static void kcf_parallel_copy(uint8_t *dst, const uint8_t *src, size_t n)
+{
+    static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned nt = (unsigned)std::min<size_t>(std::min(hw, 6u), std::max<size_t>(n >> 22, 1)); // >= 4 MB per thread
+    if (nt <= 1) {
+        memcpy(dst, src, n);
+        return;
+    }
+    std::thread th[8];
+    const size_t per = ((n / nt) + 4095) & ~(size_t)4095;
+    for (unsigned t = 0; t < nt; ++t) {
+        const size_t a = std::min(n, (size_t)t * per), b = (t + 1 == nt) ? n : std::min(n, (size_t)(t + 1) * per);
+        th[t] = std::thread([=] { if (b > a) memcpy(dst + a, src + a, b - a); });
+    }
+    for (unsigned t = 0; t < nt; ++t) th[t].join();
+}
 
 
 // ---- Signature.java:23-95 on the device: one thread per m-mer -----------------------------------
@@ -98,10 +118,25 @@ __device__ __forceinline__ void kcf_filter_add(uint8_t *home_line, uint64_t key,
 __global__ void __launch_bounds__(256) kcf_ingest_kernel(KcfIngestParams p, KcfTableGeom g)
 {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // (bin, prefix) range holding record i: last idx with lut[idx] <= i.  The LUT is monotone, so the answers of a CTA's
+    // 256 consecutive records lie between those of its first and its last record: two threads search the whole LUT
+    // (23 dependent loads for 512 bins x 4^7 prefixes), the others the few entries in between.
+    __shared__ uint64_t s_bound[2];
+    if (threadIdx.x < 2) {
+        const uint64_t first = (uint64_t)blockIdx.x * blockDim.x;
+        const uint64_t ib = p.rec0 + (threadIdx.x == 0 ? first : min(first + blockDim.x - 1, p.n_rec - 1));
+        uint64_t lo = 0, hi = p.lut_len;
+        while (lo < hi) {
+            uint64_t mid = (lo + hi) >> 1;
+            if (p.lut[mid] <= ib) lo = mid + 1;
+            else hi = mid;
+        }
+        s_bound[threadIdx.x] = lo;
+    }
+    __syncthreads();
     if (t >= p.n_rec) return;
     const uint64_t i = p.rec0 + t;
-    // (bin, prefix) range holding record i: last idx with lut[idx] <= i
-    uint64_t lo = 0, hi = p.lut_len;
+    uint64_t lo = s_bound[0], hi = s_bound[1];
     while (lo < hi) {
         uint64_t mid = (lo + hi) >> 1;
         if (p.lut[mid] <= i) lo = mid + 1;
@@ -448,7 +483,7 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
         for (uint64_t r0 = 0; r0 < N; r0 += chunk_rec, j ^= 1) {
             uint64_t n = std::min<uint64_t>(chunk_rec, N - r0);
             DB_CUDA(cudaEventSynchronize(ev[j])); // staging buffer j free again
-            memcpy(h_stage[j], recs + r0 * rec_size, n * rec_size);
+            kcf_parallel_copy(h_stage[j], recs + r0 * rec_size, n * rec_size); // page cache / caller memory -> pinned staging
             DB_CUDA(cudaMemcpyAsync(d_stage[j], h_stage[j], n * rec_size, cudaMemcpyHostToDevice, ctx->stream));
             KcfIngestParams p{};
             p.rec = d_stage[j];
