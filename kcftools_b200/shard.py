@@ -82,3 +82,39 @@ def screen_sharded(screen_fn, wins: np.ndarray, segs: np.ndarray, group=None) ->
     dist.all_gather(bufs, padded, group=group)
     out = np.concatenate([bufs[r][:parts[r].numel()].cpu().numpy() for r in range(world)]).view(RESULT_DTYPE)
     return out
+
+
+# ---- C5: many databases against one reference, SAMPLES sharded over the GPUs -----------------------------------------
+def assign_samples(n_samples: int, world: int) -> list[list[int]]:
+    """contiguous blocks of samples per rank (64 databases on 8 GPUs: 8 each); every sample on exactly one rank"""
+    cuts = [n_samples * r // world for r in range(world + 1)]
+    return [list(range(cuts[r], cuts[r + 1])) for r in range(world)]
+
+
+def cohort_sharded(screen_sample_fn, n_samples: int, n_windows: int, group=None) -> np.ndarray:
+    """screen_sample_fn(sample) -> CELL_DTYPE array of n_windows cells (Cohort.fetch of the column this rank filled with
+    Cohort.add_plan after screening database `sample` against the resident reference).  Every rank screens its block of
+    samples; the columns are gathered so that every rank returns the whole [n_samples, n_windows] matrix, in sample
+    order — what Plugins/Cohort.java builds by re-reading one KCF per sample.  The only communication is this gather."""
+    import torch
+    import torch.distributed as dist
+    from ._lib import CELL_DTYPE
+    if not (dist.is_available() and dist.is_initialized()):
+        cols = [np.ascontiguousarray(screen_sample_fn(s), CELL_DTYPE) for s in range(n_samples)]
+        return np.stack(cols) if cols else np.zeros((0, n_windows), CELL_DTYPE)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    blocks = assign_samples(n_samples, world)
+    mine = [np.ascontiguousarray(screen_sample_fn(s), CELL_DTYPE) for s in blocks[rank]]
+    assert all(c.shape == (n_windows,) for c in mine)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    row = n_windows * CELL_DTYPE.itemsize
+    most = max(len(b) for b in blocks) * row
+    padded = torch.zeros(max(most, 1), dtype=torch.uint8, device=dev)
+    if mine:
+        src = torch.from_numpy(np.stack(mine).view(np.uint8).reshape(-1).copy()).to(dev)
+        padded[:src.numel()] = src
+    bufs = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(bufs, padded, group=group)
+    parts = [bufs[r][:len(blocks[r]) * row].cpu().numpy().view(CELL_DTYPE).reshape(len(blocks[r]), n_windows) for r in range(world)]
+    return np.concatenate(parts) if parts else np.zeros((0, n_windows), CELL_DTYPE)

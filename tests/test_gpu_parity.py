@@ -1,5 +1,7 @@
 """GPU parity tests: the CUDA path through the C ABI against the CPU oracle on the same seeded inputs.
 Bar: integer columns bit-exact, score within 1e-9 relative (north_star)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -337,3 +339,19 @@ def test_partitioned_database_scan_path(sc_main, world, batch_tiles, kind):
         db.close()
     for c in ctxs:
         c.close()
+
+
+def test_large_reference_windows_reproduce_the_small_run():
+    """size-independent property used at full C4 reference size by tools/scale_c4ref.py (profiles/r1f_scale_c4_reference.json:
+    1.5e10 positions, 300,069 windows): a reference whose sequences START with the chromosomes of a smaller run must give
+    the smaller run's rows for every window inside those cores, and exact totals / no hits in the unrelated random tails."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "scale_c4ref.py"), "--core", "c2s", "--seqs", "14", "--seq-len", "12000000"],
+                       capture_output=True, text=True, cwd=root)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    out = json.loads(p.stdout.strip().split("\n")[-1])
+    assert out["ok"] and out["core_windows_identical"] and out["core_windows_compared"] == 14 * 150 and out["tail_totals_exact"]
+    assert out["windows"] == 14 * 241 and out["tail_observed_kmers"] < 10

@@ -67,3 +67,59 @@ def test_two_rank_gloo_sharded_screen(tmp_path):
     a = np.load(tmp_path / "rank0.npy")
     b = np.load(tmp_path / "rank1.npy")
     assert (a == b).all() and a.size > 0
+
+
+def test_grid_layout_and_sample_blocks():
+    # scan placement on N = T x S ranks: slice r % T, window shard r // T, reduction group = the T ranks of the shard
+    assert shard.grid_layout(5, 8, 2) == (1, 2, [4, 5])
+    assert shard.grid_layout(3, 4, 4) == (3, 0, [0, 1, 2, 3])
+    assert shard.grid_layout(0, 1, 1) == (0, 0, [0])
+    seen = set()
+    for r in range(8):
+        sl, sh, grp = shard.grid_layout(r, 8, 4)
+        assert r in grp and len(grp) == 4 and (sl, sh) not in seen
+        seen.add((sl, sh))
+    with pytest.raises(ValueError):
+        shard.grid_layout(0, 8, 3)
+    for n, world in [(64, 8), (5, 2), (3, 4), (0, 2)]:
+        blocks = shard.assign_samples(n, world)
+        assert len(blocks) == world and [s for b in blocks for s in b] == list(range(n))
+        assert max(len(b) for b in blocks) - min(len(b) for b in blocks) <= 1
+
+
+def _cohort_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from kcftools_b200._lib import CELL_DTYPE
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_samples, n_windows = 5, 37
+    calls = []
+
+    def column(s):  # stands for: open database s, plan.run, cohort.add_plan, cohort.fetch
+        calls.append(s)
+        c = np.zeros(n_windows, CELL_DTYPE)
+        c["obs"] = np.arange(n_windows) * 10 + s
+        c["ibs"] = -1
+        c["kmer_count"] = (np.arange(n_windows, dtype=np.int64) + 1) * (s + 1) * 1_000_003
+        c["score"] = s + np.arange(n_windows) / 64.0
+        return c
+    got = shard.cohort_sharded(column, n_samples, n_windows)
+    assert calls == shard.assign_samples(n_samples, world)[rank]  # only this rank's databases were screened here
+    assert got.shape == (n_samples, n_windows)
+    for s in range(n_samples):
+        want = column(s)
+        assert (got[s] == want).all()
+    np.save(os.path.join(out_dir, f"cohort{rank}.npy"), got.view(np.uint8))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_samples_sharded_cohort(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_cohort_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a = np.load(tmp_path / "cohort0.npy")
+    b = np.load(tmp_path / "cohort1.npy")
+    assert (a == b).all() and a.size == 5 * 37 * 40
