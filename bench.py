@@ -303,7 +303,7 @@ def main():
     db = KMC(ctx, pre=kmc.pre, suf=kmc.suf, placement=1 if partitioned else 0)
     db_load_s = time.time() - t0
     log(f"[bench r{rank}] db resident: {db.info.resident_kmers} records in {db.info.n_buckets} buckets "
-        f"({db.info.table_bytes / 1e9:.2f} GB, stash {db.info.stash_kmers}) in {db_load_s:.1f}s")
+        f"({db.info.table_bytes / 1e9:.2f} GB, stash {db.info.stash_kmers}) in {db_load_s:.3f}s")
     # reference sequences: pinned host copies (the e2e leg re-uploads them every step)
     pinned = []
     for i in range(len(fasta.names)):

@@ -83,6 +83,22 @@ __global__ void kcf_lut_check_kernel(const uint64_t *__restrict__ lut, uint64_t 
     if (bad) atomicOr(&flags[FLAG_LUT_BAD], 1u);
 }
 
+// bound[c] = first LUT index whose value exceeds record rec0 + 256 c (c = 0 .. n_cta; the last one bounds the chunk's last record)
+__global__ void kcf_lut_bounds_kernel(const uint64_t *__restrict__ lut, uint64_t lut_len, uint64_t rec0, uint64_t n_rec, uint32_t n_cta,
+                                      uint64_t *__restrict__ bound)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_cta) return;
+    const uint64_t ib = rec0 + min((uint64_t)c * 256, n_rec - 1);
+    uint64_t lo = 0, hi = lut_len;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (lut[mid] <= ib) lo = mid + 1;
+        else hi = mid;
+    }
+    bound[c] = lo;
+}
+
 struct KcfIngestParams {
     const uint8_t *rec;      // staged records of this chunk
     uint64_t rec0;           // global index of the first staged record
@@ -90,6 +106,7 @@ struct KcfIngestParams {
     uint8_t prev[16];        // record rec0-1 (valid when rec0 > 0)
     const uint64_t *lut;
     uint64_t lut_len;
+    const uint64_t *cta_bound; // per CTA of this chunk (+1): first LUT index whose value exceeds the CTA's first record
     const uint32_t *sigmap;
     const uint32_t *norm;
     uint32_t P, L, nsb, cs, rec_size;
@@ -119,24 +136,12 @@ __global__ void __launch_bounds__(256) kcf_ingest_kernel(KcfIngestParams p, KcfT
 {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     // (bin, prefix) range holding record i: last idx with lut[idx] <= i.  The LUT is monotone, so the answers of a CTA's
-    // 256 consecutive records lie between those of its first and its last record: two threads search the whole LUT
-    // (23 dependent loads for 512 bins x 4^7 prefixes), the others the few entries in between.
-    __shared__ uint64_t s_bound[2];
-    if (threadIdx.x < 2) {
-        const uint64_t first = (uint64_t)blockIdx.x * blockDim.x;
-        const uint64_t ib = p.rec0 + (threadIdx.x == 0 ? first : min(first + blockDim.x - 1, p.n_rec - 1));
-        uint64_t lo = 0, hi = p.lut_len;
-        while (lo < hi) {
-            uint64_t mid = (lo + hi) >> 1;
-            if (p.lut[mid] <= ib) lo = mid + 1;
-            else hi = mid;
-        }
-        s_bound[threadIdx.x] = lo;
-    }
-    __syncthreads();
+    // 256 consecutive records lie between those of its first record and of the next CTA's first record, which
+    // kcf_lut_bounds_kernel searched beforehand (23 dependent loads for 512 bins x 4^7 prefixes, once per CTA instead of
+    // once per record); what is left here is a search over the few entries in between.
     if (t >= p.n_rec) return;
     const uint64_t i = p.rec0 + t;
-    uint64_t lo = s_bound[0], hi = s_bound[1];
+    uint64_t lo = p.cta_bound[blockIdx.x], hi = p.cta_bound[blockIdx.x + 1];
     while (lo < hi) {
         uint64_t mid = (lo + hi) >> 1;
         if (p.lut[mid] <= i) lo = mid + 1;
@@ -199,28 +204,44 @@ __global__ void __launch_bounds__(256) kcf_ingest_kernel(KcfIngestParams p, KcfT
             uint8_t *line = p.table + (uint64_t)kcf_line_wrap(home, d, g) * KCF_LINE_BYTES;
             uint32_t *w = reinterpret_cast<uint32_t *>(line);
             bool placed = false;
-            for (uint32_t s = 0; s < g.S; ++s) {
-                uint32_t v = ((volatile uint32_t *)w)[s];
-                if (v == KCF_EMPTY_LO) {
-                    v = atomicCAS(&w[s], KCF_EMPTY_LO, lo); // claiming a slot and publishing the low word are one step
-                    if (v == KCF_EMPTY_LO) {
-                        w[g.S + s] = hi;
-                        // count and mask bits are cleared out of the all-ones initial image (atomics: several writers
-                        // share these 32-bit words)
-                        const uint32_t off = g.coff + g.cw * s;
-                        const uint32_t sh = 8 * (off & 3u);
-                        const uint32_t field = g.cw == 4 ? 0xFFFFFFFFu : (((1u << (8 * g.cw)) - 1u) << sh);
-                        atomicAnd(w + (off >> 2), ~field | (count << sh));
-                        atomicAnd(home_w31, ~(1u << (16 + d)));
-                        if (d > 0) kcf_filter_add(home_line, kmer, g);
-                        atomicAdd(&p.counters[0], 1ULL);
-                        placed = true;
-                        break;
-                    }
+            // One look at the line's low key words (four 16-byte loads past L1), then claim the first slot seen empty.
+            // Slots fill in order and never change once written, so every slot before the one claimed has been compared
+            // with its final content: either in the snapshot, or through the value a failed CAS returns.
+            uint32_t snap[16];
+            {
+                const uint4 *q = reinterpret_cast<const uint4 *>(line);
+                const uint4 a = __ldcg(q), b = __ldcg(q + 1), c = __ldcg(q + 2), e = __ldcg(q + 3);
+                snap[0] = a.x; snap[1] = a.y; snap[2] = a.z; snap[3] = a.w; snap[4] = b.x; snap[5] = b.y; snap[6] = b.z; snap[7] = b.w;
+                snap[8] = c.x; snap[9] = c.y; snap[10] = c.z; snap[11] = c.w; snap[12] = e.x; snap[13] = e.y; snap[14] = e.z; snap[15] = e.w;
+            }
+            bool dup = false;
+            uint32_t s0 = g.S;
+#pragma unroll
+            for (uint32_t s = 0; s < 13; ++s) {
+                if (s < g.S && s < s0) {
+                    if (snap[s] == lo) dup = true;
+                    else if (snap[s] == KCF_EMPTY_LO) s0 = s;
                 }
-                // a key with the same low word already lives in this line: keep low words unique per line (a probe
-                // then has one candidate at most) and move on to the next line
-                if (v == lo) break;
+            }
+            // a key with the same low word already lives in this line: keep low words unique per line (a probe then has
+            // one candidate at most) and move on to the next line
+            for (uint32_t s = s0; !dup && s < g.S; ++s) {
+                const uint32_t v = atomicCAS(&w[s], KCF_EMPTY_LO, lo); // claiming a slot and publishing the low word are one step
+                if (v == KCF_EMPTY_LO) {
+                    w[g.S + s] = hi;
+                    // count and mask bits are cleared out of the all-ones initial image (atomics: several writers
+                    // share these 32-bit words)
+                    const uint32_t off = g.coff + g.cw * s;
+                    const uint32_t sh = 8 * (off & 3u);
+                    const uint32_t field = g.cw == 4 ? 0xFFFFFFFFu : (((1u << (8 * g.cw)) - 1u) << sh);
+                    atomicAnd(w + (off >> 2), ~field | (count << sh));
+                    atomicAnd(home_w31, ~(1u << (16 + d)));
+                    if (d > 0) kcf_filter_add(home_line, kmer, g);
+                    atomicAdd(&p.counters[0], 1ULL);
+                    placed = true;
+                    break;
+                }
+                if (v == lo) dup = true;
             }
             if (placed) return;
         }
@@ -427,6 +448,7 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     uint8_t *h_stage[2] = {nullptr, nullptr};
     KcfStashEntry *d_ovf = nullptr;
     unsigned long long *d_counters = nullptr;
+    uint64_t *d_bound = nullptr; // per-CTA LUT bounds of the chunk in flight
     cudaEvent_t ev[2] = {nullptr, nullptr};
     int rc = KCF_OK;
     const uint64_t chunk_rec = std::max<uint64_t>(1, (64ULL << 20) / std::max<uint32_t>(rec_size, 1));
@@ -451,6 +473,7 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     DB_CUDA(cudaMalloc(&d_sigmap, sig_map_size * 4));
     DB_CUDA(cudaMalloc(&d_norm, (1ULL << (2 * L)) * 4));
     DB_CUDA(cudaMalloc(&d_counters, 4 * sizeof(unsigned long long)));
+    DB_CUDA(cudaMalloc(&d_bound, ((chunk_rec + 255) / 256 + 2) * sizeof(uint64_t)));
     DB_CUDA(cudaMemsetAsync(d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
     DB_CUDA(cudaMemsetAsync(ctx->d_flags, 0, FLAG_COUNT * sizeof(uint32_t), ctx->stream));
     DB_CUDA(cudaMalloc(&d_ovf, ovf_cap * sizeof(KcfStashEntry)));
@@ -493,6 +516,11 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
             if (r0 > 0) memcpy(p.prev, recs + (r0 - 1) * rec_size, std::min<uint32_t>(rec_size, 16));
             p.lut = d_lut;
             p.lut_len = lut_len;
+            {
+                const uint32_t n_cta = (uint32_t)((n + 255) / 256);
+                kcf_lut_bounds_kernel<<<(n_cta + 1 + 255) / 256, 256, 0, ctx->stream>>>(d_lut, lut_len, r0, n, n_cta, d_bound);
+            }
+            p.cta_bound = d_bound;
             p.sigmap = d_sigmap;
             p.norm = d_norm;
             p.P = (uint32_t)P;
@@ -552,6 +580,7 @@ done:
     if (d_norm) cudaFree(d_norm);
     if (d_ovf) cudaFree(d_ovf);
     if (d_counters) cudaFree(d_counters);
+    if (d_bound) cudaFree(d_bound);
     if (rc != KCF_OK) {
         if (db->table) cudaFree(db->table);
         if (db->stash) cudaFree(db->stash);
