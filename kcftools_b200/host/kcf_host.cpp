@@ -4,6 +4,7 @@
 #include "kcf_tools.hpp"
 
 #include <algorithm>
+#include <charconv>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -66,23 +67,19 @@ template <typename T> Digits shortest_digits(T v, int max_prec)
         r.e = 1;
         return r;
     }
+    // std::to_chars without a precision = the shortest digits that read back as the same value, the closest such
+    // decimal when there are several (what Double.toString / Float.toString start from); scientific form d.ddde+XX
+    (void)max_prec;
     char buf[64];
-    for (int p = 1; p <= max_prec; ++p) {
-        std::snprintf(buf, sizeof buf, "%.*e", p - 1, (double)std::fabs(v));
-        const T back = sizeof(T) == 4 ? (T)std::strtof(buf, nullptr) : (T)std::strtod(buf, nullptr);
-        if (back == std::fabs(v) || p == max_prec) {
-            // d.ddddde±xx
-            std::string s(buf);
-            const size_t epos = s.find('e');
-            std::string mant = s.substr(0, epos);
-            const int ex = std::atoi(s.c_str() + epos + 1);
-            mant.erase(std::remove(mant.begin(), mant.end(), '.'), mant.end());
-            while (mant.size() > 1 && mant.back() == '0') mant.pop_back();
-            r.d = mant;
-            r.e = ex + 1;
-            return r;
-        }
-    }
+    const auto res = std::to_chars(buf, buf + sizeof buf, (T)std::fabs(v), std::chars_format::scientific);
+    std::string s(buf, res.ptr);
+    const size_t epos = s.find('e');
+    std::string mant = s.substr(0, epos);
+    const int ex = std::atoi(s.c_str() + epos + 1);
+    mant.erase(std::remove(mant.begin(), mant.end(), '.'), mant.end());
+    while (mant.size() > 1 && mant.back() == '0') mant.pop_back();
+    r.d = mant;
+    r.e = ex + 1;
     return r;
 }
 
@@ -805,12 +802,14 @@ std::string kcfRowText(const Window &w, const kcf_result_t &r, const double weig
     const double kd = r.obs > 0 ? (double)r.kmer_count_sum / r.obs : 0.0; // Data.java:87
     std::ostringstream sb;
     sb << w.sequenceName << "\t" << w.start << "\t" << w.end << "\t" << w.windowId << "\t" << r.total_kmers << "\t";
-    sb << "EFFLEN=" << r.eff_len << ";IS=" << java_format_2f(minScore) << ";XS=" << java_format_2f(maxScore) << ";MS=" << java_format_2f(score)
+    const std::string sc2 = java_format_2f(score); // min = max = mean = the score unless it is 0 (XS then starts from Float.MIN_VALUE)
+    sb << "EFFLEN=" << r.eff_len << ";IS=" << (minScore == score ? sc2 : java_format_2f(minScore)) << ";XS=" << (maxScore == score ? sc2 : java_format_2f(maxScore))
+       << ";MS=" << sc2
        << ";IO=" << r.obs << ";XO=" << r.obs << ";MO=" << java_format_2f((double)meanObs) << ";IV=" << r.variations << ";XV=" << r.variations
        << ";MV=" << java_float_to_string(meanVar);
     sb << "\tGT:VA:OB:ID:LD:RD:KD:SC\t";
     sb << "N:" << r.variations << ":" << r.obs << ":" << r.inner << ":" << r.left << ":" << r.right << ":" << java_format_2f(kd) << ":"
-       << java_format_2f(score);
+       << sc2;
     return sb.str();
 }
 
@@ -848,6 +847,27 @@ static void screenAllSequences(Device &dev, const std::vector<std::vector<Window
     }
 }
 
+// A command uses ONE GPU.  CUDA's start-up cost grows with the number of visible devices (3.5 s on an 8-GPU B200 box
+// against 0.4 s with one device visible), so before the first CUDA call the process narrows CUDA_VISIBLE_DEVICES to the
+// device it was asked for and addresses it as ordinal 0.  Returns the ordinal to pass to kcf_init.
+int restrictToDevice(int device)
+{
+    static bool done = false;
+    if (done) return 0;
+    const char *cur = std::getenv("CUDA_VISIBLE_DEVICES");
+    std::string pick = std::to_string(device);
+    if (cur && *cur) { // already a list: take its device-th entry
+        const std::vector<std::string> ids = java_split(cur, ',');
+        if (device < 0 || (size_t)device >= ids.size()) return device; // let kcf_init report the bad ordinal
+        pick = ids[(size_t)device];
+    } else if (device < 0) {
+        return device;
+    }
+    setenv("CUDA_VISIBLE_DEVICES", pick.c_str(), 1);
+    done = true;
+    return 0;
+}
+
 int getVariations(GetVariantsOptions o)
 {
     // Extension: `-k a,b,c -s x,y,z` screens several databases against the same reference and writes
@@ -861,11 +881,17 @@ int getVariations(GetVariantsOptions o)
     if (!multi) sampleNames = {o.sampleName};
     for (std::string &s : sampleNames) s = cleanSampleName(s);
     Device dev;
-    if (kcf_init(o.device, &dev.ctx) != KCF_OK) Logger::error("KMC", std::string(kcf_last_error(nullptr)));
+    if (kcf_init(restrictToDevice(o.device), &dev.ctx) != KCF_OK) Logger::error("KMC", std::string(kcf_last_error(nullptr)));
     if (kcf_db_open(dev.ctx, prefixes[0].c_str(), 0, &dev.db) != KCF_OK) dev.fail("KMC");
     kcf_db_info_t info;
     kcf_db_info(dev.db, &info);
     const int kmerSize = info.kmer_length;
+    {
+        char buf[256];
+        std::snprintf(buf, sizeof buf, "KMC database resident on device %d: %lld kmers (k=%d) in a %.2f GB table, loaded in %.3f s", o.device,
+                      (long long)info.resident_kmers, kmerSize, (double)info.table_bytes / 1e9, info.load_seconds);
+        Logger::info("KMC", buf);
+    }
 
     FastaIndex index(o.refFasta);
     std::unique_ptr<GTF> gtf;
@@ -910,6 +936,7 @@ int getVariations(GetVariantsOptions o)
             if (rc == KCF_ERR_WEIGHTS) Logger::error("Data", "Weights should sum to 1.0");
             if (rc != KCF_OK) dev.fail(GV_CLASS);
         }
+        Logger::info(GV_CLASS, "Screened " + std::to_string(totalWindows) + " windows");
         out << kcfHeaderText(o, sampleNames[0], index, kmerSize, (int)totalWindows, today());
         for (size_t s = 0; s < perSeq.size(); ++s)
             for (size_t i : sorted[s]) out << kcfRowText(perSeq[s][i], results[s][i], weights) << "\n";
@@ -972,6 +999,7 @@ int getVariations(GetVariantsOptions o)
     }
     out.flush();
     if (!out) throw FatalError("Error writing KCF file window");
+    Logger::info(GV_CLASS, "KCF file written: " + o.outFile);
     return 0;
 }
 
@@ -1119,6 +1147,14 @@ int cliMain(int argc, const char *const *argv)
         return argc < 2 ? 2 : 0;
     }
     const std::string cmd = argv[1];
+    const auto t_start = std::chrono::steady_clock::now();
+    auto finish = [&](int rc) { // KCFTOOLS.java:44-62
+        const long long ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t_start).count();
+        char buf[64];
+        std::snprintf(buf, sizeof buf, "%02lld:%02lld:%02lld", ms / 3600000, (ms % 3600000) / 60000, (ms % 60000) / 1000);
+        if (rc == 0) Logger::info("KCFTOOLS", std::string("Total execution time: ") + buf);
+        return rc;
+    };
     std::string cmdline;
     for (int i = 0; i < argc; ++i) cmdline += std::string(i ? " " : "") + argv[i];
     try {
@@ -1132,11 +1168,11 @@ int cliMain(int argc, const char *const *argv)
             ps.o.commandLine = cmdline;
             printCommandLine(ps.o);
             validateCMD(ps.o);
-            return getVariations(ps.o);
+            return finish(getVariations(ps.o));
         }
-        if (cmd == "cohort") return cohortMain(argc, argv, cmdline);
-        if (cmd == "findIBS") return findIBSMain(argc, argv, cmdline);
-        if (cmd == "kcf2gt") return kcf2gtMain(argc, argv, cmdline);
+        if (cmd == "cohort") return finish(cohortMain(argc, argv, cmdline));
+        if (cmd == "findIBS") return finish(findIBSMain(argc, argv, cmdline));
+        if (cmd == "kcf2gt") return finish(kcf2gtMain(argc, argv, cmdline));
         if (cmd == "_kcfheader") { // test hook: parse a KCF file's header (and rows) on the host, print the header back
             if (argc < 3) throw UsageError("_kcfheader <file.kcf>");
             const KcfFile f = readKcf(argv[2]);

@@ -146,6 +146,7 @@ double computeScore(const kcf_result_t &r, const double weights[3]);          //
 int cohortMain(int argc, const char *const *argv, const std::string &cmdline);   // Plugins/Cohort.java
 int findIBSMain(int argc, const char *const *argv, const std::string &cmdline);  // Plugins/FindIBS.java
 int kcf2gtMain(int argc, const char *const *argv, const std::string &cmdline);   // Plugins/KCFToGenotypeTable.java
+int restrictToDevice(int device);                                              // narrow CUDA_VISIBLE_DEVICES before the first CUDA call
 int getVariations(GetVariantsOptions o);                                       // GetVariants.java:92-183; 0 or throws
 int cliMain(int argc, const char *const *argv);                                // KCFTOOLS.main + picocli parsing
 

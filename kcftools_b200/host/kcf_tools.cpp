@@ -259,7 +259,7 @@ struct Dev {
     }
     void open(int device, const char *cls)
     {
-        if (kcf_init(device, &ctx) != KCF_OK) Logger::error(cls, std::string(kcf_last_error(nullptr)));
+        if (kcf_init(restrictToDevice(device), &ctx) != KCF_OK) Logger::error(cls, std::string(kcf_last_error(nullptr)));
     }
     [[noreturn]] void fail(const char *cls) const { Logger::error(cls, kcf_last_error(ctx)); }
 };
