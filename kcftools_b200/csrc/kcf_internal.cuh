@@ -140,6 +140,7 @@ struct kcf_ctx {
     // raw FASTA bytes are staged through two device buffers: the H2D copy of one sequence (copy stream) overlaps the
     // 2-bit packing of the previous one and whatever screening is queued on the main stream
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t desc_stream = nullptr; // window descriptors of new plans: never queued behind a sequence upload
     uint8_t *d_raw[2] = {nullptr, nullptr};
     size_t d_raw_cap[2] = {0, 0};
     cudaEvent_t raw_free[2] = {nullptr, nullptr}; // pack kernel done: staging buffer reusable
@@ -175,6 +176,7 @@ struct kcf_plan {
     kcf_ctx *ctx = nullptr;
     int32_t k = 0;
     uint64_t n_wins = 0, n_segs = 0, n_tiles = 0, n_positions = 0;
+    void *d_block = nullptr;          // the one device allocation holding the arrays below
     kcf_window_t *d_wins = nullptr;
     kcf_segment_t *d_segs = nullptr;
     uint32_t *d_seg_off = nullptr;    // offset of each segment inside its window

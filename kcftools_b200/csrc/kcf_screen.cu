@@ -701,13 +701,7 @@ extern "C" void kcf_plan_destroy(kcf_plan *plan)
     if (!plan) return;
     cudaSetDevice(plan->ctx->device);
     cudaStreamSynchronize(plan->ctx->stream);
-    cudaFree(plan->d_wins);
-    cudaFree(plan->d_segs);
-    cudaFree(plan->d_seg_off);
-    cudaFree(plan->d_win_len);
-    cudaFree(plan->d_tile_first);
-    cudaFree(plan->d_tile_sum);
-    cudaFree(plan->d_out);
+    cudaFree(plan->d_block); // d_wins .. d_out live in it
     cudaFree(plan->x_keys);
     cudaFree(plan->x_homes);
     cudaFree(plan->x_okw);
@@ -774,22 +768,42 @@ extern "C" int kcf_plan_create(kcf_ctx *ctx, int32_t kmer_length, const kcf_wind
         if (e__ != cudaSuccess && rc == KCF_OK)                                                         \
             rc = kcf_fail(ctx, e__ == cudaErrorMemoryAllocation ? KCF_ERR_NOMEM : KCF_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
     } while (0)
-    PL_CUDA(cudaMalloc(&plan->d_wins, std::max<uint64_t>(n_wins, 1) * sizeof(kcf_window_t)));
-    PL_CUDA(cudaMalloc(&plan->d_segs, std::max<uint64_t>(n_segs, 1) * sizeof(kcf_segment_t)));
-    PL_CUDA(cudaMalloc(&plan->d_seg_off, std::max<uint64_t>(n_segs, 1) * 4));
-    PL_CUDA(cudaMalloc(&plan->d_win_len, std::max<uint64_t>(n_wins, 1) * 4));
-    PL_CUDA(cudaMalloc(&plan->d_tile_first, (n_wins + 1) * 8));
-    PL_CUDA(cudaMalloc(&plan->d_tile_sum, std::max<uint64_t>(tiles, 1) * sizeof(KcfGap) + 8)); // +8: the tile counter lives at the end
-    PL_CUDA(cudaMalloc(&plan->d_out, std::max<uint64_t>(n_wins, 1) * sizeof(kcf_result_t)));
-    if (rc == KCF_OK && n_wins) {
-        // descriptors travel on the copy stream: creating a plan never waits for kernels queued on the main stream
-        PL_CUDA(cudaMemcpyAsync(plan->d_wins, wins, n_wins * sizeof(kcf_window_t), cudaMemcpyHostToDevice, ctx->copy_stream));
-        PL_CUDA(cudaMemcpyAsync(plan->d_segs, segs, n_segs * sizeof(kcf_segment_t), cudaMemcpyHostToDevice, ctx->copy_stream));
-        PL_CUDA(cudaMemcpyAsync(plan->d_seg_off, seg_off.data(), n_segs * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
-        PL_CUDA(cudaMemcpyAsync(plan->d_win_len, win_len.data(), n_wins * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    {
+        // one device block for all arrays of the plan (one cudaMalloc on the upload path instead of seven)
+        auto up = [](uint64_t b) { return (b + 255) & ~255ULL; };
+        const uint64_t nw = std::max<uint64_t>(n_wins, 1), ns = std::max<uint64_t>(n_segs, 1);
+        const uint64_t b_wins = up(nw * sizeof(kcf_window_t)), b_segs = up(ns * sizeof(kcf_segment_t)), b_off = up(ns * 4), b_len = up(nw * 4),
+                       b_tf = up((n_wins + 1) * 8), b_ts = up(std::max<uint64_t>(tiles, 1) * sizeof(KcfGap) + 8), // +8: the tile counter lives at the end
+                       b_out = up(nw * sizeof(kcf_result_t));
+        uint8_t *base = nullptr;
+        PL_CUDA(cudaMalloc(&base, b_wins + b_segs + b_off + b_len + b_tf + b_ts + b_out));
+        plan->d_block = base;
+        if (base) {
+            plan->d_wins = reinterpret_cast<kcf_window_t *>(base);
+            base += b_wins;
+            plan->d_segs = reinterpret_cast<kcf_segment_t *>(base);
+            base += b_segs;
+            plan->d_seg_off = reinterpret_cast<uint32_t *>(base);
+            base += b_off;
+            plan->d_win_len = reinterpret_cast<uint32_t *>(base);
+            base += b_len;
+            plan->d_tile_first = reinterpret_cast<uint64_t *>(base);
+            base += b_tf;
+            plan->d_tile_sum = reinterpret_cast<KcfGap *>(base);
+            base += b_ts;
+            plan->d_out = reinterpret_cast<kcf_result_t *>(base);
+        }
     }
-    if (rc == KCF_OK) PL_CUDA(cudaMemcpyAsync(plan->d_tile_first, tile_first.data(), (n_wins + 1) * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
-    if (rc == KCF_OK) PL_CUDA(cudaStreamSynchronize(ctx->copy_stream)); // host vectors go out of scope; caller may free wins/segs
+    if (rc == KCF_OK && n_wins) {
+        // descriptors travel on their own stream: creating a plan waits neither for kernels queued on the main stream nor
+        // for a sequence upload in flight on the copy stream (the host goes on to queue the next upload at once)
+        PL_CUDA(cudaMemcpyAsync(plan->d_wins, wins, n_wins * sizeof(kcf_window_t), cudaMemcpyHostToDevice, ctx->desc_stream));
+        PL_CUDA(cudaMemcpyAsync(plan->d_segs, segs, n_segs * sizeof(kcf_segment_t), cudaMemcpyHostToDevice, ctx->desc_stream));
+        PL_CUDA(cudaMemcpyAsync(plan->d_seg_off, seg_off.data(), n_segs * 4, cudaMemcpyHostToDevice, ctx->desc_stream));
+        PL_CUDA(cudaMemcpyAsync(plan->d_win_len, win_len.data(), n_wins * 4, cudaMemcpyHostToDevice, ctx->desc_stream));
+    }
+    if (rc == KCF_OK) PL_CUDA(cudaMemcpyAsync(plan->d_tile_first, tile_first.data(), (n_wins + 1) * 8, cudaMemcpyHostToDevice, ctx->desc_stream));
+    if (rc == KCF_OK) PL_CUDA(cudaStreamSynchronize(ctx->desc_stream)); // host vectors go out of scope; caller may free wins/segs
 #undef PL_CUDA
     if (rc != KCF_OK) {
         kcf_plan_destroy(plan);
