@@ -26,12 +26,12 @@
 static void kcf_parallel_copy(uint8_t *dst, const uint8_t *src, size_t n)
 {
     static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const unsigned nt = (unsigned)std::min<size_t>(std::min(hw, 6u), std::max<size_t>(n >> 22, 1)); // >= 4 MB per thread
+    const unsigned nt = (unsigned)std::min<size_t>(std::min(hw > 2 ? hw - 2 : 1u, 12u), std::max<size_t>(n >> 22, 1)); // >= 4 MB per thread
     if (nt <= 1) {
         memcpy(dst, src, n);
         return;
     }
-    std::thread th[8];
+    std::thread th[12];
     const size_t per = ((n / nt) + 4095) & ~(size_t)4095;
     for (unsigned t = 0; t < nt; ++t) {
         const size_t a = std::min(n, (size_t)t * per), b = (t + 1 == nt) ? n : std::min(n, (size_t)(t + 1) * per);
@@ -449,7 +449,8 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     KcfStashEntry *d_ovf = nullptr;
     unsigned long long *d_counters = nullptr;
     uint64_t *d_bound = nullptr; // per-CTA LUT bounds of the chunk in flight
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};    // ingest kernel of the chunk staged in buffer j done: both staging buffers j reusable
+    cudaEvent_t evc[2] = {nullptr, nullptr};   // H2D copy of buffer j done
     int rc = KCF_OK;
     const uint64_t chunk_rec = std::max<uint64_t>(1, (64ULL << 20) / std::max<uint32_t>(rec_size, 1));
     const uint64_t chunk_bytes = chunk_rec * std::max<uint32_t>(rec_size, 1);
@@ -489,6 +490,7 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
         DB_CUDA(cudaMalloc(&d_stage[j], chunk_bytes));
         DB_CUDA(cudaHostAlloc(&h_stage[j], chunk_bytes, cudaHostAllocDefault));
         DB_CUDA(cudaEventCreateWithFlags(&ev[j], cudaEventDisableTiming));
+        DB_CUDA(cudaEventCreateWithFlags(&evc[j], cudaEventDisableTiming));
     }
     for (int pass = 0; pass < 4; ++pass) {
         if (pass > 0) {
@@ -507,7 +509,10 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
             uint64_t n = std::min<uint64_t>(chunk_rec, N - r0);
             DB_CUDA(cudaEventSynchronize(ev[j])); // staging buffer j free again
             kcf_parallel_copy(h_stage[j], recs + r0 * rec_size, n * rec_size); // page cache / caller memory -> pinned staging
-            DB_CUDA(cudaMemcpyAsync(d_stage[j], h_stage[j], n * rec_size, cudaMemcpyHostToDevice, ctx->stream));
+            // the copy rides the copy stream: chunk j+1 crosses PCIe while the ingest kernel of chunk j runs
+            DB_CUDA(cudaMemcpyAsync(d_stage[j], h_stage[j], n * rec_size, cudaMemcpyHostToDevice, ctx->copy_stream));
+            DB_CUDA(cudaEventRecord(evc[j], ctx->copy_stream));
+            DB_CUDA(cudaStreamWaitEvent(ctx->stream, evc[j], 0));
             KcfIngestParams p{};
             p.rec = d_stage[j];
             p.rec0 = r0;
@@ -574,6 +579,7 @@ done:
         if (d_stage[j]) cudaFree(d_stage[j]);
         if (h_stage[j]) cudaFreeHost(h_stage[j]);
         if (ev[j]) cudaEventDestroy(ev[j]);
+        if (evc[j]) cudaEventDestroy(evc[j]);
     }
     if (d_lut) cudaFree(d_lut);
     if (d_sigmap) cudaFree(d_sigmap);

@@ -225,7 +225,7 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
         if (hit) sum += cnt;                                                                                           \
         const uint32_t hb = __ballot_sync(0xffffffffu, hit);                                                           \
         const uint32_t pb = __ballot_sync(0xffffffffu, pending);                                                       \
-        if (lane == 0) W.hit[JJ] = hb; /* the queue flush ORs late hits into it, after this store */                    \
+        W.hit[JJ] = hb; /* every lane stores the same word; the queue flush ORs late hits into it, after this store */  \
         if (COUNTS) p.counts_out[(tile - p.counts_tile0) * KCF_TILE + chunk * KCF_CHUNK + cpos] = ok ? (int32_t)cnt : -1; \
         if (pb) {                                                                                                      \
             if (pending) {                                                                                             \
