@@ -213,7 +213,8 @@ typedef struct kcf_cell_t {   /* one sample in one window = Data/Data.java:16-24
     int64_t kmer_count;       /* Σ count (from a plan) or Math.round(KD * obs) (from a KCF row, Window.java:70) */
     double score;
 } kcf_cell_t;
-/* total_kmers / eff_len: per window (host arrays), or both NULL when the first kcf_cohort_add_plan is to define them. */
+/* total_kmers / eff_len: per window (host arrays), or both NULL: the first sample added with kcf_cohort_add_plan then
+ * defines them, and has to be added completely (all its plans) before any other sample. */
 int kcf_cohort_create(kcf_ctx *ctx, uint64_t n_windows, uint32_t n_samples, const int32_t *total_kmers, const int32_t *eff_len,
                       kcf_cohort **out);
 void kcf_cohort_destroy(kcf_cohort *c);
