@@ -18,6 +18,7 @@
 #include <sstream>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <thread>
 #include <unistd.h>
 
 namespace kcfh {
@@ -875,13 +876,14 @@ int getVariations(GetVariantsOptions o)
     const std::vector<std::string> prefixes = java_split(o.kmcDBprefix, ',');
     std::vector<std::string> sampleNames = java_split(o.sampleName, ',');
     const bool multi = prefixes.size() > 1;
+    const bool multiDevice = multi && o.devices.size() > 1;
     if (multi && sampleNames.size() != prefixes.size())
         Logger::error(GV_CLASS, "Number of sample names (" + std::to_string(sampleNames.size()) + ") differs from the number of KMC databases (" +
                                     std::to_string(prefixes.size()) + ")");
     if (!multi) sampleNames = {o.sampleName};
     for (std::string &s : sampleNames) s = cleanSampleName(s);
     Device dev;
-    if (kcf_init(restrictToDevice(o.device), &dev.ctx) != KCF_OK) Logger::error("KMC", std::string(kcf_last_error(nullptr)));
+    if (kcf_init(multiDevice ? o.device : restrictToDevice(o.device), &dev.ctx) != KCF_OK) Logger::error("KMC", std::string(kcf_last_error(nullptr)));
     if (kcf_db_open(dev.ctx, prefixes[0].c_str(), 0, &dev.db) != KCF_OK) dev.fail("KMC");
     kcf_db_info_t info;
     kcf_db_info(dev.db, &info);
@@ -910,12 +912,15 @@ int getVariations(GetVariantsOptions o)
             if (w.noFasta) Logger::error(GV_CLASS, "Fasta object is null for window: " + w.windowId); // GetVariants.java:213-216
 
     // upload the sequences (queued; the copies overlap the 2-bit packing), then one plan per sequence
-    for (const FastaIndexEntry &e : index.entries()) {
-        uint64_t n = 0;
-        const uint8_t *bytes = index.seqBytes(e.seqId, &n);
-        int sid = -1;
-        if (kcf_ref_add_async(dev.ctx, bytes, n, (uint32_t)e.lineBases, (uint32_t)e.lineWidth, (uint64_t)e.length, &sid) != KCF_OK) dev.fail(FAI_CLASS);
-    }
+    auto uploadReference = [&index](Device &dv) {
+        for (const FastaIndexEntry &e : index.entries()) {
+            uint64_t n = 0;
+            const uint8_t *bytes = index.seqBytes(e.seqId, &n);
+            int sid = -1;
+            if (kcf_ref_add_async(dv.ctx, bytes, n, (uint32_t)e.lineBases, (uint32_t)e.lineWidth, (uint64_t)e.length, &sid) != KCF_OK) dv.fail(FAI_CLASS);
+        }
+    };
+    uploadReference(dev);
     const double weights[3] = {o.innerDistanceWeight, o.tailDistanceWeight, o.kmerRatioWeight}; // getWeights(), :388-390
     // per sequence: the order the reference writes (stable sort by start, GetVariants.java:169-171)
     std::vector<std::vector<size_t>> sorted(perSeq.size());
@@ -940,6 +945,82 @@ int getVariations(GetVariantsOptions o)
         out << kcfHeaderText(o, sampleNames[0], index, kmerSize, (int)totalWindows, today());
         for (size_t s = 0; s < perSeq.size(); ++s)
             for (size_t i : sorted[s]) out << kcfRowText(perSeq[s][i], results[s][i], weights) << "\n";
+    } else if (multiDevice) {
+        // configs[4] of BASELINE.json on one box: the SAMPLES are shared out over the GPUs (database d on device d mod G);
+        // every device holds the reference, screens its databases in turn, and the host gathers the rows.  The scores of a
+        // plan are bit-identical to the ones `cohort` recomputes from the integers (same formula, same roundings).
+        const size_t G = o.devices.size(), D = prefixes.size();
+        std::vector<std::vector<std::vector<kcf_result_t>>> rows(D, std::vector<std::vector<kcf_result_t>>(perSeq.size()));
+        std::vector<std::string> failure(G);
+        auto work = [&](size_t g, Device *dv) {
+            try {
+                std::unique_ptr<Device> own;
+                if (!dv) { // device 0 of the list is `dev`: context, first database and reference are already there
+                    own.reset(new Device());
+                    dv = own.get();
+                    if (kcf_init(o.devices[g], &dv->ctx) != KCF_OK) Logger::error("KMC", std::string(kcf_last_error(nullptr)));
+                    uploadReference(*dv);
+                }
+                for (size_t d = g; d < D; d += G) {
+                    if (!(dv == &dev && d == 0)) {
+                        for (kcf_plan *p : dv->plans) kcf_plan_destroy(p);
+                        dv->plans.clear();
+                        if (dv->db) kcf_db_close(dv->db);
+                        dv->db = nullptr;
+                        if (kcf_db_open(dv->ctx, prefixes[d].c_str(), 0, &dv->db) != KCF_OK) dv->fail("KMC");
+                        kcf_db_info_t inf;
+                        kcf_db_info(dv->db, &inf);
+                        if (inf.kmer_length != kmerSize) Logger::error("KCFHeader", "Kmer size mismatch between the KCFs");
+                    }
+                    screenAllSequences(*dv, perSeq, kmerSize, o.minKmerCount, weights);
+                    for (size_t s = 0; s < perSeq.size(); ++s) {
+                        rows[d][s].resize(perSeq[s].size());
+                        const int rc = kcf_plan_fetch(dv->ctx, dv->plans[s], rows[d][s].data());
+                        if (rc == KCF_ERR_WEIGHTS) Logger::error("Data", "Weights should sum to 1.0");
+                        if (rc != KCF_OK) dv->fail(GV_CLASS);
+                    }
+                    Logger::info(GV_CLASS, "Sample " + sampleNames[d] + " screened on device " + std::to_string(o.devices[g]));
+                }
+            } catch (const std::exception &e) {
+                failure[g] = e.what()[0] ? e.what() : "failed";
+            }
+        };
+        std::vector<std::thread> threads;
+        for (size_t g = 1; g < G; ++g) threads.emplace_back(work, g, (Device *)nullptr);
+        work(0, &dev);
+        for (std::thread &t : threads) t.join();
+        for (size_t g = 0; g < G; ++g)
+            if (!failure[g].empty()) throw FatalError(failure[g]); // already logged by the worker
+        std::string sampleCols = sampleNames[0];
+        for (size_t d = 1; d < D; ++d) sampleCols += "\t" + sampleNames[d];
+        out << kcfHeaderText(o, sampleCols, index, kmerSize, (int)totalWindows, today());
+        for (size_t s = 0; s < perSeq.size(); ++s)
+            for (size_t i : sorted[s]) {
+                const Window &w = perSeq[s][i];
+                KcfRow row;
+                row.seq = w.sequenceName;
+                row.wid = w.windowId;
+                row.start = w.start;
+                row.end = w.end;
+                row.total = rows[0][s][i].total_kmers;
+                row.eff = rows[0][s][i].eff_len;
+                for (size_t d = 0; d < D; ++d) {
+                    const kcf_result_t &r = rows[d][s][i];
+                    if (r.total_kmers != row.total || r.eff_len != row.eff) Logger::error("Cohort", "Windows mismatch found in sample: " + sampleNames[d]);
+                    kcf_cell_t c{};
+                    c.obs = r.obs;
+                    c.variations = r.variations;
+                    c.inner = r.inner;
+                    c.left = r.left;
+                    c.right = r.right;
+                    c.ibs = -1;
+                    const double kd = r.obs > 0 ? (double)r.kmer_count_sum / r.obs : 0.0;                     // Data.java:87, as written by getVariations
+                    c.kmer_count = java_round(std::strtod(java_format_2f(kd).c_str(), nullptr) * (double)r.obs); // as re-read by cohort
+                    c.score = r.score;
+                    row.cells.push_back(c);
+                }
+                out << kcfRowTextMulti(row) << "\n";
+            }
     } else {
         // every database in turn against the resident reference; its rows go device-to-device into the cohort matrix
         std::vector<size_t> offset(perSeq.size() + 1, 0);
@@ -1025,7 +1106,8 @@ const char *const USAGE =
     "  -g, --gtf=<gtfFile>          GTF file name\n"
     "  -c, --min-k-count=<minKmerCount> Minimum kmer count to consider [1]\n"
     "  -p, --step=<stepSize>        Step size for sliding window [window size]\n"
-    "      --device=<cudaOrdinal>   CUDA device (this build; the database always lives in HBM, -m and -t are accepted)\n";
+    "      --device=<cudaOrdinal>   CUDA device (this build; the database always lives in HBM, -m and -t are accepted)\n"
+    "      --devices=<a,b,...>      with several databases (-k x,y,... -s p,q,...): share them out over these CUDA devices\n";
 
 struct OptSpec {
     const char *shortName, *longName;
@@ -1035,7 +1117,7 @@ struct OptSpec {
 const OptSpec SPECS[] = {{"-r", "--reference", 0, true}, {"-k", "--kmc", 0, true},     {"-o", "--output", 0, true}, {"-s", "--sample", 0, true},
                          {"-f", "--feature", 0, true},   {"-t", "--threads", 1, false}, {"-m", "--memory", 3, false}, {nullptr, "--wi", 2, false},
                          {nullptr, "--wt", 2, false},    {nullptr, "--wr", 2, false},   {"-w", "--window", 1, false}, {"-g", "--gtf", 0, false},
-                         {"-c", "--min-k-count", 1, false}, {"-p", "--step", 1, false}, {nullptr, "--device", 1, false}, {nullptr, "--kmer-size", 1, false}};
+                         {"-c", "--min-k-count", 1, false}, {"-p", "--step", 1, false}, {nullptr, "--device", 1, false}, {nullptr, "--kmer-size", 1, false}, {nullptr, "--devices", 0, false}};
 
 struct Parsed {
     GetVariantsOptions o;
@@ -1107,6 +1189,15 @@ Parsed parse_options(int argc, const char *const *argv, int first, bool need_kmc
     I("--min-k-count", o.minKmerCount);
     I("--step", o.stepSize);
     I("--device", o.device);
+    if (ps.seen.count("--devices")) {
+        for (const std::string &d : java_split(ps.seen["--devices"], ',')) {
+            char *end = nullptr;
+            const long v = std::strtol(d.c_str(), &end, 10);
+            if (d.empty() || *end || v < 0 || v > 1023) throw UsageError("Invalid value for option '--devices': '" + d + "' is not a CUDA ordinal");
+            o.devices.push_back((int)v);
+        }
+        if (!o.devices.empty()) o.device = o.devices[0];
+    }
     I("--kmer-size", ps.kmerSizeOverride);
     D("--wi", o.innerDistanceWeight);
     D("--wt", o.tailDistanceWeight);

@@ -132,6 +132,7 @@ struct GetVariantsOptions {             // GetVariants.java:21-61, same names an
     int minKmerCount = 1;
     int stepSize = 0;
     int device = 0;                     // extension: CUDA ordinal (--device)
+    std::vector<int> devices;           // extension: --devices a,b,...: several databases (-k x,y,...) are shared out over these GPUs
     std::string commandLine;            // for ##CMD
 };
 

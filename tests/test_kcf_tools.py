@@ -338,6 +338,11 @@ def test_cohort_fed_from_device_results_equals_the_file_pipeline(cli, tmp_path):
     direct = str(tmp_path / "direct.kcf")
     run(cli, "getVariations", "-r", fa, "-k", ",".join(prefixes), "-o", direct, "-s", ",".join(names), "-f", "window", "-w", "2500")
     assert strip_volatile(open(direct).read()) == strip_volatile(open(merged).read())
+    # the same with the databases shared out over several devices (here two contexts on the one GPU: the thread-per-device
+    # path of configs[4], samples sharded over the GPUs of a box)
+    spread = str(tmp_path / "spread.kcf")
+    p = run(cli, "getVariations", "-r", fa, "-k", ",".join(prefixes), "-o", spread, "-s", ",".join(names), "-f", "window", "-w", "2500", "--devices", "0,0")
+    assert "Sample s1 screened on device 0" in p.stdout and strip_volatile(open(spread).read()) == strip_volatile(open(merged).read())
     rows = [l for l in open(direct).read().split("\n") if l and not l.startswith("#")]
     assert len(rows) == 22 and all(len(r.split("\t")) == 10 for r in rows)
     sc = np.array([[float(f.split(":")[7]) for f in r.split("\t")[7:]] for r in rows])

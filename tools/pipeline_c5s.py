@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--chrom-len", type=int, default=7_500_000)
     ap.add_argument("--window", type=int, default=50_000)
     ap.add_argument("--keep", default=None)
+    ap.add_argument("--devices", default=None, help="e.g. 0,1,2,3: also time the multi-database run with the samples shared out over these GPUs")
     args = ap.parse_args()
     import torch
     from tools import synth
@@ -71,6 +72,10 @@ def main():
     run("getVariations", "-r", fa, "-k", prefixes[0], "-o", os.path.join(d, "warm.kcf"), "-s", "warm", *w)  # .faidx + page cache
     direct = os.path.join(d, "cohort_direct.kcf")
     t_direct = run("getVariations", "-r", fa, "-k", ",".join(prefixes), "-o", direct, "-s", ",".join(names), *w)
+    t_spread = None
+    if args.devices:
+        spread = os.path.join(d, "cohort_spread.kcf")
+        t_spread = run("getVariations", "-r", fa, "-k", ",".join(prefixes), "-o", spread, "-s", ",".join(names), "--devices", args.devices, *w)
     singles, t_single = [], []
     for pre, nm in zip(prefixes, names):
         o = os.path.join(d, nm + ".kcf")
@@ -89,6 +94,8 @@ def main():
            "wall_s": {"getVariations_all_databases_to_cohort": round(t_direct, 3), "getVariations_per_sample": [round(t, 3) for t in t_single],
                       "cohort_from_files": round(t_cohort, 3), "findIBS_summary_bed": round(t_ibs, 3), "kcf2gt": round(t_gt, 3)},
            "direct_equals_file_pipeline": body(direct) == body(merged),
+           "wall_s_samples_over_devices": None if t_spread is None else {"devices": args.devices, "getVariations_all_databases_to_cohort": round(t_spread, 3),
+                                                                          "equals_file_pipeline": body(os.path.join(d, "cohort_spread.kcf")) == body(merged)},
            "ibs_blocks": len(open(os.path.join(d, "ibs.summary.tsv")).read().strip().split("\n")) - 1,
            "genotype_rows": len(open(os.path.join(d, "gt.tsv")).read().strip().split("\n")) - 2}
     print(json.dumps(out), flush=True)
