@@ -184,11 +184,14 @@ __device__ __forceinline__ bool kcf_probe_line(const uint8_t *line, uint64_t key
     if (S > 11 && c.w == lo) idx = 11;
     if (S > 12 && d.x == lo) idx = 12;
     if (idx < 0) return false;
-    if (__ldg(reinterpret_cast<const uint32_t *>(line) + S + idx) != (uint32_t)(key >> 32)) return false;
+    // high word and count depend on the slot only: both loads go out together (one L1 round trip, not two)
     constexpr int CW = S == 13 ? 1 : (S == 12 ? 2 : 4);
     constexpr int COFF = S == 13 ? 112 : 8 * S;
     const uint8_t *cp = line + COFF + CW * idx;
-    count = CW == 1 ? (uint32_t)__ldg(cp) : (CW == 2 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(cp)) : __ldg(reinterpret_cast<const uint32_t *>(cp)));
+    const uint32_t hiw = __ldg(reinterpret_cast<const uint32_t *>(line) + S + idx);
+    const uint32_t cntw = CW == 1 ? (uint32_t)__ldg(cp) : (CW == 2 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(cp)) : __ldg(reinterpret_cast<const uint32_t *>(cp)));
+    if (hiw != (uint32_t)(key >> 32)) return false;
+    count = cntw;
     return true;
 }
 
