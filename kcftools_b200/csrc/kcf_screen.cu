@@ -209,13 +209,15 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
         bool pending = false;                                                                                          \
         if (ok && mine) {                                                                                              \
             const bool inl = KCF_KEY_IN_LINES(key);                                                                    \
+            /* filter and mask words of the line travel with its key words: a miss needs them, and asking for them */  \
+            /* only after the compare would add a dependent round trip */                                              \
+            const uint32_t w31 = __ldg(reinterpret_cast<const uint32_t *>(L) + 31);                                    \
+            const unsigned long long fword = S == 13 ? __ldg(reinterpret_cast<const unsigned long long *>(L + 104))    \
+                                                     : (unsigned long long)__ldg(reinterpret_cast<const uint32_t *>(L + 120)); \
             if (!(inl && kcf_probe_line<S>(L, key, cnt))) {                                                            \
                 cnt = 0;                                                                                               \
                 /* absent unless the home line's filter says a key like this one lives outside it */                   \
-                /* filter and mask words go out together: the mask is needed whenever the filter passes */            \
-                const uint32_t w31 = __ldg(reinterpret_cast<const uint32_t *>(L) + 31);                                \
-                const bool maybe = S == 13 ? kcf_filter_pass64(__ldg(reinterpret_cast<const unsigned long long *>(L + 104)), key) \
-                                           : kcf_filter_pass32(__ldg(reinterpret_cast<const uint32_t *>(L + 120)), key); \
+                const bool maybe = S == 13 ? kcf_filter_pass64(fword, key) : kcf_filter_pass32((uint32_t)fword, key);  \
                 if (maybe) {                                                                                           \
                     mask = kcf_mask_from_word31(w31);                                                                  \
                     if (inl && (mask & 0x7FFEu)) pending = true;                                                       \
