@@ -201,7 +201,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=os.environ.get("KCF_BENCH_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-windows", type=int, default=0, help="windows in the CPU baseline sample (0 = auto, ~15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cli", action="store_true",
@@ -460,7 +460,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if scan else "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "kmers/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_step, "h2d_copy_alone_ms": h2d_floor_ms, "what": "per chromosome: kcf_ref_add_async (pinned FASTA bytes -> H2D -> 2-bit pack) + kcf_plan_create (window "
+                    "ms_per_step": e2e_step, "ms_each_step": [round(x, 3) for x in e2e_ms], "h2d_copy_alone_ms": h2d_floor_ms, "what": "per chromosome: kcf_ref_add_async (pinned FASTA bytes -> H2D -> 2-bit pack) + kcf_plan_create (window "
                                                      "H2D) + kcf_plan_run; then kcf_plan_fetch (result D2H) of every chromosome; database resident (loaded once: db_load_s)"},
             "gpu_launches": int(args.steps * plan.kernels_per_run),
             "roofline": roof, "clocks": clocks, "db_load_s": db_load_s,
