@@ -160,14 +160,13 @@ __device__ __forceinline__ uint32_t kcf_lookup(const uint8_t *__restrict__ table
     return kcf_lookup_at(table, stash, g, key, kcf_home_line(kcf_minimizer_of_key(key, g), g));
 }
 
-// Probe one table line for `key`: the S low key words sit in the line's first two 32-byte sectors (4 x 16-byte loads);
-// live low words of a line are distinct, so the low-word match is the only candidate and is confirmed on the high word.
-// The loads allocate in L1: the high word, the count, the filter and the mask of the same line are read right after.
+// Search the S low key words of a line (already in registers: a, b, c and the 13th in d0) for `key`; live low words of a line
+// are distinct, so the low-word match is the only candidate and is confirmed on the high word.  The line is in L1 by then:
+// high word and count depend on the slot only and are read together (one L1 round trip, not two).
 template <int S>
-__device__ __forceinline__ bool kcf_probe_line(const uint8_t *line, uint64_t key, uint32_t &count)
+__device__ __forceinline__ bool kcf_match_line(const uint4 a, const uint4 b, const uint4 c, const uint32_t d0, const uint8_t *line, uint64_t key,
+                                               uint32_t &count)
 {
-    const uint4 *q = reinterpret_cast<const uint4 *>(line);
-    const uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
     const uint32_t lo = (uint32_t)key;
     int idx = -1;
     if (a.x == lo) idx = 0;
@@ -182,9 +181,8 @@ __device__ __forceinline__ bool kcf_probe_line(const uint8_t *line, uint64_t key
     if (c.y == lo) idx = 9;
     if (S > 10 && c.z == lo) idx = 10;
     if (S > 11 && c.w == lo) idx = 11;
-    if (S > 12 && d.x == lo) idx = 12;
+    if (S > 12 && d0 == lo) idx = 12;
     if (idx < 0) return false;
-    // high word and count depend on the slot only: both loads go out together (one L1 round trip, not two)
     constexpr int CW = S == 13 ? 1 : (S == 12 ? 2 : 4);
     constexpr int COFF = S == 13 ? 112 : 8 * S;
     const uint8_t *cp = line + COFF + CW * idx;
@@ -195,3 +193,12 @@ __device__ __forceinline__ bool kcf_probe_line(const uint8_t *line, uint64_t key
     return true;
 }
 
+// Probe one table line for `key`: the S low key words sit in the line's first two 32-byte sectors (4 loads of up to 16 bytes).
+template <int S>
+__device__ __forceinline__ bool kcf_probe_line(const uint8_t *line, uint64_t key, uint32_t &count)
+{
+    const uint4 *q = reinterpret_cast<const uint4 *>(line);
+    const uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    const uint32_t d0 = S > 12 ? __ldg(reinterpret_cast<const uint32_t *>(line) + 12) : 0u;
+    return kcf_match_line<S>(a, b, c, d0, line, key, count);
+}
