@@ -164,7 +164,7 @@ def test_high_load_factor_uses_displacement_and_stash(ctx, sc_main):
     db.close()
 
 
-@pytest.mark.parametrize("m,lf", [(16, 0.5), (12, 0.3), (4, 0.5), (1, 0.9), (10, 0.9), (19, 0.3), (24, 0.6)])
+@pytest.mark.parametrize("m,lf", [(16, 0.5), (12, 0.3), (4, 0.5), (1, 0.9), (10, 0.9), (18, 0.3), (19, 0.3), (24, 0.6)])
 def test_minimizer_length_and_load_factor_never_change_results(ctx, sc_main, m, lf):
     """the home-line function (minimizer length) and the load factor are layout knobs only.  m = 4 / 1 pile thousands
     of keys onto few minimizers: displaced lines, continuation fetches and the stash all get exercised."""
@@ -184,6 +184,26 @@ def test_minimizer_length_and_load_factor_never_change_results(ctx, sc_main, m, 
     rc, want = _oracle_screen(sc, wins, segs)
     got = ctx.screen(db, wins, segs)
     assert_results_equal(got, want)
+    db.close()
+
+
+@pytest.mark.parametrize("k,m", [(21, 18), (21, 19), (21, 9), (21, 8), (13, 10), (16, 3)])
+def test_sliding_minimum_paths_at_their_boundaries(ctx, k, m):
+    """w = k - m + 1 = 4 and 13 bound the register sliding minimum of the screening kernel, 3 and 14 fall to the doubling path:
+    (21, 18) w = 4, (21, 19) w = 3, (21, 9) w = 13, (21, 8) w = 14, (13, 10) w = 4, (16, 3) w = 14; windows long enough for
+    several 512-position chunks, so the carried hashes between chunks are exercised too"""
+    sc = Scenario(seq_lens=(9_000, 700), k=k, P=5 if (k - 5) % 4 == 0 else (k % 4 if k % 4 else 4), L=5, n_bins=8, seed=100 + k + m, n_runs=4)
+    sc.add_to(ctx)
+    ctx.set_minimizer_length(m)
+    try:
+        db = KMC(ctx, pre=sc.kmc.pre, suf=sc.kmc.suf)
+    finally:
+        ctx.set_minimizer_length(0)
+    assert db.info.resident_kmers == sc.kmc.total
+    wins, segs, *_ = fixed_windows(sc.seq_lens, 3000, 1700, k)
+    rc, want = _oracle_screen(sc, wins, segs)
+    assert rc == 0
+    assert_results_equal(ctx.screen(db, wins, segs), want)
     db.close()
 
 
