@@ -32,6 +32,7 @@ def test_struct_sizes_match_header():
     assert _lib.RESULT_DTYPE.fields["kmer_count_sum"][1] == 32 and _lib.RESULT_DTYPE.fields["score"][1] == 40
     assert _lib.WINDOW_DTYPE.itemsize == 8 and _lib.SEGMENT_DTYPE.itemsize == 12
     assert C.sizeof(_lib.DbInfo) == 96
+    assert _lib.CELL_DTYPE.itemsize == 40 and _lib.CELL_DTYPE.fields["kmer_count"][1] == 24 and _lib.CELL_DTYPE.fields["score"][1] == 32  # kcf_cell_t
 
 
 def test_version_string():
