@@ -242,6 +242,8 @@ int kcf_cohort_fetch(kcf_ctx *ctx, kcf_cohort *c, uint32_t sample, kcf_cell_t *c
 /* Random 32-byte-sector gather bandwidth of this GPU (the random-access roofline of SURVEY §8(d)):
  * n_loads independent 32-B loads from uniformly random sector addresses of a buffer of n_bytes. */
 int kcf_measure_random_sector_gbps(kcf_ctx *ctx, uint64_t n_bytes, uint64_t n_loads, int repeats, double *gbps_out);
+/* Layout statistics: hist_out[n] = table lines (home + overflow) holding n keys, n = 0 .. 15. */
+int kcf_db_line_histogram(kcf_db *db, uint64_t hist_out[16]);
 /* Milliseconds of the screening kernel in the last kcf_plan_run when profiling is on. */
 int kcf_set_profiling(kcf_ctx *ctx, int on);
 int kcf_last_kernel_ms(kcf_ctx *ctx, float *screen_ms, float *finalize_ms);

@@ -77,6 +77,7 @@ SYMBOLS = {
     "kcf_cohort_find_ibs": (C.c_int, [_P, _P, _P, _P, C.c_uint64, C.c_int, C.c_int32, C.c_float]),
     "kcf_cohort_genotypes": (C.c_int, [_P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P]),
     "kcf_cohort_fetch": (C.c_int, [_P, _P, C.c_uint32, _P, _P, _P]),
+    "kcf_db_line_histogram": (C.c_int, [_P, _P]),
     "kcf_scan_owned": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_int32, _P, _P]),
     "kcf_scan_fold": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P, _P]),
     "kcf_measure_random_sector_gbps": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),

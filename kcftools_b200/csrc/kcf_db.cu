@@ -671,3 +671,36 @@ extern "C" int kcf_db_count(kcf_ctx *ctx, kcf_db *db, const char *kmers_ascii, u
     if (e != cudaSuccess) return kcf_fail(ctx, KCF_ERR_CUDA, "kcf_db_count: %s", cudaGetErrorString(e));
     return KCF_OK;
 }
+
+// ---- layout statistics (measurement helper): how many home / overflow lines hold 0, 1, ..., S keys --------------------
+__global__ void kcf_line_hist_kernel(const uint8_t *__restrict__ table, uint64_t n_lines, uint32_t S, unsigned long long *__restrict__ hist)
+{
+    __shared__ unsigned int sh[16];
+    if (threadIdx.x < 16) sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(table + i * KCF_LINE_BYTES);
+        uint32_t n = 0;
+        for (uint32_t s = 0; s < S; ++s) n += w[s] != KCF_EMPTY_LO;
+        atomicAdd(&sh[n], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 16 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+extern "C" int kcf_db_line_histogram(kcf_db *db, uint64_t hist_out[16])
+{
+    if (!db || !hist_out) return KCF_ERR_ARG;
+    kcf_ctx *ctx = db->ctx;
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned long long *d = nullptr;
+    KCF_CUDA(ctx, cudaMalloc(&d, 16 * 8));
+    cudaMemsetAsync(d, 0, 16 * 8, ctx->stream);
+    const uint64_t n = db->geom.n_local + db->geom.n_ov;
+    kcf_line_hist_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(db->table, n, db->geom.S, d);
+    cudaError_t e = cudaMemcpyAsync(hist_out, d, 16 * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return kcf_fail(ctx, KCF_ERR_CUDA, "kcf_db_line_histogram: %s", cudaGetErrorString(e));
+    return KCF_OK;
+}
