@@ -74,9 +74,9 @@ extern "C" int kcf_init(int device, kcf_ctx **out)
     return KCF_OK;
 }
 
-// device memory of cleared sequences is kept and handed out again: a host that re-screens (or a cohort run that swaps
+// device memory of cleared sequences and destroyed plans is kept and handed out again: a host that re-screens (or a cohort run that swaps
 // references) does not pay cudaMalloc / cudaFree per sequence
-static void *kcf_pool_get(kcf_ctx *ctx, size_t bytes)
+void *kcf_pool_get(kcf_ctx *ctx, size_t bytes)
 {
     int best = -1;
     for (size_t i = 0; i < ctx->pool.size(); ++i)
@@ -96,6 +96,11 @@ static void *kcf_pool_get(kcf_ctx *ctx, size_t bytes)
         if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
     }
     return p;
+}
+
+void kcf_pool_put(kcf_ctx *ctx, void *p, size_t bytes)
+{
+    if (p) ctx->pool.push_back({p, bytes});
 }
 
 extern "C" int kcf_ref_clear(kcf_ctx *ctx)

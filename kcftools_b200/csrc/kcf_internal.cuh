@@ -176,7 +176,8 @@ struct kcf_plan {
     kcf_ctx *ctx = nullptr;
     int32_t k = 0;
     uint64_t n_wins = 0, n_segs = 0, n_tiles = 0, n_positions = 0;
-    void *d_block = nullptr;          // the one device allocation holding the arrays below
+    void *d_block = nullptr;          // the one device block (from the context's pool) holding the arrays below
+    size_t d_block_bytes = 0;
     kcf_window_t *d_wins = nullptr;
     kcf_segment_t *d_segs = nullptr;
     uint32_t *d_seg_off = nullptr;    // offset of each segment inside its window
@@ -207,6 +208,10 @@ struct kcf_plan {
 enum { FLAG_LUT_BAD = 0, FLAG_ORDER_BAD = 1, FLAG_SCORE_USED = 2, FLAG_COUNT = 8 };
 
 int kcf_fail(kcf_ctx *ctx, int code, const char *fmt, ...);
+// device blocks are recycled through the context (cudaMalloc / cudaFree are slow, far slower once a communication library
+// has enabled peer access, and cudaFree synchronises the device): sequences and plans take their memory from here
+void *kcf_pool_get(kcf_ctx *ctx, size_t bytes);
+void kcf_pool_put(kcf_ctx *ctx, void *p, size_t bytes);
 int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t min_count, uint64_t tile_begin, uint64_t tile_end,
                       int32_t *d_counts, bool extract, uint32_t *d_owned_hit, unsigned long long *d_owned_sum);
 #define KCF_CUDA(ctx, call)                                                                        \

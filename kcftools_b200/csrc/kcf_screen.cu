@@ -705,7 +705,7 @@ extern "C" void kcf_plan_destroy(kcf_plan *plan)
     if (!plan) return;
     cudaSetDevice(plan->ctx->device);
     cudaStreamSynchronize(plan->ctx->stream);
-    cudaFree(plan->d_block); // d_wins .. d_out live in it
+    kcf_pool_put(plan->ctx, plan->d_block, plan->d_block_bytes); // d_wins .. d_out live in it; the stream is idle (synchronised above)
     cudaFree(plan->x_keys);
     cudaFree(plan->x_homes);
     cudaFree(plan->x_okw);
@@ -779,9 +779,11 @@ extern "C" int kcf_plan_create(kcf_ctx *ctx, int32_t kmer_length, const kcf_wind
         const uint64_t b_wins = up(nw * sizeof(kcf_window_t)), b_segs = up(ns * sizeof(kcf_segment_t)), b_off = up(ns * 4), b_len = up(nw * 4),
                        b_tf = up((n_wins + 1) * 8), b_ts = up(std::max<uint64_t>(tiles, 1) * sizeof(KcfGap) + 8), // +8: the tile counter lives at the end
                        b_out = up(nw * sizeof(kcf_result_t));
-        uint8_t *base = nullptr;
-        PL_CUDA(cudaMalloc(&base, b_wins + b_segs + b_off + b_len + b_tf + b_ts + b_out));
+        const size_t total = b_wins + b_segs + b_off + b_len + b_tf + b_ts + b_out;
+        uint8_t *base = (uint8_t *)kcf_pool_get(ctx, total);
+        if (!base && rc == KCF_OK) rc = kcf_fail(ctx, KCF_ERR_NOMEM, "device memory for a plan of %llu windows", (unsigned long long)n_wins);
         plan->d_block = base;
+        plan->d_block_bytes = total;
         if (base) {
             plan->d_wins = reinterpret_cast<kcf_window_t *>(base);
             base += b_wins;
