@@ -120,7 +120,7 @@ int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_len, const ui
                     int placement, kcf_db **out);
 int kcf_db_info(kcf_db *db, kcf_db_info_t *out);
 void kcf_db_close(kcf_db *db);
-/* Load-factor target for subsequently opened databases (0 < lf <= 0.9; 0 = automatic, the default: 0.2, denser when
+/* Load-factor target for subsequently opened databases (0 < lf <= 0.9; 0 = automatic, the default: 0.15, denser when
  * the table would take more than 40 % of the device memory). */
 int kcf_set_load_factor(kcf_ctx *ctx, double lf);
 /* Minimizer length of the home-line function for subsequently opened databases (1..24; 0 = chosen from the

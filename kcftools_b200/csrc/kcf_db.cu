@@ -415,14 +415,17 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
         g.mmask = (1ULL << (2 * m)) - 1ULL;
     }
     double lf = ctx->load_factor;
-    if (lf <= 0.0) { // automatic: sparse tables are faster (fewer keys outside their home line: 60.7 / 64.8 / 68.6 G k-mers/s at
-                     // 0.4 / 0.3 / 0.2 on C2); start at 0.2 and give memory back when it is scarce
+    if (lf <= 0.0) { // automatic: sparse tables are faster (fewer keys outside their home line: 72.8 / 74.9 / 76.9 / 78.9 / 79.7 G
+                     // k-mers/s at 0.3 / 0.25 / 0.2 / 0.15 / 0.125 on C2); start at 0.15 and give memory back when it is scarce
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         const double share = part_world > 1 ? 1.0 / part_world : 1.0;
-        lf = 0.2;
+        const double steps[] = {0.15, 0.2, 0.3, 0.4, 0.5, 0.6};
         // against the device's TOTAL memory: every rank of a partitioned database must derive the same geometry
-        while (lf < 0.6 && (double)N * share / (g.S * lf) * KCF_LINE_BYTES > 0.4 * (double)total_b) lf += 0.1;
+        for (double cand : steps) {
+            lf = cand;
+            if ((double)N * share / (g.S * lf) * KCF_LINE_BYTES <= 0.4 * (double)total_b) break;
+        }
     }
     uint64_t nb = cs == 0 ? 1 : (uint64_t)((double)N / (g.S * lf)) + 1;
     nb = std::max<uint64_t>(nb, cs == 0 ? 1 : 64);

@@ -152,7 +152,7 @@ struct kcf_ctx {
         size_t bytes;
     };
     std::vector<PoolBlock> pool; // device blocks of cleared sequences, reused by later kcf_ref_add calls
-    double load_factor = 0.0;    // 0 = automatic: 0.2, denser when the table would crowd the device memory
+    double load_factor = 0.0;    // 0 = automatic: 0.15, denser when the table would crowd the device memory
     int minimizer_len = 0;       // 0 = chosen from the database size
     int part_rank = 0, part_world = 1; // slice kept by databases opened with placement 1 (kcf_set_partition)
     int sm_count = 148;
