@@ -375,3 +375,36 @@ def test_large_reference_windows_reproduce_the_small_run():
     out = json.loads(p.stdout.strip().split("\n")[-1])
     assert out["ok"] and out["core_windows_identical"] and out["core_windows_compared"] == 14 * 150 and out["tail_totals_exact"]
     assert out["windows"] == 14 * 241 and out["tail_observed_kmers"] < 10
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+def test_random_window_layouts(ctx, sc_main, seed):
+    """seeded fuzz over window shapes: 1-9 segments per window, segment lengths from 1 base to several tiles, segments that
+    overlap, repeat, abut, sit at sequence ends, windows shorter than k, junctions every few bases (k-mers spanning several
+    segments), all mixed in one call; min_count and weights vary with the seed"""
+    rng = np.random.default_rng(seed)
+    sc = sc_main
+    lists = []
+    for _ in range(160):
+        nseg = int(rng.integers(1, 10))
+        segs = []
+        for _ in range(nseg):
+            sid = int(rng.integers(0, 3))
+            n = sc.seq_lens[sid]
+            kind = rng.random()
+            length = int(rng.integers(1, 12)) if kind < 0.25 else int(rng.integers(12, 400)) if kind < 0.7 else int(rng.integers(400, 9000))
+            length = min(length, n)
+            start = int(rng.integers(0, n - length + 1)) if rng.random() < 0.9 else (0 if rng.random() < 0.5 else n - length)
+            segs.append((sid, start, length))
+        lists.append(segs)
+    wins, segs = windows_from_lists(lists)
+    mc = int(rng.integers(1, 4))
+    wts = [(0.3, 0.3, 0.4), (0.5, 0.25, 0.25), (0.0, 0.0, 1.0), (0.125, 0.125, 0.75)][seed % 4]
+    rc, want = _oracle_screen(sc, wins, segs, min_count=mc, w=wts)
+    assert rc == 0
+    db = KMC(ctx, pre=sc.kmc.pre, suf=sc.kmc.suf)
+    sc.add_to(ctx)
+    got = ctx.screen(db, wins, segs, min_count=mc, weights=wts)
+    assert_results_equal(got, want)
+    assert (want["total_kmers"] == 0).any() and (want["obs"] > 0).any()  # the mix contains empty and observed windows
+    db.close()
