@@ -399,13 +399,13 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     g.both_strands = (uint32_t)info.both_strands;
     {
         // minimizer length: long enough that one m-mer value rarely names more than one locus of the sampled genome
-        // (4^m >= 4 N) and that a run of k-mers sharing it fits one line (w = k-m+1 <= S: a group larger than a line always
+        // (4^m >= 4 N) and that a run of k-mers sharing it fits one line (w = k-m+1 < S: a group larger than a line always
         // overflows), short enough that consecutive k-mers share it at all
         int m = ctx->minimizer_len;
         if (m <= 0) {
             m = 8;
             while (m < 16 && (1ULL << (2 * m)) < 4 * N) ++m;
-            m = std::max(m, k - (int)g.S + 2);
+            m = std::max(m, k - (int)g.S + 3); // w = S - 2: a run leaves two slots of its line free (C2: 78.9 / 79.9 / 79.9 G k-mers/s at w = 12 / 11 / 10)
         }
         m = std::min(std::min(m, 24), k);
         m = std::max(m, 1);
