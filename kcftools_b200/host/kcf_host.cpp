@@ -1234,6 +1234,7 @@ void printCommandLine(const GetVariantsOptions &o) // HelperFunctions.java:269-2
 int cliMain(int argc, const char *const *argv)
 {
     if (argc < 2 || std::string(argv[1]) == "-h" || std::string(argv[1]) == "--help") {
+        std::fputs("Usage: kcftools [-h] [COMMAND]\nCommands (this build): getVariations, cohort, findIBS, kcf2gt (each with --help)\n\n", argc < 2 ? stderr : stdout);
         std::fputs(USAGE, argc < 2 ? stderr : stdout);
         return argc < 2 ? 2 : 0;
     }
@@ -1303,7 +1304,8 @@ int cliMain(int argc, const char *const *argv)
         }
         throw UsageError("Unmatched argument at index 0: '" + cmd + "'");
     } catch (const UsageError &e) {
-        std::fprintf(stderr, "%s\n%s", e.what(), USAGE);
+        const bool own = cmd == "cohort" || cmd == "findIBS" || cmd == "kcf2gt"; // their message carries their own usage text
+        std::fprintf(stderr, "%s\n%s", e.what(), own ? "" : USAGE);
         return 2;
     } catch (const FatalError &) {
         return 1;

@@ -301,9 +301,16 @@ struct Opt {
     bool required;
 };
 
-std::map<std::string, std::string> parseOpts(int argc, const char *const *argv, const std::vector<Opt> &specs)
+struct HelpShown {};
+
+std::map<std::string, std::string> parseOpts(int argc, const char *const *argv, const std::vector<Opt> &specs, const char *usage)
 {
     std::map<std::string, std::string> seen;
+    for (int i = 2; i < argc; ++i)
+        if (std::string(argv[i]) == "-h" || std::string(argv[i]) == "--help") {
+            std::fputs(usage, stdout);
+            throw HelpShown();
+        }
     for (int i = 2; i < argc; ++i) {
         std::string a = argv[i], val;
         bool hasVal = false;
@@ -316,7 +323,7 @@ std::map<std::string, std::string> parseOpts(int argc, const char *const *argv, 
         const Opt *sp = nullptr;
         for (const Opt &s : specs)
             if ((s.shortName && a == s.shortName) || a == s.longName) sp = &s;
-        if (!sp) throw UsageError("Unknown option: '" + std::string(argv[i]) + "'");
+        if (!sp) throw UsageError("Unknown option: '" + std::string(argv[i]) + "'\n" + usage);
         if (sp->kind == 3) {
             seen[sp->longName] = "true";
             continue;
@@ -339,9 +346,42 @@ std::map<std::string, std::string> parseOpts(int argc, const char *const *argv, 
     std::string missing;
     for (const Opt &s : specs)
         if (s.required && !seen.count(s.longName)) missing += std::string(missing.empty() ? "" : ", ") + "'" + s.longName + "'";
-    if (!missing.empty()) throw UsageError("Missing required options: " + missing);
+    if (!missing.empty()) throw UsageError("Missing required options: " + missing + "\n" + usage);
     return seen;
 }
+
+const char *const COHORT_USAGE =
+    "Usage: kcftools cohort [-i=<inFiles>[,<inFiles>...]]... [-l=<listFile>] -o=<outFile> [--device=<cudaOrdinal>]\n"
+    "Create a cohort of samples kcf files\n"
+    "  -i, --input=<inFiles>[,<inFiles>...]   List of samples kcf files\n"
+    "  -l, --list=<listFile>     File containing list of samples kcf files\n"
+    "  -o, --output=<outFile>    Output file name\n"
+    "      --device=<cudaOrdinal> CUDA device (this build)\n";
+const char *const FINDIBS_USAGE =
+    "Usage: kcftools findIBS [--bed] [--summary] [--var] -i=<inFile> [--min=<minConsecutive>] -o=<outFile>\n"
+    "                        [--score=<scoreCutOff>] [--device=<cudaOrdinal>]\n"
+    "Find IBS windows in a KCF file\n"
+    "      --bed                 Write bed file [default: false]\n"
+    "  -i, --input=<inFile>      Input KCF file name\n"
+    "      --min=<minConsecutive> Minimum number of consecutive windows [default: 4]\n"
+    "  -o, --output=<outFile>    Output KCF file name\n"
+    "      --score=<scoreCutOff> Score cut-off [default: 95.00]\n"
+    "      --summary             Write summary tsv file [default: false]\n"
+    "      --var                 Detect Variable Regions instead of IBS [default: false]\n"
+    "      --device=<cudaOrdinal> CUDA device (this build)\n";
+const char *const KCF2GT_USAGE =
+    "Usage: kcftools kcf2gt [--chrs=<chrsFile>] -i=<inFile> [--maf=<minMAF>] [--max-missing=<maxMissing>] -o=<outFile>\n"
+    "                       [--score_a=<scoreA>] [--score_b=<scoreB>] [--score_n=<scoreN>] [--device=<cudaOrdinal>]\n"
+    "Convert KCF to Genotype Table\n"
+    "      --chrs=<chrsFile>     List file with chromosomes to include\n"
+    "  -i, --input=<inFile>      Input KCF file\n"
+    "      --maf=<minMAF>        minimum allele frequency to consider a window valid\n"
+    "      --max-missing=<maxMissing> maximum proportion of missing data to consider a window valid\n"
+    "  -o, --output=<outFile>    Output file\n"
+    "      --score_a=<scoreA>    Lower score cut-off for reference allele (default = 95.0)\n"
+    "      --score_b=<scoreB>    Lower score cut-off for alternate allele (default = 60.0)\n"
+    "      --score_n=<scoreN>    Score value for missing data (default = 30.0)\n"
+    "      --device=<cudaOrdinal> CUDA device (this build)\n";
 
 void writeText(const std::string &path, const std::string &text)
 {
@@ -354,11 +394,21 @@ void writeText(const std::string &path, const std::string &text)
 } // namespace
 
 // ================================================================================================ cohort
+static int cohortMainImpl(int argc, const char *const *argv, const std::string &cmdline);
 int cohortMain(int argc, const char *const *argv, const std::string &cmdline)
+{
+    try {
+        return cohortMainImpl(argc, argv, cmdline);
+    } catch (const HelpShown &) {
+        return 0;
+    }
+}
+
+static int cohortMainImpl(int argc, const char *const *argv, const std::string &cmdline)
 {
     static const char *const CLS = "Cohort";
     const std::vector<Opt> specs = {{"-o", "--output", 0, true}, {"-i", "--input", 0, false}, {"-l", "--list", 0, false}, {nullptr, "--device", 1, false}};
-    auto o = parseOpts(argc, argv, specs);
+    auto o = parseOpts(argc, argv, specs, COHORT_USAGE);
     std::vector<std::string> inFiles;
     if (!o.count("--input") && !o.count("--list")) Logger::error(CLS, "No input files provided");
     if (o.count("--input")) inFiles = java_split(o["--input"], ','); // picocli split = ","
@@ -448,12 +498,22 @@ int cohortMain(int argc, const char *const *argv, const std::string &cmdline)
 }
 
 // ================================================================================================ findIBS
+static int findIBSMainImpl(int argc, const char *const *argv, const std::string &cmdline);
 int findIBSMain(int argc, const char *const *argv, const std::string &cmdline)
+{
+    try {
+        return findIBSMainImpl(argc, argv, cmdline);
+    } catch (const HelpShown &) {
+        return 0;
+    }
+}
+
+static int findIBSMainImpl(int argc, const char *const *argv, const std::string &cmdline)
 {
     static const char *const CLS = "FindIBS";
     const std::vector<Opt> specs = {{"-i", "--input", 0, true}, {"-o", "--output", 0, true}, {nullptr, "--var", 3, false},   {nullptr, "--min", 1, false},
                                     {nullptr, "--score", 2, false}, {nullptr, "--summary", 3, false}, {nullptr, "--bed", 3, false}, {nullptr, "--device", 1, false}};
-    auto o = parseOpts(argc, argv, specs);
+    auto o = parseOpts(argc, argv, specs, FINDIBS_USAGE);
     std::string outFile = o["--output"];
     const bool detectVar = o.count("--var") != 0, writeSummary = o.count("--summary") != 0, writeBed = o.count("--bed") != 0;
     int minConsecutive = o.count("--min") ? std::atoi(o["--min"].c_str()) : 4;
@@ -567,14 +627,24 @@ int findIBSMain(int argc, const char *const *argv, const std::string &cmdline)
 }
 
 // ================================================================================================ kcf2gt
+static int kcf2gtMainImpl(int argc, const char *const *argv, const std::string &cmdline);
 int kcf2gtMain(int argc, const char *const *argv, const std::string &cmdline)
+{
+    try {
+        return kcf2gtMainImpl(argc, argv, cmdline);
+    } catch (const HelpShown &) {
+        return 0;
+    }
+}
+
+static int kcf2gtMainImpl(int argc, const char *const *argv, const std::string &cmdline)
 {
     (void)cmdline;
     static const char *const CLS = "KCFToGenotypeTable";
     const std::vector<Opt> specs = {{"-i", "--input", 0, true},      {"-o", "--output", 0, true},   {nullptr, "--score_a", 2, false},     {nullptr, "--score_b", 2, false},
                                     {nullptr, "--score_n", 2, false}, {nullptr, "--maf", 2, false}, {nullptr, "--max-missing", 2, false}, {nullptr, "--chrs", 0, false},
                                     {nullptr, "--device", 1, false}};
-    auto o = parseOpts(argc, argv, specs);
+    auto o = parseOpts(argc, argv, specs, KCF2GT_USAGE);
     auto D = [&](const char *k, double dflt) { return o.count(k) ? std::strtod(o[k].c_str(), nullptr) : dflt; };
     double scoreA = D("--score_a", 95.0), scoreB = D("--score_b", 60.0), scoreN = D("--score_n", 30.0);
     const double minMAF = D("--maf", 0.0), maxMissing = D("--max-missing", 1.0);

@@ -212,6 +212,16 @@ def test_cohort_restatement(cohort_files):
         pykcf.cohort([texts[0], texts[0]], ["a", "b"], "c", "d")
 
 
+def test_cli_usage_of_the_new_commands(cli):
+    for cmd, first in (("cohort", "Usage: kcftools cohort"), ("findIBS", "Usage: kcftools findIBS"), ("kcf2gt", "Usage: kcftools kcf2gt")):
+        p = run(cli, cmd, "--help")
+        assert p.stdout.startswith(first)
+        p = run(cli, cmd, "--nonsense", check=False)
+        assert p.returncode == 2 and "Unknown option: '--nonsense'" in p.stderr and first in p.stderr
+    p = run(cli, "kcf2gt", "-i", "x.kcf", check=False)
+    assert p.returncode == 2 and "Missing required options: '--output'" in p.stderr
+
+
 def test_cli_header_hook(cli, cohort_files):
     """the C++ KCF header parser / writer on CPU (no device needed for this hook)"""
     out = run(cli, "_kcfheader", cohort_files["paths"][0]).stdout
