@@ -24,7 +24,7 @@
  * O(k) loop, its signature is the minimum of k-L+1 table lookups, and the
  * count comes from a per-(bin,prefix) binary search over the on-disk records
  * with an unsigned byte-wise comparison.  Only the Java object allocations are
- * gone.  Limited to k <= 32 (one 64-bit word), like the CUDA path.
+ * gone.  k up to 256 (long[] words like Kmer.java); the CUDA path covers k <= 32.
  *
  * Build: see oracle/Makefile  (gcc -O2 -ffp-contract=off -shared -fPIC -pthread)
  */
@@ -88,8 +88,11 @@ int orc_norm_table(int sign_len, int32_t *out)
 }
 
 /* ------------------------------------------------------------------ */
-/* D/Kmer.java (single-word case, k <= 32)                            */
+/* D/Kmer.java (long[] words, 32 bases per word, k <= 256)            */
 /* ------------------------------------------------------------------ */
+#define ORC_MAX_K 256
+#define ORC_KWORDS (ORC_MAX_K / 32)
+typedef struct kword { uint64_t w[ORC_KWORDS]; } kword; /* Kmer.kmerLong; words past ceil(2k/64) stay 0 */
 
 /* D/Kmer.java:286-294 baseToBits; input already upper-cased ACGT */
 static inline uint64_t base_to_bits(char b)
@@ -102,73 +105,72 @@ static inline uint64_t base_to_bits(char b)
     }
 }
 
-/* D/Kmer.java:232-252 kmerToLong: base i at bits 62-2i (MSB first, left aligned) */
-static uint64_t kmer_to_long(const char *kmer, int k)
+/* base i of a packed k-mer: word i/32, bits 62-2(i%32) (bit offsets are always even, so the reference's
+ * "split between two longs" branches, D/Kmer.java:216-220, 245-248, 315-319, never run) */
+static inline uint32_t kword_base(const kword *x, int i) { return (uint32_t)((x->w[i >> 5] >> (62 - 2 * (i & 31))) & 3u); }
+
+/* D/Kmer.java:232-252 kmerToLong: base i at bits 62-2(i%32) of word i/32 (MSB first, left aligned) */
+static kword kmer_to_long(const char *kmer, int k)
 {
-    uint64_t r = 0;
-    for (int i = 0; i < k; i++) r |= base_to_bits(kmer[i]) << (62 - 2 * i);
+    kword r;
+    memset(&r, 0, sizeof r);
+    for (int i = 0; i < k; i++) r.w[i >> 5] |= base_to_bits(kmer[i]) << (62 - 2 * (i & 31));
     return r;
 }
 
 /* D/Kmer.java:300-338 getReverseComplement */
-static uint64_t kmer_revcomp(uint64_t w, int k)
+static kword kmer_revcomp(const kword *x, int k)
 {
-    uint64_t rev = 0;
+    kword rev;
+    memset(&rev, 0, sizeof rev);
     for (int i = 0; i < k; i++) {
-        uint64_t bits = (w >> (62 - 2 * i)) & 3u;
-        uint64_t comp = (~bits) & 3u;
-        int rev_index = (k - i - 1) * 2;
-        rev |= comp << (62 - rev_index);
+        uint64_t comp = (~(uint64_t)kword_base(x, i)) & 3u;
+        int j = k - i - 1;
+        rev.w[j >> 5] |= comp << (62 - 2 * (j & 31));
     }
     return rev;
 }
 
-/* D/Kmer.java:72-79 getCanonical + :406-414 compareLongArrays (unsigned; tie keeps forward) */
-static uint64_t kmer_canonical(uint64_t fwd, int k, int both_strands)
+/* D/Kmer.java:72-79 getCanonical + :406-414 compareLongArrays (word by word, unsigned; tie keeps forward) */
+static kword kmer_canonical(kword fwd, int k, int both_strands)
 {
     if (both_strands) {
-        uint64_t rc = kmer_revcomp(fwd, k);
-        if (fwd > rc) return rc;
+        kword rc = kmer_revcomp(&fwd, k);
+        int nw = (2 * k + 63) / 64;
+        for (int i = 0; i < nw; i++) {
+            if (fwd.w[i] != rc.w[i]) return fwd.w[i] > rc.w[i] ? rc : fwd;
+        }
     }
     return fwd;
 }
 
-/* D/Kmer.java:208-226 extractIntFromBits (offset is always even and <= 62 for one word) */
-static uint32_t extract_int_from_bits(uint64_t w, int start_base, int length_bases)
+/* D/Kmer.java:208-226 extractIntFromBits */
+static uint32_t extract_int_from_bits(const kword *x, int start_base, int length_bases)
 {
     uint32_t result = 0;
-    for (int i = 0; i < length_bases; i++) {
-        int bit_index = (start_base + i) * 2;
-        uint32_t base_bits = (uint32_t)((w >> (62 - bit_index)) & 3u);
-        result = (result << 2) | base_bits;
-    }
+    for (int i = 0; i < length_bases; i++) result = (result << 2) | kword_base(x, start_base + i);
     return result;
 }
 
 /* D/Kmer.java:105-118 getSignature */
-static int32_t kmer_signature(uint64_t w, int k, int sign_len, const int32_t *norm)
+static int32_t kmer_signature(const kword *x, int k, int sign_len, const int32_t *norm)
 {
-    uint32_t cur = extract_int_from_bits(w, 0, sign_len);
+    uint32_t cur = extract_int_from_bits(x, 0, sign_len);
     int32_t min_sig = norm[cur];
     uint32_t mask = (1u << (2 * sign_len)) - 1u;
     for (int i = 1; i <= k - sign_len; i++) {
-        cur = ((cur << 2) & mask) | extract_int_from_bits(w, i + sign_len - 1, 1);
+        cur = ((cur << 2) & mask) | extract_int_from_bits(x, i + sign_len - 1, 1);
         if (norm[cur] < min_sig) min_sig = norm[cur];
     }
     return min_sig;
 }
 
 /* D/Kmer.java:143-170 extractSuffix: bases P..k-1 packed 4 per byte, first base in bits 7..6 */
-static void kmer_extract_suffix(uint64_t w, int k, int prefix_len, uint8_t *suffix /* (k-P+3)/4 bytes */)
+static void kmer_extract_suffix(const kword *x, int k, int prefix_len, uint8_t *suffix /* (k-P+3)/4 bytes */)
 {
     int suffix_len = k - prefix_len;
     memset(suffix, 0, (size_t)(suffix_len + 3) / 4);
-    int bit_start = 2 * prefix_len;
-    for (int i = 0; i < suffix_len; ++i) {
-        int bit_index = bit_start + i * 2;
-        uint32_t base_bits = (uint32_t)((w >> (62 - bit_index)) & 3u);
-        suffix[i / 4] |= (uint8_t)(base_bits << ((3 - i % 4) * 2));
-    }
+    for (int i = 0; i < suffix_len; ++i) suffix[i / 4] |= (uint8_t)(kword_base(x, prefix_len + i) << ((3 - i % 4) * 2));
 }
 
 /* ------------------------------------------------------------------ */
@@ -235,8 +237,8 @@ int orc_kmc_open_mem(const uint8_t *pre, int64_t pre_len, const uint8_t *suf, in
     db->both_strands = (h[36] == 0);                                              /* :133 */
     db->version = (int32_t)rd_u32(h + 36 + 1 + 3 + 24);                          /* :134-138 */
     if (db->version != 0x200) { free(db); return ORC_ERR_FATAL; }                /* :139-141 */
-    if (db->kmer_length < 1 || db->kmer_length > 32 || db->signature_length < 3 || db->signature_length > 13 ||
-        db->lut_prefix_length < 0 || db->lut_prefix_length > db->kmer_length || db->counter_size < 0 ||
+    if (db->kmer_length < 1 || db->kmer_length > ORC_MAX_K || db->signature_length < 3 || db->signature_length > 13 ||
+        db->lut_prefix_length < 0 || db->lut_prefix_length > db->kmer_length || db->lut_prefix_length > 15 || db->counter_size < 0 ||
         db->counter_size > 4 || (db->suffix_length % 4) != 0) {
         free(db);
         return ORC_ERR_ARG; /* outside what this restatement (and the CUDA path) covers */
@@ -337,12 +339,12 @@ static int compare_byte_array(const uint8_t *a, const uint8_t *b, int n)
 /* D/KMC.java:292-326 getCount, :366-401 getEntry/getSuffixFromEntry/getCountFromEntry.
  * `w` is the already-canonicalised k-mer word (P/GetVariants.java:222-223).
  * Returns the Java int count (may be negative for 4-byte counters >= 2^31). */
-static int32_t kmc_get_count_word(const orc_kmc *db, uint64_t w)
+static int32_t kmc_get_count_word(const orc_kmc *db, const kword *w)
 {
     int k = db->kmer_length, P = db->lut_prefix_length;
     int32_t signature = kmer_signature(w, k, db->signature_length, db->norm);
     int32_t prefix = (int32_t)extract_int_from_bits(w, 0, P);                    /* D/Kmer.java:123-128 */
-    uint8_t suffix[16];
+    uint8_t suffix[ORC_MAX_K / 4 + 1];
     kmer_extract_suffix(w, k, P, suffix);
     int nsb = db->suffix_length / 4;
     int64_t signature_index = (int64_t)db->signature_map[signature] * db->lut_prefix_array_size; /* :300 */
@@ -369,16 +371,16 @@ static int32_t kmc_get_count_word(const orc_kmc *db, uint64_t w)
 /* count of one k-mer given as ASCII (upper-case ACGT), canonicalised per the DB's flag */
 int32_t orc_kmc_count(const orc_kmc *db, const char *kmer_ascii)
 {
-    uint64_t w = kmer_to_long(kmer_ascii, db->kmer_length);
+    kword w = kmer_to_long(kmer_ascii, db->kmer_length);
     w = kmer_canonical(w, db->kmer_length, db->both_strands);
-    return kmc_get_count_word(db, w);
+    return kmc_get_count_word(db, &w);
 }
 
 int32_t orc_kmc_signature(const orc_kmc *db, const char *kmer_ascii)
 {
-    uint64_t w = kmer_to_long(kmer_ascii, db->kmer_length);
+    kword w = kmer_to_long(kmer_ascii, db->kmer_length);
     w = kmer_canonical(w, db->kmer_length, db->both_strands);
-    return kmer_signature(w, db->kmer_length, db->signature_length, db->norm);
+    return kmer_signature(&w, db->kmer_length, db->signature_length, db->norm);
 }
 
 /* ------------------------------------------------------------------ */
@@ -512,7 +514,7 @@ int orc_process_window(const orc_kmc *db, const char *seq, int32_t n, int32_t mi
     int32_t total = 0, obs = 0, variation = 0, inner = 0, gap = 0, left = 0, right = 0;
     int is_tail = 1;
     int64_t kmer_count_sum = 0;
-    char chars[64];
+    char chars[ORC_MAX_K + 8];
     int have_kmer = 0;
     int32_t valid_start = 0;
     memset(chars, 0, sizeof chars);
@@ -533,9 +535,9 @@ int orc_process_window(const orc_kmc *db, const char *seq, int32_t n, int32_t mi
             chars[k - 1] = base;
         }
         if (!have_kmer) continue;
-        uint64_t w = kmer_to_long(chars, k);                       /* new Kmer(char[]) per position, D/Fasta.java:108,118 */
+        kword w = kmer_to_long(chars, k);                          /* new Kmer(char[]) per position, D/Fasta.java:108,118 */
         w = kmer_canonical(w, k, db->both_strands);                /* new Kmer(k, kmc.isBothStrands()), P/GetVariants.java:222 */
-        int32_t cnt = kmc_get_count_word(db, w);                   /* :223 */
+        int32_t cnt = kmc_get_count_word(db, &w);                  /* :223 */
         if (counts_out) counts_out[total] = cnt;
         total++;                                                   /* :221 */
         if (cnt >= min_kmer_count) {                               /* :224 */

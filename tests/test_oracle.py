@@ -144,3 +144,42 @@ def test_screen_threads_equal_single():
     rc1, a = db.screen(sc.seqs(), wins, segs, threads=1)
     rc2, b = db.screen(sc.seqs(), wins, segs, threads=4)
     assert rc1 == 0 and rc2 == 0 and (a == b).all() and a["total_kmers"].sum() > 0
+
+
+@pytest.mark.parametrize("k,P,L,cs,both", [(33, 5, 9, 1, True), (41, 5, 7, 2, True), (64, 8, 9, 1, True), (65, 5, 9, 1, False), (100, 8, 11, 3, True),
+                                            (31, 7, 9, 1, True)])
+def test_multiword_kmers_c_oracle_vs_python(k, P, L, cs, both):
+    """groundwork for SURVEY §8 row f4 (k > 32; the CUDA path stops at 32): the C restatement follows Kmer.java's long[]
+    words (32 bases per word, word-by-word unsigned canonical compare) and agrees with the string-based Python restatement
+    on databases written by the any-k generator — canonical orientation across word boundaries, signature, prefix / suffix
+    bytes, binary search, gap statistics and score."""
+    rng = np.random.default_rng(1000 + k)
+    ref = "".join("ACGT"[c] for c in rng.integers(0, 4, 2600))
+    ref = ref[:700] + "NNNN" + ref[700:1500].lower() + "R" + ref[1500:]
+    # the sample: the reference with SNPs, a deletion, and a stretch in the opposite orientation
+    qry = list(ref.upper().replace("N", "A").replace("R", "G"))
+    for pos in rng.integers(0, len(qry), 25):
+        qry[pos] = "ACGT"[(("ACGT".index(qry[pos])) + 1 + int(rng.integers(0, 3))) % 4]
+    qry = "".join(qry[:1800] + qry[1900:])
+    qry = qry[:400] + pyoracle.revcomp(qry[400:900]) + qry[900:]
+    img = synth.kmc_image_from_strings([qry], k=k, P=P, L=L, n_bins=8, counter_size=cs, both_strands=both, seed=k)
+    db = ob.OracleKMC(img.pre, img.suf)
+    py = pyoracle.PyKMC(img.pre.tobytes(), img.suf.tobytes())
+    assert db.info.kmer_length == k == py.k and db.info.total_kmers == img.total == py.total
+    rc, res, counts = db.process_window(ref.encode(), min_count=1, want_counts=True)
+    assert rc == 0
+    want = pyoracle.process_window(py, ref)
+    for f in ("total_kmers", "eff_len", "obs", "variations", "inner", "left", "right", "kmer_count_sum"):
+        assert getattr(res, f) == want[f], f
+    assert res.score == want["score"]
+    kms = pyoracle.kmers_list(ref, k)
+    assert list(counts[:len(kms)]) == [py.get_count(py.canonical(s)) for s in kms]
+    assert 0 < res.obs < res.total_kmers
+    if both:  # the inverted stretch is found through the reverse-complement orientation
+        inv = pyoracle.kmers_list(ref[450:850], k)
+        assert sum(py.get_count(py.canonical(s)) > 0 for s in inv) > len(inv) // 2
+    # every record of the database is found under its own text with its own count
+    some = list(pyoracle.kmers_list(qry, k))[::37]
+    for s in some:
+        c = db.count(py.canonical(s))
+        assert c == py.get_count(py.canonical(s)) and (c > 0 or cs == 0)

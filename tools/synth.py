@@ -433,3 +433,64 @@ def synthetic_gtf(chroms: list[tuple[str, int]], genes_per_chrom: int, seed: int
                     lines.append(f'{chrom}\tsynth\texon\t{s}\t{e}\t.\t{strand}\t.\t'
                                  f'gene_id "{gname}"; transcript_id "{tname}";')
     return "\n".join(lines) + "\n"
+
+
+# ----------------------------------------------------------------------------------------
+# any k (test scale): the same file layout from Python strings and ints, for k-mers wider than one word
+# ----------------------------------------------------------------------------------------
+def kmc_image_from_strings(seqs: list[str], *, k: int, P: int, L: int, n_bins: int, counter_size: int = 1, both_strands: bool = True,
+                           coverage: float = 8.0, seed: int = 1, sigmap: np.ndarray | None = None) -> KmcImage:
+    """KMC 0x200 image of all k-mers of `seqs` (strings over ACGT; other characters break the runs), any k with
+    (k - P) % 4 == 0.  Pure Python: thousands of k-mers, not millions."""
+    assert (k - P) % 4 == 0 and 0 <= P <= 15 and L <= k
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+    norm = norm_table(L)
+    if sigmap is None:
+        sigmap = default_sigmap(L, n_bins)
+    rng = np.random.default_rng(seed)
+    counts: dict[str, int] = {}
+    for s in seqs:
+        s = s.upper()
+        run = 0
+        for i, ch in enumerate(s):
+            run = run + 1 if ch in code else 0
+            if run >= k:
+                km = s[i - k + 1:i + 1]
+                if both_strands:
+                    rc = "".join(comp[c] for c in reversed(km))
+                    if rc < km:
+                        km = rc
+                counts[km] = counts.get(km, 0) + int(rng.poisson(coverage))
+    cmax = (1 << (8 * counter_size)) - 1 if counter_size else 0
+    recs = []
+    for km, c in counts.items():
+        if counter_size and c == 0:
+            continue  # KMC drops k-mers below its minimum count
+        val = 0
+        for ch in km:
+            val = (val << 2) | code[ch]
+        sig = min(int(norm[(val >> (2 * (k - L - j))) & ((1 << (2 * L)) - 1)]) for j in range(k - L + 1))
+        recs.append((int(sigmap[sig]), val, min(c, cmax)))
+    recs.sort()  # bin, then k-mer value: inside a bin ascending (prefix, suffix)
+    N = len(recs)
+    sbits = 2 * (k - P)
+    nsb = (k - P) // 4
+    hist = np.zeros(n_bins << (2 * P), np.int64)
+    body = bytearray()
+    for b, val, c in recs:
+        hist[(b << (2 * P)) + (val >> sbits)] += 1
+        body += (val & ((1 << sbits) - 1)).to_bytes(nsb, "big") + c.to_bytes(counter_size, "little")
+    lut = (np.cumsum(hist) - hist).astype("<u8")
+    suf = np.frombuffer(b"KMCS" + bytes(body) + b"KMCS", np.uint8).copy()
+    header = struct.pack("<7IQB3x24xI", k, 0, counter_size, P, L, 1, max(cmax, 1), N, 0 if both_strands else 1, 0x200)
+    pre = np.concatenate([
+        np.frombuffer(b"KMCP", np.uint8),
+        lut.view(np.uint8),
+        np.frombuffer(struct.pack("<Q", N), np.uint8),
+        sigmap.astype("<u4").view(np.uint8),
+        np.frombuffer(header, np.uint8),
+        np.frombuffer(struct.pack("<I", 68), np.uint8),
+        np.frombuffer(b"KMCP", np.uint8),
+    ])
+    return KmcImage(pre=pre, suf=suf, k=k, P=P, L=L, n_bins=n_bins, counter_size=counter_size, total=N, both_strands=both_strands)
