@@ -483,7 +483,10 @@ def main():
     achieved = total_kmers * ALGO_BYTES_PER_KMER / (screen_ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
             "peak_source": peak_src, "kernel": "kcf_screen_kernel", "kernel_ms": screen_ms, "finalize_ms": finalize_ms,
-            "algorithmic_bytes_per_kmer": ALGO_BYTES_PER_KMER, "kmers_per_launch": total_kmers}
+            "algorithmic_bytes_per_kmer": ALGO_BYTES_PER_KMER, "kmers_per_launch": total_kmers,
+            "kernel_ms_how": "CUDA events around kcf_screen_kernel on the library's own stream (kcf_last_kernel_ms), mean of 3 launches right after "
+                             "the timed region; the timed region is K back-to-back steps timed by events on the same stream, its ms_per_step = "
+                             "kernel_ms + finalize_ms + launch gaps"}
     if rank == 0:
         try:
             rnd = ctx.random_sector_gbps(min(16 << 30, max(1 << 30, 2 * db.info.table_bytes)), 1 << 28, 5)
