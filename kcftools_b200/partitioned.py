@@ -144,14 +144,16 @@ def screen_partitioned_scan(ctx, db, plan, group=None, min_count: int = 1, weigh
     holds ALL windows (the same plan on every rank).  Returns all rows (identical on every rank)."""
     import torch
     import torch.distributed as dist
-    dev = torch.device("cuda", ctx.device)
+    on_gpu = dist.get_backend(group) == "nccl"  # gloo: the host-logic test on CPU (tests/test_shard.py)
+    dev = torch.device("cuda", ctx.device) if on_gpu else torch.device("cpu")
     for t0 in range(0, plan.n_tiles, batch_tiles):
         t1 = t0 + batch_tiles
         hit, sums = _scan_owned(ctx, db, plan, t0, t1, min_count, torch, dev)
         # the owners' bitmaps are disjoint, so the sum is the union (no carries; NCCL has no bitwise reduction)
         dist.all_reduce(hit, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-        torch.cuda.current_stream(dev).synchronize()  # NCCL ran on torch's stream, the library has its own
+        if on_gpu:
+            torch.cuda.current_stream(dev).synchronize()  # NCCL ran on torch's stream, the library has its own
         _scan_fold(ctx, plan, t0, t1, hit, sums)
     return _finish(ctx, plan, weights)
 

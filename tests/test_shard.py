@@ -123,3 +123,64 @@ def test_two_rank_gloo_samples_sharded_cohort(tmp_path):
     a = np.load(tmp_path / "cohort0.npy")
     b = np.load(tmp_path / "cohort1.npy")
     assert (a == b).all() and a.size == 5 * 37 * 40
+
+
+def _scan_worker(rank, world, port, out_dir):
+    """host logic of the scan placement (kcftools_b200.partitioned.screen_partitioned_scan) with the three library calls
+    replaced by CPU stand-ins: rank r "owns" the hit bits b with (word + b) % T == slice, every rank of a window shard's
+    group must see the union after the all-reduce, batch by batch, and only its own shard"""
+    import types
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from kcftools_b200 import partitioned, shard as sh
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    T = 2
+    groups = [dist.new_group(list(range(s * T, (s + 1) * T))) for s in range(world // T)]
+    slice_id, shard_id, members = sh.grid_layout(rank, world, T)
+    assert rank in members
+    n_tiles = 11 + shard_id  # the shards differ in size
+    rng = np.random.default_rng(77 + shard_id)  # the same "truth" on every rank of a shard
+    truth = rng.integers(0, 2**32, n_tiles * 64, dtype=np.uint64).astype(np.uint32)
+    tsum = rng.integers(0, 10**12, n_tiles).astype(np.int64)
+    bit = np.arange(32, dtype=np.uint64)
+    word = np.arange(n_tiles * 64, dtype=np.uint64)
+    own_mask = np.zeros(n_tiles * 64, np.uint32)
+    for b in range(32):
+        own_mask |= (((word + bit[b]) % T == slice_id).astype(np.uint32) << np.uint32(b))
+    seen = {"owned": [], "fold": []}
+
+    def fake_owned(ctx, db, plan, t0, t1, min_count, torch_, dev):
+        t1 = min(t1, plan.n_tiles)
+        seen["owned"].append((t0, t1))
+        hit = (truth[t0 * 64:t1 * 64] & own_mask[t0 * 64:t1 * 64]).view(np.int32).copy()
+        sums = np.where(np.arange(t0, t1) % T == slice_id, tsum[t0:t1], 0).astype(np.int64)
+        return torch_.from_numpy(hit), torch_.from_numpy(sums)
+
+    def fake_fold(ctx, plan, t0, t1, hit, sums):
+        t1 = min(t1, plan.n_tiles)
+        seen["fold"].append((t0, t1))
+        assert (hit.numpy().view(np.uint32) == truth[t0 * 64:t1 * 64]).all()  # sum of disjoint bit sets = their union
+        assert (sums.numpy() == tsum[t0:t1]).all()
+
+    partitioned._scan_owned, partitioned._scan_fold = fake_owned, fake_fold
+    partitioned._finish = lambda ctx, plan, weights: ("rows of shard", shard_id)
+    plan = types.SimpleNamespace(n_tiles=n_tiles)
+    ctx = types.SimpleNamespace(device=0)
+    out = partitioned.screen_partitioned_scan(ctx, None, plan, group=groups[shard_id], batch_tiles=4)
+    assert out == ("rows of shard", shard_id)
+    want = [(t, min(t + 4, n_tiles)) for t in range(0, n_tiles, 4)]
+    assert seen["owned"] == want and seen["fold"] == want
+    open(os.path.join(out_dir, f"scan{rank}.ok"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_four_rank_gloo_scan_placement_groups(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_scan_worker, args=(4, port, str(tmp_path)), nprocs=4, join=True)
+    assert all((tmp_path / f"scan{r}.ok").exists() for r in range(4))
