@@ -21,6 +21,10 @@
 #include "kcf_lookup.cuh"
 #include <thread>
 
+#ifndef KCF_INGEST_CHUNK_BYTES
+#define KCF_INGEST_CHUNK_BYTES (64ULL << 20) // staging chunk (two pinned + two device buffers of this size; 128 MB measured no faster)
+#endif
+
 // The records reach the device through two pinned staging buffers; filling them is a host memcpy out of the page cache
 // (or the caller's array), and one thread doing it (~11 GB/s) was slower than the ingest kernel it feeds.
 static void kcf_parallel_copy(uint8_t *dst, const uint8_t *src, size_t n)
@@ -455,7 +459,7 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     cudaEvent_t ev[2] = {nullptr, nullptr};    // ingest kernel of the chunk staged in buffer j done: both staging buffers j reusable
     cudaEvent_t evc[2] = {nullptr, nullptr};   // H2D copy of buffer j done
     int rc = KCF_OK;
-    const uint64_t chunk_rec = std::max<uint64_t>(1, (64ULL << 20) / std::max<uint32_t>(rec_size, 1));
+    const uint64_t chunk_rec = std::max<uint64_t>(1, (KCF_INGEST_CHUNK_BYTES) / std::max<uint32_t>(rec_size, 1));
     const uint64_t chunk_bytes = chunk_rec * std::max<uint32_t>(rec_size, 1);
     uint64_t ovf_cap = N / 16 + 4096;
     unsigned long long counters[4] = {0, 0, 0, 0};
