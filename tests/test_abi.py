@@ -56,3 +56,27 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
                 src = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle" not in src.lower() or f == "README.md", f"{f} mentions the oracle"
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """the boundary is a C ABI: the header must compile as C99 (no C++ types) and a plain C program must link the library;
+    without a device kcf_init fails loudly (no fallback), with one it succeeds"""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "kcf_b200.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "kcf_b200.h"\n'
+                   'int main(void) { kcf_ctx *c = NULL; int rc = kcf_init(0, &c);\n'
+                   '  printf("%s|%d|%zu|%zu|%zu|%zu\\n", kcf_version(), rc, sizeof(kcf_result_t), sizeof(kcf_cell_t), sizeof(kcf_window_t), sizeof(kcf_segment_t));\n'
+                   '  if (rc != KCF_OK) { printf("%s\\n", kcf_last_error(NULL)); return 0; }\n  kcf_shutdown(c); return 0; }\n')
+    exe = tmp_path / "abi"
+    lib = os.path.join(ROOT, "kcftools_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src), "-L", lib, "-lkcfgpu", f"-Wl,-rpath,{lib}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    ver, rc, *sizes = out[0].split("|")
+    assert "sm_100a" in ver and [int(x) for x in sizes] == [48, 40, 8, 12]
+    import torch
+    if torch.cuda.is_available():
+        assert int(rc) == 0
+    else:
+        assert int(rc) < 0 and "no CPU fallback" in out[1]
