@@ -98,6 +98,13 @@ void *kcf_pool_get(kcf_ctx *ctx, size_t bytes)
     return p;
 }
 
+void kcf_pool_trim(kcf_ctx *ctx)
+{
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &b : ctx->pool) cudaFree(b.p);
+    ctx->pool.clear();
+}
+
 void kcf_pool_put(kcf_ctx *ctx, void *p, size_t bytes)
 {
     if (p) ctx->pool.push_back({p, bytes});

@@ -475,7 +475,11 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
         }                                                                                                     \
     } while (0)
 
-    DB_CUDA(cudaMalloc(&db->table, nb * KCF_LINE_BYTES));
+    if (cudaMalloc(&db->table, nb * KCF_LINE_BYTES) != cudaSuccess) { // give the context's recycled blocks back to the driver, try again
+        (void)cudaGetLastError();
+        kcf_pool_trim(ctx);
+        DB_CUDA(cudaMalloc(&db->table, nb * KCF_LINE_BYTES));
+    }
     DB_CUDA(cudaMemsetAsync(db->table, 0xFF, nb * KCF_LINE_BYTES, ctx->stream)); // empty keys, zero counts and masks (stored inverted)
     DB_CUDA(cudaMalloc(&d_lut, std::max<uint64_t>(lut_len, 1) * 8));
     DB_CUDA(cudaMalloc(&d_sigmap, sig_map_size * 4));
