@@ -144,7 +144,8 @@ int kcf_ref_add(kcf_ctx *ctx, const uint8_t *fasta_seq_bytes, uint64_t n_bytes, 
 int kcf_ref_add_async(kcf_ctx *ctx, const uint8_t *fasta_seq_bytes, uint64_t n_bytes, uint32_t line_bases,
                       uint32_t line_width, uint64_t seq_len, int *seq_id_out);
 int kcf_ref_sync(kcf_ctx *ctx);
-/* Forget all sequences (their device memory is kept for reuse by later kcf_ref_add calls). */
+/* Forget all sequences (their device memory is kept for reuse by later kcf_ref_add calls).  Plans created before the
+ * call refer to sequences that no longer exist: running them afterwards fails with KCF_ERR_ARG. */
 int kcf_ref_clear(kcf_ctx *ctx);
 
 /* ---- screening: replaces GetVariants.java:126-159 ---------------------------------------- */
@@ -152,6 +153,28 @@ int kcf_ref_clear(kcf_ctx *ctx);
  * w = {wi, wt, wr} = {--wi, --wt, --wr} in the order of getWeights() (GetVariants.java:388-390). */
 int kcf_screen(kcf_ctx *ctx, kcf_db *db, const kcf_window_t *wins, uint64_t n_wins, const kcf_segment_t *segs,
                uint64_t n_segs, int32_t min_count, const double w[3], kcf_result_t *out);
+
+/* ---- one job on several GPUs of one process: replaces the pool over all windows, GetVariants.java:129-151 ---------
+ * The host side of the reference hands every window to one pool (`-t` threads); here the window list is cut into n
+ * contiguous ranges balanced on the number of bases (kcf_shard_windows: bounds_out[n_shards + 1]) and range g is screened
+ * on ctxs[g] against dbs[g] — the same database opened (placement 0) on every context.  The reference sequences are
+ * given as HOST bytes (seqs[i] = what kcf_ref_add takes for sequence id i): each context uploads only the line-aligned
+ * stretches its windows touch, screening them while the next stretch crosses PCIe, and the rows land in out[] at their
+ * window's index.  One host thread per context; no communication library, no device-to-device traffic.  The call
+ * replaces whatever sequences the contexts held (kcf_ref_clear).  n = 1 is the plain "screen from host buffers" call.
+ * Errors: the first failing context's code; its message is copied to ctxs[0]. */
+typedef struct kcf_host_seq_t {
+    const uint8_t *bytes;  /* raw FASTA bytes of the sequence, newlines included (FastaIndex.java:54-68) */
+    uint64_t n_bytes;
+    uint32_t line_bases;   /* .faidx columns */
+    uint32_t line_width;
+    uint64_t seq_len;
+} kcf_host_seq_t;
+int kcf_shard_windows(const kcf_window_t *wins, uint64_t n_wins, const kcf_segment_t *segs, uint64_t n_segs, int n_shards,
+                      uint64_t *bounds_out);
+int kcf_screen_sharded(kcf_ctx *const *ctxs, kcf_db *const *dbs, int n, const kcf_host_seq_t *seqs, uint32_t n_seqs,
+                       const kcf_window_t *wins, uint64_t n_wins, const kcf_segment_t *segs, uint64_t n_segs, int32_t min_count,
+                       const double w[3], kcf_result_t *out);
 
 /* The same in three steps, for callers that screen one window list against many databases (cohorts)
  * or want the device-resident part timed alone. */

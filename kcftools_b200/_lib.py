@@ -28,6 +28,11 @@ STATUS = {0: "KCF_OK", -1: "KCF_ERR_CUDA", -2: "KCF_ERR_IO", -3: "KCF_ERR_DB_FOR
           -10: "KCF_ERR_DB_ORDER"}
 
 
+class HostSeq(C.Structure):  # kcf_host_seq_t
+    _fields_ = [("bytes", C.c_void_p), ("n_bytes", C.c_uint64), ("line_bases", C.c_uint32), ("line_width", C.c_uint32),
+                ("seq_len", C.c_uint64)]
+
+
 class DbInfo(C.Structure):
     _fields_ = [("kmer_length", C.c_int32), ("lut_prefix_length", C.c_int32), ("signature_length", C.c_int32),
                 ("counter_size", C.c_int32), ("both_strands", C.c_int32), ("min_count", C.c_int32),
@@ -58,6 +63,8 @@ SYMBOLS = {
     "kcf_ref_sync": (C.c_int, [_P]),
     "kcf_ref_clear": (C.c_int, [_P]),
     "kcf_screen": (C.c_int, [_P, _P, _P, C.c_uint64, _P, C.c_uint64, C.c_int32, C.POINTER(C.c_double), _P]),
+    "kcf_shard_windows": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64, C.c_int, _P]),
+    "kcf_screen_sharded": (C.c_int, [_P, _P, C.c_int, _P, C.c_uint32, _P, C.c_uint64, _P, C.c_uint64, C.c_int32, C.POINTER(C.c_double), _P]),
     "kcf_plan_create": (C.c_int, [_P, C.c_int32, _P, C.c_uint64, _P, C.c_uint64, C.POINTER(_P)]),
     "kcf_plan_run": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(C.c_double)]),
     "kcf_plan_fetch": (C.c_int, [_P, _P, _P]),

@@ -275,6 +275,49 @@ class Cohort:
             self._h = C.c_void_p()
 
 
+def host_seqs(seqs) -> "C.Array":
+    """kcf_host_seq_t array over (bytes, line_bases, line_width, seq_len) tuples; the byte arrays must stay alive"""
+    arr = (_lib.HostSeq * max(len(seqs), 1))()
+    for i, (raw, lb, lw, sl) in enumerate(seqs):
+        assert raw.dtype == np.uint8 and raw.flags.c_contiguous
+        arr[i] = _lib.HostSeq(_ptr(raw), raw.size, int(lb), int(lw), int(sl))
+    return arr
+
+
+def shard_windows(wins: np.ndarray, segs: np.ndarray, n_shards: int) -> np.ndarray:
+    """bounds[n_shards + 1] of the contiguous window ranges kcf_screen_sharded gives its contexts (balanced on bases)"""
+    wins = np.ascontiguousarray(wins, WINDOW_DTYPE)
+    segs = np.ascontiguousarray(segs, SEGMENT_DTYPE)
+    out = np.zeros(n_shards + 1, np.uint64)
+    rc = _lib.load().kcf_shard_windows(_ptr(wins), wins.size, _ptr(segs), segs.size, n_shards, _ptr(out))
+    if rc:
+        raise KcfError(rc, "kcf_shard_windows: bad window / segment arrays")
+    return out
+
+
+def screen_sharded(ctxs, dbs, seqs, wins: np.ndarray, segs: np.ndarray, min_count: int = 1, weights=(0.3, 0.3, 0.4),
+                   out: np.ndarray | None = None) -> np.ndarray:
+    """ONE job over the GPUs of this process (GetVariants.java:129-151): `dbs[g]` is the same database opened on `ctxs[g]`;
+    `seqs` = [(fasta bytes, line_bases, line_width, seq_len), ...] in HOST memory (pinned for full-rate copies).  Every
+    context uploads only the stretches its window range touches.  len(ctxs) == 1 is the plain host-buffer call."""
+    wins = np.ascontiguousarray(wins, WINDOW_DTYPE)
+    segs = np.ascontiguousarray(segs, SEGMENT_DTYPE)
+    if out is None:
+        out = np.zeros(wins.size, RESULT_DTYPE)
+    n = len(ctxs)
+    assert n >= 1 and len(dbs) == n
+    hs = seqs if not isinstance(seqs, (list, tuple)) else host_seqs(seqs)
+    n_seqs = len(seqs) if isinstance(seqs, (list, tuple)) else len(hs)
+    ch = (C.c_void_p * n)(*[c._h for c in ctxs])
+    dh = (C.c_void_p * n)(*[d._h for d in dbs])
+    w = (C.c_double * 3)(*weights)
+    lib = ctxs[0]._lib
+    ctxs[0]._check(lib.kcf_screen_sharded(ch, dh, n, hs, n_seqs, _ptr(wins), wins.size, _ptr(segs), segs.size, min_count, w, _ptr(out)))
+    for c in ctxs:
+        c.n_seqs = 0  # the call replaced the contexts' sequences
+    return out
+
+
 def fixed_windows(seq_lens, window: int, step: int, k: int):
     """window / segment arrays of the `-f window` mode (GetVariants.java:292-320) for sequences 0..n-1.
     Returns (wins, segs, starts, ends, seq_ids)."""

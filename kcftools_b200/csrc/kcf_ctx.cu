@@ -124,6 +124,7 @@ extern "C" int kcf_ref_clear(kcf_ctx *ctx)
     ctx->seqs.clear();
     ctx->seqs_dirty = true;
     ctx->seqs_uploaded = 0;
+    ++ctx->ref_generation; // plans built before this point address recycled memory: kcf_plan_run refuses them
     return KCF_OK;
 }
 
@@ -188,7 +189,7 @@ extern "C" int kcf_last_kernel_ms(kcf_ctx *ctx, float *screen_ms, float *finaliz
 // ---- K2 ----------------------------------------------------------------------------------------
 // One CTA converts PACK_BASES consecutive bases.  The raw bytes they occupy (bases + line terminators)
 // are staged in shared memory with 16-byte loads from a 16-byte aligned window, then each thread turns
-// 32 bases into two code words and one validity word.
+// 32 bases into the two bit planes of their codes and one validity word.
 #define PACK_THREADS 256
 #define PACK_BASES (PACK_THREADS * 32)
 
@@ -215,15 +216,15 @@ kcf_pack_kernel(const uint8_t *__restrict__ raw, uint64_t n_bytes_padded, uint32
     uint32_t line = (uint32_t)(p / line_bases);
     uint32_t col = (uint32_t)(p % line_bases);
     uint32_t off = (uint32_t)((uint64_t)line * line_width + col - a0);
-    uint32_t lo = 0, hi = 0, v = 0;
+    uint32_t pl0 = 0, pl1 = 0, v = 0;
     const uint32_t nb = (uint32_t)min((uint64_t)32, seq_len - p);
     for (uint32_t j = 0; j < nb; ++j) {
         uint32_t b = s_raw[off];
         uint32_t u = b & 0xDFu; // Character.toUpperCase for ASCII letters (Fasta.java:98)
         uint32_t ok = (u == 'A') | (u == 'C') | (u == 'G') | (u == 'T'); // Fasta.java:132-134
         uint32_t c = (((b >> 1) & 3u) ^ ((b >> 2) & 1u)) & (0u - ok);    // A0 C1 G2 T3 (Kmer.java:286-294)
-        if (j < 16) lo |= c << (2 * j);
-        else hi |= c << (2 * (j - 16));
+        pl0 |= (c & 1u) << j;
+        pl1 |= (c >> 1) << j;
         v |= ok << j;
         ++col;
         ++off;
@@ -233,8 +234,7 @@ kcf_pack_kernel(const uint8_t *__restrict__ raw, uint64_t n_bytes_padded, uint32
         }
     }
     const uint64_t w = p >> 5;
-    codes[2 * w] = lo;
-    codes[2 * w + 1] = hi;
+    reinterpret_cast<uint2 *>(codes)[w] = make_uint2(pl0, pl1);
     valid[w] = v;
 }
 

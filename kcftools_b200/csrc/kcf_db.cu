@@ -195,15 +195,17 @@ __global__ void __launch_bounds__(256) kcf_ingest_kernel(KcfIngestParams p, KcfT
         atomicAdd(&p.counters[0], 1ULL);
         return;
     }
-    const uint32_t home = kcf_home_line(kcf_minimizer_of_key(kmer, g), g);
+    // proof done in the reference's encoding; from here on the record is its table key (bit planes, kcf_lookup.cuh)
+    const uint64_t tkey = kcf_table_key(kmer, g);
+    const uint32_t home = kcf_home_line(kcf_minimizer_of_key(tkey, g), g);
     if (p.part_world > 1 && kcf_line_owner(home, g.n_lines, p.part_world) != p.part_rank) { // another rank's slice
         atomicAdd(&p.counters[3], 1ULL);
         return;
     }
     uint8_t *home_line = p.table + (uint64_t)kcf_line_wrap(home, 0, g) * KCF_LINE_BYTES;
     uint32_t *home_w31 = reinterpret_cast<uint32_t *>(home_line) + 31;
-    if (KCF_KEY_IN_LINES(kmer)) {
-        const uint32_t lo = (uint32_t)kmer, hi = (uint32_t)(kmer >> 32);
+    if (KCF_KEY_IN_LINES(tkey)) {
+        const uint32_t lo = (uint32_t)tkey, hi = (uint32_t)(tkey >> 32);
         for (uint32_t d = 0; d <= KCF_MAX_DISP; ++d) {
             uint8_t *line = p.table + (uint64_t)kcf_line_wrap(home, d, g) * KCF_LINE_BYTES;
             uint32_t *w = reinterpret_cast<uint32_t *>(line);
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(256) kcf_ingest_kernel(KcfIngestParams p, KcfT
                     const uint32_t field = g.cw == 4 ? 0xFFFFFFFFu : (((1u << (8 * g.cw)) - 1u) << sh);
                     atomicAnd(w + (off >> 2), ~field | (count << sh));
                     atomicAnd(home_w31, ~(1u << (16 + d)));
-                    if (d > 0) kcf_filter_add(home_line, kmer, g);
+                    if (d > 0) kcf_filter_add(home_line, tkey, g);
                     atomicAdd(&p.counters[0], 1ULL);
                     placed = true;
                     break;
@@ -251,10 +253,10 @@ __global__ void __launch_bounds__(256) kcf_ingest_kernel(KcfIngestParams p, KcfT
         }
     }
     atomicAnd(home_w31, ~(1u << (16 + KCF_STASH_BIT)));
-    kcf_filter_add(home_line, kmer, g);
+    kcf_filter_add(home_line, tkey, g);
     unsigned long long pos = atomicAdd(&p.counters[2], 1ULL);
     if (pos < p.ovf_cap) {
-        p.ovf[pos].key = kmer;
+        p.ovf[pos].key = tkey;
         p.ovf[pos].meta = (1ULL << 63) | count;
     }
 }
@@ -293,11 +295,7 @@ __global__ void kcf_count_kernel(const char *__restrict__ ascii, uint64_t n, con
         out[t] = 0;
         return;
     }
-    if (g.both_strands) {
-        uint64_t rc = kcf_revcomp(v, g.kshift);
-        if (rc < v) v = rc;
-    }
-    out[t] = (int32_t)kcf_lookup(table, stash, g, v);
+    out[t] = (int32_t)kcf_lookup(table, stash, g, kcf_table_key(v, g)); // strand symmetric for a both-strands database
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -395,6 +393,7 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     g.k = (uint32_t)k;
     g.kshift = 64 - kk2;
     g.kmask = kk2 == 64 ? ~0ULL : ((1ULL << kk2) - 1);
+    g.km = k >= 32 ? 0xFFFFFFFFu : ((1u << k) - 1u);
     g.cw = cs <= 1 ? 1u : (cs == 2 ? 2u : 4u);
     g.S = g.cw == 1 ? 13u : (g.cw == 2 ? 12u : 10u);
     g.coff = g.cw == 1 ? 112u : 8u * g.S;
@@ -416,7 +415,7 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
         if (k - m + 1 > 32) m = k - 31;
         g.m = (uint32_t)m;
         g.w = (uint32_t)(k - m + 1);
-        g.mmask = (1ULL << (2 * m)) - 1ULL;
+        g.mm = m >= 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
     }
     double lf = ctx->load_factor;
     if (lf <= 0.0) { // automatic: sparse tables are faster (fewer keys outside their home line: 72.8 / 74.9 / 76.9 / 78.9 / 79.7 G

@@ -16,12 +16,13 @@
 // line is chosen by the k-mer's MINIMIZER, so that the ~(w+1)/2 consecutive reference k-mers
 // sharing a minimizer probe the same line:
 //
-//   o(x)   = mix32(min(x, revcomp(x)))         order hash of an m-mer, strand symmetric
+//   o(x)   = hash(smaller strand of x)         order hash of an m-mer, strand symmetric (kcf_lookup.cuh)
 //   mu(K)  = min o(x) over the w = k-m+1 m-mers of K
 //   home   = floor(mix32(mu ^ c) * n_lines / 2^32)
 //   line   = S key low words | S key high words | filter | S counts | 16-bit mask
 //            (S = 13 slots and a 64-bit filter for 1-byte counts; 12 / 10 slots and 32 bits for 2 / 4-byte counts;
-//             key = canonical k-mer value, stored in full; low word 0xFFFFFFFF = empty slot)
+//             key = the k-mer's bit planes, plane1 << 32 | plane0 (kcf_lookup.cuh), stored in full; low word
+//             0xFFFFFFFF = empty slot)
 //
 // A key lives in its home line or, when that was full at insertion time (no deletions), in one of 14 lines of a
 // separate OVERFLOW region starting at a hash of the home line — home lines only ever hold their own keys, so one
@@ -44,13 +45,14 @@ struct KcfTableGeom {
     uint64_t line_lo;    // global index of local home line 0 (0 unless the database is partitioned)
     uint64_t n_local;    // home lines held by this table (== n_lines unless partitioned)
     uint64_t n_ov;       // overflow lines, stored after the home lines: keys that do not fit their home line
-    uint64_t kmask;      // 2k one-bits
+    uint64_t kmask;      // 2k one-bits (the reference's k-mer value)
     uint64_t stash_mask; // stash capacity - 1 (power of two), 0 when the stash is empty
     uint32_t k;
     uint32_t kshift;     // 64 - 2k
     uint32_t m;          // minimizer length, 1..24, <= k
     uint32_t w;          // k - m + 1 (1..32)
-    uint64_t mmask;      // 2m one-bits
+    uint32_t km;         // k one-bits (one bit plane of a k-mer)
+    uint32_t mm;         // m one-bits (one bit plane of an m-mer)
     uint32_t S;          // slots per line: 13 / 12 / 10 for count width 1 / 2 / 4
     uint32_t cw;         // bytes per stored count: 1, 2 or 4 (0-byte counters store nothing)
     uint32_t coff;       // byte offset of the counts inside a line: 112 / 96 / 80
@@ -93,8 +95,9 @@ __host__ __device__ __forceinline__ uint64_t kcf_mix64(uint64_t x)
 }
 
 // ------------------------------------------------------------------------------------------
-// Reference sequences: 2-bit codes (16 bases per u32, base j of a word in bits 2j..2j+1) and a
-// validity bitmap (32 bases per u32).  A = 0, C = 1, G = 2, T = 3 (Kmer.java:286-294).
+// Reference sequences: two bit planes of the 2-bit base codes (A = 0, C = 1, G = 2, T = 3, Kmer.java:286-294) and a
+// validity bitmap, 32 bases per word: codes[2i] = bit 0 of bases 32i .. 32i+31 (base j in bit j), codes[2i+1] = bit 1,
+// valid[i] = base is one of ACGTacgt.
 // ------------------------------------------------------------------------------------------
 struct KcfSeqDev {
     const uint32_t *codes;
@@ -160,7 +163,8 @@ struct kcf_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_screen_ms = 0.f, last_finalize_ms = 0.f;
     bool ev_valid = false;
-    uint32_t *d_flags = nullptr; // device error / status flags
+    uint32_t *d_flags = nullptr; // device error / status flags (database load)
+    uint64_t ref_generation = 1; // bumped by kcf_ref_clear: plans remember the generation they were built against
 };
 
 struct kcf_db {
@@ -185,6 +189,8 @@ struct kcf_plan {
     uint64_t *d_tile_first = nullptr; // n_wins + 1: first tile of each window
     KcfGap *d_tile_sum = nullptr;     // one summary per tile
     kcf_result_t *d_out = nullptr;
+    uint32_t *d_flags = nullptr;      // this plan's status word(s): FLAG_SCORE_USED of ITS last run (several plans may be queued)
+    uint64_t ref_generation = 0;      // ctx->ref_generation at creation: the sequences its segments point into
     std::vector<uint32_t> h_win_len;
     std::vector<uint64_t> h_tile_first;
     bool ran = false;
@@ -202,7 +208,7 @@ struct kcf_plan {
 };
 
 #define KCF_TILE 2048          // positions per tile = the unit of work one warp takes
-#define KCF_HALO 32            // bases staged before a chunk (>= k-1, word aligned)
+#define KCF_HALO 64            // bases staged before a chunk (>= k-1 + the minimizer window, word aligned)
 
 // indices into kcf_ctx::d_flags
 enum { FLAG_LUT_BAD = 0, FLAG_ORDER_BAD = 1, FLAG_SCORE_USED = 2, FLAG_COUNT = 8 };

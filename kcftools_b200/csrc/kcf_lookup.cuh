@@ -1,8 +1,23 @@
 // kcf_lookup.cuh — device-side pieces shared by the database loader and the screening kernel:
-// k-mer bit tricks, the minimizer that picks a k-mer's home line, and the generic (global-memory)
+// the two k-mer encodings, the minimizer that picks a k-mer's home line, and the generic (global-memory)
 // probe that replaces KMC.getCount (KMC.java:292-326) outside the tiled fast path.
 #pragma once
 #include "kcf_internal.cuh"
+
+// ------------------------------------------------------------------------------------------------------------
+// Two encodings of a k-mer meet in this library.
+//
+//   * the REFERENCE's value (Kmer.java:232-252): 2 bits per base, first base most significant, right aligned in
+//     64 bits.  The database records arrive in it and the loader's reachability proof (canonical form, signature,
+//     bin) is stated in it.
+//   * the TABLE KEY: two BIT PLANES of k bits each, base j in bit j — plane 0 holds bit 0 of every base code, plane 1
+//     bit 1 (A = 00, C = 01, G = 10, T = 11); key = plane1 << 32 | plane0.  The packed reference sequences use the same
+//     planes (32 bases per word pair), so the screening kernel cuts a k-mer or an m-mer out of them with one funnel
+//     shift per plane, and the reverse complement is ONE bit reversal per plane plus a complement (A<->T, C<->G flips
+//     both bits) — no pair swaps.  For a both-strands database the key is the smaller of the two strands' plane
+//     forms: any strand-symmetric injective choice works, since the table only has to answer "is the record that
+//     spells this k-mer's canonical form present" and the loader stores exactly that record under this key.
+// ------------------------------------------------------------------------------------------------------------
 
 // bit-reverse a 64-bit word keeping each 2-bit base code intact: base j moves to pair 31-j
 __device__ __forceinline__ uint64_t kcf_pair_reverse64(uint64_t x)
@@ -24,15 +39,59 @@ __device__ __forceinline__ uint64_t kcf_pair_reverse(uint64_t x, uint32_t kshift
     return kcf_pair_reverse64(x) >> kshift;
 }
 
-// Order hash of the m-mer that starts at base j of E (E: up to 32 bases packed LSB-first, R =
-// kcf_pair_reverse64(~E), i.e. the reverse complement of all 32 bases).  Strand symmetric: an m-mer
-// and its reverse complement get the same value.
-__device__ __forceinline__ uint32_t kcf_mmer_order(uint64_t E, uint64_t R, uint32_t j, const KcfTableGeom &g)
+// the even bits of x, compacted
+__host__ __device__ __forceinline__ uint32_t kcf_even_bits(uint64_t x)
 {
-    const uint64_t x = (E >> (2 * j)) & g.mmask;
-    const uint64_t r = (R >> (2 * (32 - g.m - j))) & g.mmask;
-    const uint64_t c = min(x, r);
-    return kcf_mix32((uint32_t)c ^ ((uint32_t)(c >> 32) * 0x9E3779B1u)); // m <= 16: the plain 32-bit value
+    x &= 0x5555555555555555ULL;
+    x = (x | (x >> 1)) & 0x3333333333333333ULL;
+    x = (x | (x >> 2)) & 0x0F0F0F0F0F0F0F0FULL;
+    x = (x | (x >> 4)) & 0x00FF00FF00FF00FFULL;
+    x = (x | (x >> 8)) & 0x0000FFFF0000FFFFULL;
+    x = (x | (x >> 16)) & 0x00000000FFFFFFFFULL;
+    return (uint32_t)x;
+}
+
+// reverse complement of one bit plane of n bases (n = 1..32; `nm` = its n one-bits)
+__device__ __forceinline__ uint32_t kcf_plane_rc(uint32_t f, uint32_t n, uint32_t nm)
+{
+    return (__brev(f) >> (32u - n)) ^ nm;
+}
+
+// the smaller of a sequence's two strands in plane form, compared as plane1:plane0 (strand symmetric)
+__device__ __forceinline__ void kcf_plane_canonical(uint32_t f0, uint32_t f1, uint32_t r0, uint32_t r1, uint32_t &c0, uint32_t &c1)
+{
+    const bool rev = r1 < f1 || (r1 == f1 && r0 < f0);
+    c0 = rev ? r0 : f0;
+    c1 = rev ? r1 : f1;
+}
+
+// table key of a k-mer given as the reference's value
+__device__ __forceinline__ uint64_t kcf_table_key(uint64_t kmer, const KcfTableGeom &g)
+{
+    const uint64_t E = kcf_pair_reverse(kmer, g.kshift); // base j in bits 2j, 2j+1
+    uint32_t f0 = kcf_even_bits(E), f1 = kcf_even_bits(E >> 1);
+    if (g.both_strands) kcf_plane_canonical(f0, f1, kcf_plane_rc(f0, g.k, g.km), kcf_plane_rc(f1, g.k, g.km), f0, f1);
+    return ((uint64_t)f1 << 32) | f0;
+}
+
+// Order hash of an m-mer from the plane form (c0, c1) of its canonical strand: what ranks the m-mers of a k-mer when
+// its minimizer is chosen.  Two multiplies fold the planes and carry every input bit upwards, one xor-shift / multiply
+// round spreads them; the rank is decided by the high bits.
+__host__ __device__ __forceinline__ uint32_t kcf_order_hash(uint32_t c0, uint32_t c1)
+{
+    uint32_t h = c0 * 0x9E3779B1u + c1 * 0x85EBCA77u;
+    h ^= h >> 15;
+    h *= 0x846ca68bU;
+    return h;
+}
+
+// order hash of the m-mer whose forward-strand planes are x0, x1 (bits above m may hold anything)
+__device__ __forceinline__ uint32_t kcf_mmer_order(uint32_t x0, uint32_t x1, uint32_t m, uint32_t mm)
+{
+    const uint32_t r0 = (~__brev(x0)) >> (32u - m), r1 = (~__brev(x1)) >> (32u - m); // the shift drops the unknown high bits
+    uint32_t c0, c1;
+    kcf_plane_canonical(x0 & mm, x1 & mm, r0, r1, c0, c1);
+    return kcf_order_hash(c0, c1);
 }
 
 __device__ __forceinline__ uint32_t kcf_home_line(uint32_t mu, const KcfTableGeom &g)
@@ -40,13 +99,13 @@ __device__ __forceinline__ uint32_t kcf_home_line(uint32_t mu, const KcfTableGeo
     return __umulhi(kcf_mix32(mu ^ 0x9E3779B9u), (uint32_t)g.n_lines);
 }
 
-// minimizer value of a k-mer given as the reference's first-base-most-significant value
+// minimizer value of a k-mer given as its table key (either strand's plane form gives the same value: the order
+// hash is strand symmetric and the k-mer's m-mers are the same set)
 __device__ __forceinline__ uint32_t kcf_minimizer_of_key(uint64_t key, const KcfTableGeom &g)
 {
-    const uint64_t E = kcf_pair_reverse(key, g.kshift);
-    const uint64_t R = kcf_pair_reverse64(~E);
+    const uint32_t f0 = (uint32_t)key, f1 = (uint32_t)(key >> 32);
     uint32_t mu = 0xFFFFFFFFu;
-    for (uint32_t j = 0; j < g.w; ++j) mu = min(mu, kcf_mmer_order(E, R, j, g));
+    for (uint32_t j = 0; j < g.w; ++j) mu = min(mu, kcf_mmer_order(f0 >> j, f1 >> j, g.m, g.mm));
     return mu;
 }
 

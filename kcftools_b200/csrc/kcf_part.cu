@@ -18,6 +18,7 @@
 #include <vector>
 #include "kcf_internal.cuh"
 #include "kcf_lookup.cuh"
+#include "kcf_gap.cuh"
 
 #define KCF_MAX_WORLD 64
 
@@ -115,79 +116,6 @@ __global__ void __launch_bounds__(256) kcf_part_unscatter_kernel(const uint32_t 
     if (i < n) cnt_by_pos[src[i]] = counts[i];
 }
 
-__device__ __forceinline__ uint32_t kcf_gap_distance_p(uint32_t gap, uint32_t k)
-{
-    int32_t d = (int32_t)gap - ((int32_t)k - 1);
-    if (d <= 0) d = abs(d + 1);
-    return (uint32_t)d;
-}
-
-// summary of 32 positions from their bitmaps (same function as in kcf_screen.cu; restated here to keep that file's
-// kernel self-contained)
-__device__ __forceinline__ KcfGap kcf_gap_bits_p(uint32_t hw, uint32_t vw, uint32_t sw, uint32_t k)
-{
-    KcfGap a;
-    a.n = __popc(vw);
-    a.obs = __popc(hw);
-    a.starts = __popc(sw);
-    a.sum = 0;
-    a.vin = a.inner = 0;
-    a.has = hw != 0;
-    if (!hw) {
-        a.lead = a.trail = a.n;
-        return a;
-    }
-    const uint32_t first = __ffs(hw) - 1, last = 31 - __clz(hw);
-    a.lead = __popc(vw & ((1u << first) - 1u));
-    a.trail = __popc(vw & ~(0xFFFFFFFFu >> (31 - last)));
-    uint32_t zr = ~hw & (0xFFFFFFFFu >> (31 - last)) & ~((1u << first) - 1u);
-    while (zr) {
-        const uint32_t s = __ffs(zr) - 1;
-        const uint32_t e = __ffs(~(zr >> s)) - 1;
-        const uint32_t gm = ((1u << e) - 1u) << s;
-        const uint32_t glen = __popc(vw & gm);
-        if (glen) {
-            a.vin += 1;
-            a.inner += kcf_gap_distance_p(glen, k);
-        }
-        zr &= ~gm;
-    }
-    return a;
-}
-
-__device__ __forceinline__ KcfGap kcf_gap_combine_p(const KcfGap &a, const KcfGap &b, uint32_t k)
-{
-    if (b.n == 0) return a;
-    if (a.n == 0) return b;
-    KcfGap r;
-    r.n = a.n + b.n;
-    r.obs = a.obs + b.obs;
-    r.sum = a.sum + b.sum;
-    r.starts = a.starts + b.starts;
-    r.vin = a.vin + b.vin;
-    r.inner = a.inner + b.inner;
-    r.has = a.has | b.has;
-    if (a.has && b.has) {
-        const uint32_t gp = a.trail + b.lead;
-        if (gp > 0) {
-            r.vin += 1;
-            r.inner += kcf_gap_distance_p(gp, k);
-        }
-        r.lead = a.lead;
-        r.trail = b.trail;
-    } else if (a.has) {
-        r.lead = a.lead;
-        r.trail = a.trail + b.n;
-    } else if (b.has) {
-        r.lead = a.n + b.lead;
-        r.trail = b.trail;
-    } else {
-        r.lead = r.n;
-        r.trail = r.n;
-    }
-    return r;
-}
-
 // one warp per tile of KCF_TILE positions: 64 words of 32 positions, two per lane, reduced in order
 __global__ void __launch_bounds__(128) kcf_part_fold_kernel(const uint32_t *__restrict__ cnt_by_pos, const uint32_t *__restrict__ okw,
                                                             const uint32_t *__restrict__ start, uint64_t n_tiles, uint32_t k, int32_t min_count,
@@ -212,23 +140,14 @@ __global__ void __launch_bounds__(128) kcf_part_fold_kernel(const uint32_t *__re
             else hw1 = hb;
         }
     }
-    KcfGap a = kcf_gap_bits_p(hw0, okw[t * WORDS + lane], start[t * WORDS + lane], k);
-    KcfGap b = kcf_gap_bits_p(hw1, okw[t * WORDS + 32 + lane], start[t * WORDS + 32 + lane], k);
-    for (int d = 1; d < 32; d <<= 1) {
-        KcfGap a2, b2;
-#define SHF(dst, srcv, f) dst.f = __shfl_down_sync(0xffffffffu, srcv.f, d)
-        SHF(a2, a, n); SHF(a2, a, obs); SHF(a2, a, lead); SHF(a2, a, trail); SHF(a2, a, vin); SHF(a2, a, inner); SHF(a2, a, has); SHF(a2, a, starts);
-        SHF(b2, b, n); SHF(b2, b, obs); SHF(b2, b, lead); SHF(b2, b, trail); SHF(b2, b, vin); SHF(b2, b, inner); SHF(b2, b, has); SHF(b2, b, starts);
-#undef SHF
-        a2.sum = b2.sum = 0;
-        if (lane + d < 32) {
-            a = kcf_gap_combine_p(a, a2, k);
-            b = kcf_gap_combine_p(b, b2, k);
-        }
-        sum += __shfl_down_sync(0xffffffffu, sum, d);
-    }
+    KcfGap a = kcf_gap_from_bits(hw0, okw[t * WORDS + lane], start[t * WORDS + lane], k);
+    KcfGap b = kcf_gap_from_bits(hw1, okw[t * WORDS + 32 + lane], start[t * WORDS + 32 + lane], k);
+    a = kcf_gap_warp_reduce(a, lane, k);
+    b = kcf_gap_warp_reduce(b, lane, k);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, d);
     if (lane == 0) {
-        KcfGap r = kcf_gap_combine_p(a, b, k);
+        KcfGap r = kcf_gap_combine(a, b, k);
         r.sum = sum;
         tile_sum[t] = r;
     }
@@ -355,22 +274,12 @@ __global__ void __launch_bounds__(128) kcf_scan_fold_kernel(const uint32_t *__re
     constexpr int WORDS = KCF_TILE / 32; // 64
     const uint64_t w0 = t * WORDS + lane, w1 = w0 + 32;
     // a hit bit is only ever set where a k-mer ends; the mask keeps a corrupted reduction from inventing k-mers
-    KcfGap a = kcf_gap_bits_p(hit[w0] & okw[w0], okw[w0], start[w0], k);
-    KcfGap b = kcf_gap_bits_p(hit[w1] & okw[w1], okw[w1], start[w1], k);
-    for (int d = 1; d < 32; d <<= 1) {
-        KcfGap a2, b2;
-#define SHF(dst, srcv, f) dst.f = __shfl_down_sync(0xffffffffu, srcv.f, d)
-        SHF(a2, a, n); SHF(a2, a, obs); SHF(a2, a, lead); SHF(a2, a, trail); SHF(a2, a, vin); SHF(a2, a, inner); SHF(a2, a, has); SHF(a2, a, starts);
-        SHF(b2, b, n); SHF(b2, b, obs); SHF(b2, b, lead); SHF(b2, b, trail); SHF(b2, b, vin); SHF(b2, b, inner); SHF(b2, b, has); SHF(b2, b, starts);
-#undef SHF
-        a2.sum = b2.sum = 0;
-        if (lane + d < 32) {
-            a = kcf_gap_combine_p(a, a2, k);
-            b = kcf_gap_combine_p(b, b2, k);
-        }
-    }
+    KcfGap a = kcf_gap_from_bits(hit[w0] & okw[w0], okw[w0], start[w0], k);
+    KcfGap b = kcf_gap_from_bits(hit[w1] & okw[w1], okw[w1], start[w1], k);
+    a = kcf_gap_warp_reduce(a, lane, k);
+    b = kcf_gap_warp_reduce(b, lane, k);
     if (lane == 0) {
-        KcfGap r = kcf_gap_combine_p(a, b, k);
+        KcfGap r = kcf_gap_combine(a, b, k);
         r.sum = sums[t];
         tile_sum[t] = r;
     }

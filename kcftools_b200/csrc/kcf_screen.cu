@@ -4,16 +4,14 @@
 // KMC.getCount KMC.java:292-326), for all windows in one launch.
 //
 // Work unit = a tile of KCF_TILE consecutive positions of one window (a window is the concatenation
-// of its segments, GTF.java:240-244 / Window.java:224-226).  A CTA stages the tile's 2-bit bases and
-// validity bits plus a 32-base halo in shared memory, every thread then owns 8 consecutive k-mer end
-// positions: it rolls the forward / reverse-complement words, issues its 8 independent 32-byte bucket
-// loads, folds the hit pattern into a gap monoid, and the CTA reduces the 256 partial monoids in
-// order with warp shuffles.  No per-k-mer data ever goes back to HBM.
+// of its segments, GTF.java:240-244 / Window.java:224-226), taken by ONE WARP and walked in chunks of
+// KCF_CHUNK positions; lanes own consecutive k-mer end positions.  The design is described above the
+// kernel.  No per-k-mer data ever goes back to HBM.
 #include <algorithm>
 #include <cstring>
-#include <cstdlib>
 #include "kcf_internal.cuh"
 #include "kcf_lookup.cuh"
+#include "kcf_gap.cuh"
 
 
 struct KcfScreenParams {
@@ -45,77 +43,25 @@ struct KcfScreenParams {
 
 enum { KCF_MODE_SCREEN = 0, KCF_MODE_COUNTS = 1, KCF_MODE_EXTRACT = 2, KCF_MODE_OWNED = 3 };
 
-// GetVariants.java:267-273 getDistance
-__device__ __forceinline__ uint32_t kcf_gap_distance(uint32_t gap, uint32_t k)
-{
-    int32_t d = (int32_t)gap - ((int32_t)k - 1);
-    if (d <= 0) d = abs(d + 1);
-    return (uint32_t)d;
-}
-
-// in-order concatenation of two summaries
-__device__ __forceinline__ KcfGap kcf_gap_combine(const KcfGap &a, const KcfGap &b, uint32_t k)
-{
-    if (b.n == 0) return a;
-    if (a.n == 0) return b;
-    KcfGap r;
-    r.n = a.n + b.n;
-    r.obs = a.obs + b.obs;
-    r.sum = a.sum + b.sum;
-    r.starts = a.starts + b.starts;
-    r.vin = a.vin + b.vin;
-    r.inner = a.inner + b.inner;
-    r.has = a.has | b.has;
-    if (a.has && b.has) {
-        uint32_t g = a.trail + b.lead; // a miss run closed by hits on both sides (GetVariants.java:227-238)
-        if (g > 0) {
-            r.vin += 1;
-            r.inner += kcf_gap_distance(g, k);
-        }
-        r.lead = a.lead;
-        r.trail = b.trail;
-    } else if (a.has) {
-        r.lead = a.lead;
-        r.trail = a.trail + b.n;
-    } else if (b.has) {
-        r.lead = a.n + b.lead;
-        r.trail = b.trail;
-    } else {
-        r.lead = r.n;
-        r.trail = r.n;
-    }
-    return r;
-}
-
-__device__ __forceinline__ KcfGap kcf_gap_shfl_down(const KcfGap &a, int delta)
-{
-    KcfGap r;
-    r.n = __shfl_down_sync(0xffffffffu, a.n, delta);
-    r.obs = __shfl_down_sync(0xffffffffu, a.obs, delta);
-    r.lead = __shfl_down_sync(0xffffffffu, a.lead, delta);
-    r.trail = __shfl_down_sync(0xffffffffu, a.trail, delta);
-    r.vin = __shfl_down_sync(0xffffffffu, a.vin, delta);
-    r.inner = __shfl_down_sync(0xffffffffu, a.inner, delta);
-    r.has = __shfl_down_sync(0xffffffffu, a.has, delta);
-    r.starts = __shfl_down_sync(0xffffffffu, a.starts, delta);
-    r.sum = __shfl_down_sync(0xffffffffu, a.sum, delta);
-    return r;
-}
-
 // ------------------------------------------------------------------------------------------------------------
-// K3/K4.  One warp = one CTA takes a tile (KCF_TILE consecutive positions of one window) and walks it in chunks of
-// KCF_CHUNK positions.  Inside a chunk LANES own consecutive positions (position = 32 j + lane in iteration j), so
-// the ~(w+1)/2 neighbouring k-mers that share a minimizer — hence a 128-byte home line of the table — sit in the
-// same load instruction and the L1 coalescer turns their probes into ONE request for that line: the de-duplication
-// that makes the table's locality pay is done by the memory pipeline, not by code.  Nothing synchronises wider
-// than a warp; the warps of an SM drift apart and hide each other's latencies.
+// K3/K4.  One warp takes a tile (KCF_TILE consecutive positions of one window) and walks it in chunks of KCF_CHUNK
+// positions.  Inside a chunk LANES own consecutive positions (position = 32 j + lane in iteration j), so the
+// ~(w+1)/2 neighbouring k-mers that share a minimizer — hence a 128-byte home line of the table — sit in the same
+// load instruction and the L1 coalescer turns their probes into ONE request for that line: the de-duplication that
+// makes the table's locality pay is done by the memory pipeline, not by code.  Nothing synchronises wider than a
+// warp; the warps of an SM drift apart and hide each other's latencies.
 //
-//   stage    2-bit bases + validity bits of the chunk (+ 32-base halo) into shared memory
-//   hash     order hash of the m-mer ending at every position, then log2 doubling passes of a sliding minimum
-//   probe    per position: canonical k-mer, minimizer -> home line, two 32-byte loads (the 14 low key words),
-//            confirm on the high word, read the count; k-mers whose home mask names other lines go to a queue
+//   stage    the two bit planes + validity bits of the chunk (+ 64-base halo): one 32-base word triple per lane,
+//            cut out of the packed sequence with funnel shifts (segment junctions and window edges piecewise)
+//   hash     order hash of the m-mer ending at every position: a lane owns 16 consecutive positions, holds their
+//            bases in four registers and needs 2 shifts + 1 bit reversal per plane and position; then the sliding
+//            minimum over w of them in registers (four minima per lane and round)
+//   probe    per position: k-mer planes by funnel shift, other strand by bit reversal, minimizer -> home line, the
+//            line's S low key words + filter + mask word requested together, confirm on the high word, read the
+//            count; k-mers whose home mask names other lines go to a queue
 //   queue    searched one item per lane, densely (continuation lines are rare per k-mer but not per warp)
-//   fold     hit / valid bitmaps (one ballot per 32 positions) -> gap summary by bit tricks -> one shuffle reduction
+//   fold     hit / valid bitmaps (one ballot per 32 positions) -> gap summary by bit tricks -> one shuffle reduction;
+//            the tile's running summary lives in shared memory, not in registers
 // ------------------------------------------------------------------------------------------------------------
 #ifndef KCF_CHUNK
 #define KCF_CHUNK 512
@@ -124,12 +70,12 @@ __device__ __forceinline__ KcfGap kcf_gap_shfl_down(const KcfGap &a, int delta)
 #define KCF_MIN_WARPS 40 // resident warps per SM the register allocation is held to (measured best of 32 / 40 / 48)
 #endif
 #define KCF_WPC 2 // independent warps per CTA (an SM holds 32 CTAs at most)
-#define S_CODE_WORDS ((KCF_CHUNK + KCF_HALO) / 16 + 4)
-#define S_VALID_WORDS ((KCF_CHUNK + KCF_HALO) / 32 + 2)
+#define S_WORDS ((KCF_CHUNK + KCF_HALO) / 32 + 2) // staged 32-base words; two spare ones: the funnel shifts read past the last
 #define S_HASH_WORDS (((KCF_CHUNK + KCF_HALO + 127) / 128) * 128 + 16) // padded: the 4-wide sliding-minimum rounds read 16 words per lane
 #ifndef KCF_QCAP
 #define KCF_QCAP 64
 #endif
+static_assert(KCF_CHUNK == 512 && KCF_HALO == 64, "the hash phase gives every lane 16 positions of a 512-position chunk; the halo is two words");
 
 struct KcfQueueItem {
     unsigned long long key;
@@ -140,164 +86,76 @@ struct KcfQueueItem {
 struct __align__(16) KcfWarpSmem {
     KcfQueueItem queue[KCF_QCAP];
     uint32_t hash[S_HASH_WORDS];
-    uint32_t codes[S_CODE_WORDS];
-    uint32_t valid[S_VALID_WORDS];
+    uint2 planes[S_WORDS];          // .x = bit 0, .y = bit 1 of the base codes; staged position q = window position o - KCF_HALO + q
+    uint32_t valid[S_WORDS];
     uint32_t hit[KCF_CHUNK / 32];   // bit = k-mer observed (count >= min_count)
     uint32_t okw[KCF_CHUNK / 32];   // bit = a k-mer ends at this position
     uint32_t start[KCF_CHUNK / 32]; // bit = k-mer opens a valid stretch (EFFLEN)
+    KcfGap acc;                     // summary of the tile's chunks done so far
 };
 
-
-// gap summary of 32 consecutive positions from their bitmaps (bit i = position i): `vw` marks the positions where a
-// k-mer ends, `hw` (a subset) the observed ones.  Positions without a k-mer are transparent: a miss run continues
-// across them (GetVariants.java:217-245 runs over the compacted k-mer list).
-__device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, uint32_t sw, uint64_t sum, uint32_t k)
+// 32 consecutive window positions [P, P + 32) as plane / validity words (bit i = position P + i).  Positions outside the
+// window read as invalid: k-mers never cross a window's edges (Window.java:224-226).  A window is the concatenation of its
+// segments (GTF.java:240-244), so a word may be assembled from several of them.
+__device__ __forceinline__ void kcf_stage_word(const KcfScreenParams &p, const kcf_window_t &win, uint32_t wlen, int32_t P, uint32_t &o0,
+                                               uint32_t &o1, uint32_t &ov)
 {
-    KcfGap a;
-    a.n = __popc(vw);
-    a.obs = __popc(hw);
-    a.starts = __popc(sw);
-    a.sum = sum;
-    a.vin = a.inner = 0;
-    a.has = hw != 0;
-    if (!hw) {
-        a.lead = a.trail = a.n;
-        return a;
-    }
-    const uint32_t first = __ffs(hw) - 1, last = 31 - __clz(hw);
-    a.lead = __popc(vw & ((1u << first) - 1u));
-    a.trail = __popc(vw & ~(0xFFFFFFFFu >> (31 - last)));
-    uint32_t zr = ~hw & (0xFFFFFFFFu >> (31 - last)) & ~((1u << first) - 1u); // non-hit positions between two hits
-    while (zr) {
-        const uint32_t s = __ffs(zr) - 1;
-        const uint32_t e = __ffs(~(zr >> s)) - 1; // length of this run of non-hit positions (ends before bit `last`)
-        const uint32_t gm = ((1u << e) - 1u) << s;
-        const uint32_t glen = __popc(vw & gm);
-        if (glen) {
-            a.vin += 1;
-            a.inner += kcf_gap_distance(glen, k);
+    o0 = o1 = ov = 0;
+    int32_t a = max(P, 0);
+    const int32_t e = (int32_t)min((int64_t)P + 32, (int64_t)wlen);
+    if (a >= e) return;
+    uint32_t s = 0;
+    if (win.n_segs > 1) {
+        uint32_t lo = 0, hi = win.n_segs; // last segment with seg_off <= a
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (p.seg_off[win.first_seg + mid] <= (uint32_t)a) lo = mid + 1;
+            else hi = mid;
         }
-        zr &= ~gm;
+        s = lo - 1;
     }
-    return a;
+    while (a < e) {
+        const uint32_t so = win.n_segs > 1 ? p.seg_off[win.first_seg + s] : 0u;
+        const uint32_t send = s + 1 < win.n_segs ? p.seg_off[win.first_seg + s + 1] : wlen;
+        const int32_t b = min(e, (int32_t)send);
+        const kcf_segment_t sg = p.segs[win.first_seg + s];
+        const KcfSeqDev sq = p.seqs[sg.seq_id];
+        const uint32_t sp = (uint32_t)sg.start0 + ((uint32_t)a - so);
+        const uint32_t wi = sp >> 5, sh = sp & 31u;
+        const uint2 c0 = __ldg(reinterpret_cast<const uint2 *>(sq.codes) + wi), c1 = __ldg(reinterpret_cast<const uint2 *>(sq.codes) + wi + 1);
+        const uint32_t v0 = __ldg(sq.valid + wi), v1 = __ldg(sq.valid + wi + 1);
+        const uint32_t nb = (uint32_t)(b - a), sl = (uint32_t)(a - P);
+        const uint32_t m = nb >= 32u ? 0xFFFFFFFFu : ((1u << nb) - 1u);
+        o0 |= (__funnelshift_r(c0.x, c1.x, sh) & m) << sl;
+        o1 |= (__funnelshift_r(c0.y, c1.y, sh) & m) << sl;
+        ov |= (__funnelshift_r(v0, v1, sh) & m) << sl;
+        a = b;
+        ++s;
+    }
 }
 
-// One probe: canonical k-mer ending at chunk position 32 JJ + lane, its home line, search, publish the warp's bitmaps,
-// queue what needs other lines.
-#define KCF_PROBE(JJ)                                                                                                      \
-    do {                                                                                                               \
-        const uint32_t cpos = 32 * (JJ) + lane;     /* chunk position of this lane's k-mer end */                      \
-        const uint32_t q = KCF_HALO + cpos;         /* the same in staged coordinates */                               \
-        const uint32_t b0 = q - k + 1;              /* first base */                                                   \
-        const bool ok = (W.okw[JJ] >> lane) & 1u; /* a k-mer ends here (bitmap built once per chunk) */                \
-        uint64_t key; /* canonical k-mer (Kmer.java:57-79, 232-252, 300-338) */                                        \
-        {                                                                                                              \
-            const uint32_t wi = b0 >> 4, sh = (b0 & 15u) * 2u;                                                         \
-            const uint32_t c0 = W.codes[wi], c1 = W.codes[wi + 1], c2 = W.codes[wi + 2];                               \
-            const uint64_t X = (((uint64_t)__funnelshift_r(c1, c2, sh) << 32) | __funnelshift_r(c0, c1, sh)) & g.kmask; \
-            const uint64_t fw = kcf_pair_reverse(X, g.kshift); /* first base most significant */                       \
-            const uint64_t rc = (~X) & g.kmask;                /* reverse complement value */                          \
-            key = (g.both_strands && rc < fw) ? rc : fw;       /* unsigned-smaller word, tie keeps forward */          \
-        }                                                                                                              \
-        /* minimizer = min over the w m-mers ending at q-w+1 .. q -> home line */                                      \
-        const uint32_t h0 = q - g.w + 1;                                                                               \
-        const uint32_t home = kcf_home_line(FASTMIN ? W.hash[h0] : min(W.hash[h0], W.hash[h0 + g.w - P2]), g);          \
-        const uint32_t lhome = OWNED ? home - (uint32_t)g.line_lo : home; /* local line index */                       \
-        const bool mine = !OWNED || lhome < (uint32_t)g.n_local;          /* this rank holds the k-mer's home line */  \
-        const uint8_t *L = p.table + (uint64_t)lhome * KCF_LINE_BYTES;                                                 \
-        uint32_t cnt = 0, mask = 0;                                                                                    \
-        bool pending = false;                                                                                          \
-        if (ok && mine) {                                                                                              \
-            const bool inl = KCF_KEY_IN_LINES(key);                                                                    \
-            /* filter and mask words of the line travel with its key words: a miss needs them, and asking for them */  \
-            /* only after the compare would add a dependent round trip */                                              \
-            const uint32_t w31 = __ldg(reinterpret_cast<const uint32_t *>(L) + 31);                                    \
-            const unsigned long long fword = S == 13 ? __ldg(reinterpret_cast<const unsigned long long *>(L + 104))    \
-                                                     : (unsigned long long)__ldg(reinterpret_cast<const uint32_t *>(L + 120)); \
-            if (!(inl && kcf_probe_line<S>(L, key, cnt))) {                                                            \
-                cnt = 0;                                                                                               \
-                /* absent unless the home line's filter says a key like this one lives outside it */                   \
-                const bool maybe = S == 13 ? kcf_filter_pass64(fword, key) : kcf_filter_pass32((uint32_t)fword, key);  \
-                if (maybe) {                                                                                           \
-                    mask = kcf_mask_from_word31(w31);                                                                  \
-                    if (inl && (mask & 0x7FFEu)) pending = true;                                                       \
-                    else if ((mask >> KCF_STASH_BIT) & 1u) cnt = kcf_stash_find(p.stash, g, key);                      \
-                }                                                                                                      \
-            }                                                                                                          \
-        }                                                                                                              \
-        const bool hit = ok && (int32_t)cnt >= p.min_count; /* Java int compare (GetVariants.java:224) */              \
-        if (hit) sum += cnt;                                                                                           \
-        const uint32_t hb = __ballot_sync(0xffffffffu, hit);                                                           \
-        const uint32_t pb = __ballot_sync(0xffffffffu, pending);                                                       \
-        W.hit[JJ] = hb; /* every lane stores the same word; the queue flush ORs late hits into it, after this store */  \
-        if (COUNTS) p.counts_out[(tile - p.counts_tile0) * KCF_TILE + chunk * KCF_CHUNK + cpos] = ok ? (int32_t)cnt : -1; \
-        if (pb) {                                                                                                      \
-            if (pending) {                                                                                             \
-                KcfQueueItem it;                                                                                       \
-                it.key = key;                                                                                          \
-                it.home = home;                                                                                        \
-                it.info = (cpos << 16) | (mask & 0xFFFEu);                                                             \
-                W.queue[qn + __popc(pb & ((1u << lane) - 1u))] = it;                                                   \
-            }                                                                                                          \
-            qn += __popc(pb);                                                                                          \
-            if (qn + 32 > KCF_QCAP) KCF_FLUSH_QUEUE(); /* nearly full: search it now */                                \
-        }                                                                                                              \
-    } while (0)
+// order hashes of the m-mers ending at the 16 staged positions q0 .. q0 + 15 (q0 a multiple of 16, q0 >= m - 1): the lane
+// holds the bases it needs — staged bits [q0 - m + 1, q0 + 16) of both planes — in two 64-bit windows
+__device__ __forceinline__ void kcf_hash16(KcfWarpSmem &W, uint32_t q0, uint32_t m, uint32_t mm)
+{
+    const uint32_t s0 = q0 + 1u - m, wi = s0 >> 5, off = s0 & 31u;
+    const uint2 a = W.planes[wi], b = W.planes[wi + 1], c = W.planes[wi + 2];
+    const uint32_t lo0 = __funnelshift_r(a.x, b.x, off), hi0 = __funnelshift_r(b.x, c.x, off);
+    const uint32_t lo1 = __funnelshift_r(a.y, b.y, off), hi1 = __funnelshift_r(b.y, c.y, off);
+    uint32_t h[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) h[i] = kcf_mmer_order(__funnelshift_r(lo0, hi0, i), __funnelshift_r(lo1, hi1, i), m, mm);
+    uint4 *dst = reinterpret_cast<uint4 *>(&W.hash[q0]);
+    dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
+    dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
+    dst[2] = make_uint4(h[8], h[9], h[10], h[11]);
+    dst[3] = make_uint4(h[12], h[13], h[14], h[15]);
+}
 
-// EXTRACT mode: the front half of a probe only — canonical k-mer, validity, home line — written out for the exchange
-#define KCF_EXTRACT(JJ)                                                                                                \
-    do {                                                                                                               \
-        const uint32_t cpos = 32 * (JJ) + lane;                                                                        \
-        const uint32_t q = KCF_HALO + cpos;                                                                            \
-        const uint32_t b0 = q - k + 1;                                                                                 \
-        const bool ok = (W.okw[JJ] >> lane) & 1u;                                                                      \
-        uint64_t key;                                                                                                  \
-        {                                                                                                              \
-            const uint32_t wi = b0 >> 4, sh = (b0 & 15u) * 2u;                                                         \
-            const uint32_t c0 = W.codes[wi], c1 = W.codes[wi + 1], c2 = W.codes[wi + 2];                               \
-            const uint64_t X = (((uint64_t)__funnelshift_r(c1, c2, sh) << 32) | __funnelshift_r(c0, c1, sh)) & g.kmask; \
-            const uint64_t fw = kcf_pair_reverse(X, g.kshift);                                                         \
-            const uint64_t rc = (~X) & g.kmask;                                                                        \
-            key = (g.both_strands && rc < fw) ? rc : fw;                                                               \
-        }                                                                                                              \
-        const uint32_t h0 = q - g.w + 1;                                                                               \
-        const uint32_t home = kcf_home_line(FASTMIN ? W.hash[h0] : min(W.hash[h0], W.hash[h0 + g.w - P2]), g);          \
-        p.x_keys[base + cpos] = key;                                                                                   \
-        p.x_homes[base + cpos] = ok ? home : 0xFFFFFFFFu;                                                              \
-        if (lane == 0) {                                                                                               \
-            p.x_okw[(base >> 5) + (JJ)] = W.okw[JJ];                                                                   \
-            p.x_start[(base >> 5) + (JJ)] = W.start[JJ];                                                               \
-        }                                                                                                              \
-    } while (0)
-
-// search the queued k-mers in the lines their home masks name; one item per lane
-#define KCF_FLUSH_QUEUE()                                                                                              \
-    do {                                                                                                               \
-        __syncwarp();                                                                                                  \
-        _Pragma("unroll 1") for (uint32_t t = lane; t < qn; t += 32)                                                   \
-        {                                                                                                              \
-            const KcfQueueItem it = W.queue[t];                                                                        \
-            uint32_t m2 = it.info & 0x7FFEu, c2 = 0;                                                                   \
-            bool found = false;                                                                                        \
-            while (m2 && !found) {                                                                                     \
-                const uint32_t d = __ffs(m2) - 1;                                                                      \
-                m2 &= m2 - 1;                                                                                          \
-                found = kcf_probe_line<S>(p.table + (uint64_t)kcf_line_wrap(it.home, d, g) * KCF_LINE_BYTES, it.key, c2); \
-            }                                                                                                          \
-            if (!found && (it.info & (1u << KCF_STASH_BIT))) c2 = kcf_stash_find(p.stash, g, it.key);                  \
-            const uint32_t pc = it.info >> 16;                                                                         \
-            if ((int32_t)c2 >= p.min_count) {                                                                          \
-                sum += c2;                                                                                             \
-                atomicOr(&W.hit[pc >> 5], 1u << (pc & 31u));                                                           \
-            }                                                                                                          \
-            if (COUNTS) p.counts_out[(tile - p.counts_tile0) * KCF_TILE + chunk * KCF_CHUNK + pc] = (int32_t)c2; \
-        }                                                                                                              \
-        qn = 0;                                                                                                        \
-        __syncwarp();                                                                                                  \
-    } while (0)
-
-template <int S, int MODE>
-__global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_screen_kernel(KcfScreenParams p, KcfTableGeom g)
+// SPEC = the common geometry compiled in: both-strands database and 4 <= w <= 13 (register sliding minimum); SPEC = false
+// reads both from the geometry at run time (any m, non-canonical databases)
+template <int S, int MODE, bool SPEC>
+__global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_screen_kernel(const KcfScreenParams p, const KcfTableGeom g)
 {
     constexpr bool COUNTS = MODE == KCF_MODE_COUNTS, EXTRACT = MODE == KCF_MODE_EXTRACT, OWNED = MODE == KCF_MODE_OWNED;
     __shared__ __align__(16) KcfWarpSmem kcf_warp_smem[KCF_WPC];
@@ -305,9 +163,11 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
 
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t k = g.k;
-    uint32_t P2 = 1; // largest power of two <= w: the sliding minimum is built by doubling up to it
-    while (2 * P2 <= g.w) P2 *= 2;
-    const bool FASTMIN = g.w >= 4 && g.w <= 13; // register sliding minimum (warp uniform)
+    const bool FASTMIN = SPEC || (g.w >= 4 && g.w <= 13); // register sliding minimum (warp uniform)
+    const bool BOTH = SPEC || g.both_strands != 0;
+    uint32_t P2 = 1; // largest power of two <= w: the general sliding minimum is built by doubling up to it
+    if (!SPEC)
+        while (2 * P2 <= g.w) P2 *= 2;
 
     for (;;) {
         // ---- take a tile: KCF_TILE consecutive positions of one window ----
@@ -330,115 +190,47 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
         w = __shfl_sync(0xffffffffu, w, 0);
         const kcf_window_t win = p.wins[w];
         const uint32_t wlen = p.win_len[w];
-        const int64_t o_tile = (int64_t)(tile - p.tile_first[w]) * KCF_TILE; // window position of the tile's first k-mer end
+        const int32_t o_tile = (int32_t)((tile - p.tile_first[w]) * KCF_TILE); // window position of the tile's first k-mer end
 
-        KcfGap acc; // summary of the chunks done so far (meaningful in lane 0)
-        acc.n = acc.obs = acc.lead = acc.trail = acc.vin = acc.inner = acc.has = acc.starts = 0;
-        acc.sum = 0;
-        uint32_t carry_hash = 0; // order hash of position KCF_CHUNK + lane of the previous chunk = position lane of this one
+        if (lane == 0) W.acc = kcf_gap_zero();
+        uint32_t carry_hash = 0; // order hash of staged position KCF_CHUNK + 32 + lane of the previous chunk = position 32 + lane of this one
         unsigned long long owned_sum = 0; // OWNED mode: Σcount of this rank's hits in the tile
 
         for (uint32_t chunk = 0; chunk < KCF_TILE / KCF_CHUNK; ++chunk) {
-            const int64_t o = o_tile + (int64_t)chunk * KCF_CHUNK;
-            if (o >= (int64_t)wlen) break;
-            const int g0 = chunk > 0 ? KCF_HALO / 8 : 0; // groups of 8 positions carried over from the previous chunk
+            const int32_t o = o_tile + (int32_t)(chunk * KCF_CHUNK);
+            if (o >= (int32_t)wlen) break;
 
-            // ---- stage bases [o - HALO, o + CHUNK): 8 positions per lane and step ----
-            if (chunk > 0) {
-                uint32_t c16 = 0, v8 = 0;
-                if (lane < KCF_HALO / 8) {
-                    c16 = reinterpret_cast<uint16_t *>(W.codes)[KCF_CHUNK / 8 + lane];
-                    v8 = reinterpret_cast<uint8_t *>(W.valid)[KCF_CHUNK / 8 + lane];
+            // ---- stage window positions [o - HALO, o + CHUNK): one word triple per lane; the halo of a later chunk is the
+            // previous chunk's tail ----
+            {
+                uint2 tp = make_uint2(0u, 0u);
+                uint32_t tv = 0;
+                if (chunk > 0 && lane < KCF_HALO / 32) {
+                    tp = W.planes[KCF_CHUNK / 32 + lane];
+                    tv = W.valid[KCF_CHUNK / 32 + lane];
                 }
                 __syncwarp();
-                if (lane < KCF_HALO / 8) {
-                    reinterpret_cast<uint16_t *>(W.codes)[lane] = (uint16_t)c16;
-                    reinterpret_cast<uint8_t *>(W.valid)[lane] = (uint8_t)v8;
+                if (lane < S_WORDS) {
+                    if (lane >= (KCF_CHUNK + KCF_HALO) / 32) tp = make_uint2(0u, 0u), tv = 0; // the spare words
+                    else if (chunk == 0 || lane >= KCF_HALO / 32) kcf_stage_word(p, win, wlen, o - KCF_HALO + 32 * (int32_t)lane, tp.x, tp.y, tv);
+                    W.planes[lane] = tp;
+                    W.valid[lane] = tv;
                 }
-            }
-#pragma unroll 1
-            for (int u = g0 + (int)lane; u < (KCF_CHUNK + KCF_HALO) / 8; u += 32) {
-                const int64_t pos0 = o - KCF_HALO + 8 * (int64_t)u;
-                uint32_t c16 = 0, v8 = 0;
-                if (pos0 + 8 > 0 && pos0 < (int64_t)wlen) {
-                    // the segment holding pos0 (a fixed / sliding window has one; a gene / transcript window one per merged locus)
-                    uint32_t s0 = 0;
-                    bool inside = pos0 >= 0 && pos0 + 8 <= (int64_t)wlen;
-                    if (inside && win.n_segs > 1) {
-                        uint32_t lo = 0, hi = win.n_segs; // last segment with seg_off <= pos0
-                        while (lo < hi) {
-                            uint32_t mid = (lo + hi) >> 1;
-                            if (p.seg_off[win.first_seg + mid] <= (uint32_t)pos0) lo = mid + 1;
-                            else hi = mid;
-                        }
-                        s0 = lo - 1;
-                        const uint32_t seg_end = s0 + 1 < win.n_segs ? p.seg_off[win.first_seg + s0 + 1] : wlen;
-                        inside = (uint32_t)pos0 + 8 <= seg_end;
-                    }
-                    if (inside) {
-                        // all 8 positions inside one segment: two funnel shifts over the packed words
-                        const kcf_segment_t sg = p.segs[win.first_seg + s0];
-                        const KcfSeqDev sq = p.seqs[sg.seq_id];
-                        const uint32_t sp = (uint32_t)sg.start0 + ((uint32_t)pos0 - (win.n_segs > 1 ? p.seg_off[win.first_seg + s0] : 0u));
-                        const uint32_t wi = sp >> 4, vi = sp >> 5;
-                        c16 = __funnelshift_r(__ldg(sq.codes + wi), __ldg(sq.codes + wi + 1), (sp & 15u) * 2u) & 0xFFFFu;
-                        v8 = __funnelshift_r(__ldg(sq.valid + vi), __ldg(sq.valid + vi + 1), sp & 31u) & 0xFFu;
-                    } else {
-                        // window edges and segment junctions: base by base
-                        uint32_t s = 0;
-                        bool have = false;
-                        for (int j = 0; j < 8; ++j) {
-                            const int64_t pos = pos0 + j;
-                            if (pos < 0 || pos >= (int64_t)wlen) continue;
-                            if (!have) {
-                                uint32_t lo = 0, hi = win.n_segs; // last segment with seg_off <= pos
-                                while (lo < hi) {
-                                    uint32_t mid = (lo + hi) >> 1;
-                                    if (p.seg_off[win.first_seg + mid] <= (uint32_t)pos) lo = mid + 1;
-                                    else hi = mid;
-                                }
-                                s = lo - 1;
-                                have = true;
-                            }
-                            while (s + 1 < win.n_segs && p.seg_off[win.first_seg + s + 1] <= (uint32_t)pos) ++s;
-                            const kcf_segment_t sg = p.segs[win.first_seg + s];
-                            const KcfSeqDev sq = p.seqs[sg.seq_id];
-                            const uint32_t sp = (uint32_t)sg.start0 + ((uint32_t)pos - p.seg_off[win.first_seg + s]);
-                            const uint32_t c = (__ldg(sq.codes + (sp >> 4)) >> ((sp & 15u) * 2u)) & 3u;
-                            const uint32_t v = (__ldg(sq.valid + (sp >> 5)) >> (sp & 31u)) & 1u;
-                            c16 |= c << (2 * j);
-                            v8 |= v << j;
-                        }
-                    }
-                }
-                reinterpret_cast<uint16_t *>(W.codes)[u] = (uint16_t)c16;
-                reinterpret_cast<uint8_t *>(W.valid)[u] = (uint8_t)v8;
             }
             __syncwarp();
 
-            // ---- order hash of the m-mer ending at every staged position (shared by the w k-mers that contain it) ----
-            if (chunk > 0) W.hash[lane] = carry_hash;
+            // ---- order hash of the m-mer ending at every staged position from 32 on (the minimizer window of the chunk's
+            // first k-mer starts at 65 - w >= 33) ----
+            if (chunk > 0) W.hash[32 + lane] = carry_hash;
 #pragma unroll 1
-            for (int u = g0 + (int)lane; u < (KCF_CHUNK + KCF_HALO) / 8; u += 32) {
-                const int q0 = 8 * u;
-                const int b0 = q0 - (int)g.m + 1; // first base of the m-mer ending at q0
-                const int b0c = b0 > 0 ? b0 : 0;  // positions whose m-mer starts before the halo are never used
-                const uint32_t wi = (uint32_t)b0c >> 4, sh = ((uint32_t)b0c & 15u) * 2u;
-                const uint64_t lo = ((uint64_t)W.codes[wi + 1] << 32) | W.codes[wi];
-                const uint64_t E = sh ? ((lo >> sh) | ((uint64_t)W.codes[wi + 2] << (64 - sh))) : lo; // 32 bases from b0c
-                const uint64_t R = kcf_pair_reverse64(~E);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int j = i + (b0 - b0c);
-                    W.hash[8 * u + i] = kcf_mmer_order(E, R, (uint32_t)(j > 0 ? j : 0), g);
-                }
-            }
+            for (uint32_t r = chunk == 0 ? 0u : 1u; r < 2; ++r) // r = 0: the halo positions 32 .. 63 of a tile's first chunk (two lanes)
+                if (r == 1 || lane < 2) kcf_hash16(W, r == 0 ? 32 + 16 * lane : KCF_HALO + 16 * lane, g.m, g.mm);
             __syncwarp();
-            carry_hash = W.hash[KCF_CHUNK + lane];
+            carry_hash = W.hash[KCF_CHUNK + 32 + lane];
             // sliding minimum over w consecutive order hashes, in place: afterwards hash[q] = min over [q, q + w) (fast path) or
             // min over [q, q + P2) (general path; the probe then combines two of them)
             if (FASTMIN) {
-                // 4 <= w <= 13 (the automatic choice w = S - 1 always is): a lane produces 4 consecutive minima per round from
+                // 4 <= w <= 13 (the automatic choice w = S - 2 always is): a lane produces 4 consecutive minima per round from
                 // the 13 hashes it holds in registers plus 3 more; the part common to the four windows is reduced once.
                 // A round rewrites [128 r, 128 r + 128) after every lane has read what it needs from it; later rounds only
                 // read higher positions.
@@ -461,13 +253,13 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
                     if (wv > 10) core = min(core, vc.z);
                     if (wv > 11) core = min(core, vc.w);
                     if (wv > 12) core = min(core, v12);
-                    uint4 o;
-                    o.x = min(min(core, va.x), min(va.y, va.z));
-                    o.y = min(min(core, va.y), min(va.z, t0));
-                    o.z = min(min(core, va.z), min(t0, t1));
-                    o.w = min(min(core, t0), min(t1, t2));
+                    uint4 ov;
+                    ov.x = min(min(core, va.x), min(va.y, va.z));
+                    ov.y = min(min(core, va.y), min(va.z, t0));
+                    ov.z = min(min(core, va.z), min(t0, t1));
+                    ov.w = min(min(core, t0), min(t1, t2));
                     __syncwarp();
-                    *reinterpret_cast<uint4 *>(&W.hash[base]) = o;
+                    *reinterpret_cast<uint4 *>(&W.hash[base]) = ov;
                     __syncwarp();
                 }
             } else {
@@ -490,7 +282,7 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
             // bits q-k+1 .. q are all set (Fasta.java:99-104), built from runs of 1, 2, 4, .. bits; a k-mer opens a valid
             // stretch when the one ending one position earlier is not valid (EFFLEN, Fasta.java:140-167)
             if (lane < KCF_CHUNK / 32) {
-                const uint64_t v64 = ((uint64_t)W.valid[lane + 1] << 32) | W.valid[lane]; // top half = this lane's 32 positions
+                const uint64_t v64 = ((uint64_t)W.valid[KCF_HALO / 32 + lane] << 32) | W.valid[KCF_HALO / 32 - 1 + lane]; // top half = this lane's 32 positions
                 uint64_t a = v64, run = ~0ULL;
                 uint32_t pos = 0;
 #pragma unroll
@@ -507,21 +299,109 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
             }
             __syncwarp();
 
-            if (EXTRACT) {
-                const uint64_t base = (tile - p.tile_begin) * KCF_TILE + (uint64_t)chunk * KCF_CHUNK;
-                const uint32_t np = (uint32_t)min((int64_t)KCF_CHUNK, (int64_t)wlen - o);
-#pragma unroll 1
-                for (uint32_t j = 0; 32 * j < np; ++j) KCF_EXTRACT(j);
-                continue;
-            }
-            // ---- probe: lanes own consecutive positions ----
-            uint64_t sum = 0;  // Σ count over this lane's observed k-mers
-            uint32_t qn = 0;   // queue length (warp uniform)
-            const uint32_t npos = (uint32_t)min((int64_t)KCF_CHUNK, (int64_t)wlen - o);
+            const uint32_t npos = (uint32_t)min((int32_t)KCF_CHUNK, (int32_t)wlen - o);
             const uint32_t J = (npos + 31) / 32;
+            unsigned long long sum = 0; // Σ count over this lane's observed k-mers
+            uint32_t qn = 0;            // queue length (warp uniform)
+
+            // search the queued k-mers in the lines their home masks name; one item per lane
+            auto flush_queue = [&]() {
+                __syncwarp();
 #pragma unroll 1
-            for (uint32_t j = 0; j < J; ++j) KCF_PROBE(j);
-            if (qn) KCF_FLUSH_QUEUE();
+                for (uint32_t t = lane; t < qn; t += 32) {
+                    const KcfQueueItem it = W.queue[t];
+                    uint32_t m2 = it.info & 0x7FFEu, c2 = 0;
+                    bool found = false;
+                    while (m2 && !found) {
+                        const uint32_t d = __ffs(m2) - 1;
+                        m2 &= m2 - 1;
+                        found = kcf_probe_line<S>(p.table + (uint64_t)kcf_line_wrap(it.home, d, g) * KCF_LINE_BYTES, it.key, c2);
+                    }
+                    if (!found && (it.info & (1u << KCF_STASH_BIT))) c2 = kcf_stash_find(p.stash, g, it.key);
+                    const uint32_t pc = it.info >> 16;
+                    if ((int32_t)c2 >= p.min_count) {
+                        sum += c2;
+                        atomicOr(&W.hit[pc >> 5], 1u << (pc & 31u));
+                    }
+                    if (COUNTS) p.counts_out[(tile - p.counts_tile0) * KCF_TILE + chunk * KCF_CHUNK + pc] = (int32_t)c2;
+                }
+                qn = 0;
+                __syncwarp();
+            };
+
+            // ---- probe: lanes own consecutive positions ----
+#pragma unroll 1
+            for (uint32_t j = 0; j < J; ++j) {
+                const uint32_t cpos = 32 * j + lane;  // chunk position of this lane's k-mer end
+                const uint32_t q = KCF_HALO + cpos;   // the same in staged coordinates
+                const bool ok = (W.okw[j] >> lane) & 1u; // a k-mer ends here (bitmap built once per chunk)
+                // table key: the k-mer's bit planes; for a both-strands database the smaller strand (kcf_lookup.cuh) — what the
+                // loader stored the record spelling this k-mer's canonical form under (Kmer.java:57-79)
+                uint32_t klo, khi;
+                {
+                    const uint32_t b0 = q - k + 1, wi = b0 >> 5, sh = b0 & 31u;
+                    const uint2 a = W.planes[wi], b = W.planes[wi + 1];
+                    klo = __funnelshift_r(a.x, b.x, sh) & g.km;
+                    khi = __funnelshift_r(a.y, b.y, sh) & g.km;
+                    if (BOTH) kcf_plane_canonical(klo, khi, kcf_plane_rc(klo, k, g.km), kcf_plane_rc(khi, k, g.km), klo, khi);
+                }
+                const uint64_t key = ((uint64_t)khi << 32) | klo;
+                // minimizer = min over the w m-mers ending at q-w+1 .. q -> home line
+                const uint32_t h0 = q - g.w + 1;
+                const uint32_t home = kcf_home_line(FASTMIN ? W.hash[h0] : min(W.hash[h0], W.hash[h0 + g.w - P2]), g);
+                if (EXTRACT) {
+                    const uint64_t base = (tile - p.tile_begin) * KCF_TILE + (uint64_t)chunk * KCF_CHUNK;
+                    p.x_keys[base + cpos] = key;
+                    p.x_homes[base + cpos] = ok ? home : 0xFFFFFFFFu;
+                    if (lane == 0) {
+                        p.x_okw[(base >> 5) + j] = W.okw[j];
+                        p.x_start[(base >> 5) + j] = W.start[j];
+                    }
+                    continue;
+                }
+                const uint32_t lhome = OWNED ? home - (uint32_t)g.line_lo : home; // local line index
+                const bool mine = !OWNED || lhome < (uint32_t)g.n_local;          // this rank holds the k-mer's home line
+                const uint8_t *L = p.table + (uint64_t)lhome * KCF_LINE_BYTES;
+                uint32_t cnt = 0, mask = 0;
+                bool pending = false;
+                if (ok && mine) {
+                    const bool inl = klo != KCF_EMPTY_LO;
+                    // filter and mask words of the line travel with its key words: a miss needs them, and asking for them
+                    // only after the compare would add a dependent round trip
+                    const uint32_t w31 = __ldg(reinterpret_cast<const uint32_t *>(L) + 31);
+                    const unsigned long long fword = S == 13 ? __ldg(reinterpret_cast<const unsigned long long *>(L + 104))
+                                                             : (unsigned long long)__ldg(reinterpret_cast<const uint32_t *>(L + 120));
+                    if (!(inl && kcf_probe_line<S>(L, key, cnt))) {
+                        cnt = 0;
+                        // absent unless the home line's filter says a key like this one lives outside it
+                        const bool maybe = S == 13 ? kcf_filter_pass64(fword, key) : kcf_filter_pass32((uint32_t)fword, key);
+                        if (maybe) {
+                            mask = kcf_mask_from_word31(w31);
+                            if (inl && (mask & 0x7FFEu)) pending = true;
+                            else if ((mask >> KCF_STASH_BIT) & 1u) cnt = kcf_stash_find(p.stash, g, key);
+                        }
+                    }
+                }
+                const bool hit = ok && (int32_t)cnt >= p.min_count; // Java int compare (GetVariants.java:224)
+                if (hit) sum += cnt;
+                const uint32_t hb = __ballot_sync(0xffffffffu, hit);
+                const uint32_t pb = __ballot_sync(0xffffffffu, pending);
+                if (lane == 0) W.hit[j] = hb; // the queue flush ORs late hits into it, after this store
+                if (COUNTS) p.counts_out[(tile - p.counts_tile0) * KCF_TILE + chunk * KCF_CHUNK + cpos] = ok ? (int32_t)cnt : -1;
+                if (pb) {
+                    if (pending) {
+                        KcfQueueItem it;
+                        it.key = key;
+                        it.home = home;
+                        it.info = (cpos << 16) | (mask & 0xFFFEu);
+                        W.queue[qn + __popc(pb & ((1u << lane) - 1u))] = it;
+                    }
+                    qn += __popc(pb);
+                    if (qn + 32 > KCF_QCAP) flush_queue(); // nearly full: search it now
+                }
+            }
+            if (EXTRACT) continue;
+            if (qn) flush_queue();
             __syncwarp();
             if (OWNED) {
                 // this rank's share of the chunk: bitmaps out, Σcount kept per tile; the gap summaries are folded after the
@@ -541,20 +421,20 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
 
             // ---- fold: lane j summarises positions [32 j, 32 j + 32), one ordered shuffle reduction per chunk ----
             constexpr uint32_t NWORDS = KCF_CHUNK / 32;
-            KcfGap a = kcf_gap_from_bits(lane < NWORDS ? W.hit[lane] : 0u, lane < NWORDS ? W.okw[lane] : 0u, lane < NWORDS ? W.start[lane] : 0u, 0, k);
-#pragma unroll 1
-            for (int d = 1; d < 32; d <<= 1) {
-                KcfGap b = kcf_gap_shfl_down(a, d);
-                if (lane + d < 32) a = kcf_gap_combine(a, b, k);
-                sum += __shfl_down_sync(0xffffffffu, sum, d); // Σ count is not tied to positions: plain warp sum
+            KcfGap a = kcf_gap_from_bits(lane < NWORDS ? W.hit[lane] : 0u, lane < NWORDS ? W.okw[lane] : 0u, lane < NWORDS ? W.start[lane] : 0u, k);
+            a = kcf_gap_warp_reduce(a, lane, k);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, d); // Σ count is not tied to positions: plain warp sum
+            if (lane == 0) {
+                a.sum = sum;
+                W.acc = kcf_gap_combine(W.acc, a, k);
             }
-            a.sum = sum;
-            acc = kcf_gap_combine(acc, a, k);
             __syncwarp(); // the bitmaps are rewritten by the next chunk
         }
         if (OWNED) {
             if (lane == 0) p.x_sum[tile - p.tile_begin] = owned_sum;
-        } else if (!EXTRACT && lane == 0) p.tile_sum[tile] = acc;
+        } else if (!EXTRACT && lane == 0) p.tile_sum[tile] = W.acc;
+        __syncwarp();
     }
 }
 
@@ -765,6 +645,7 @@ extern "C" int kcf_plan_create(kcf_ctx *ctx, int32_t kmer_length, const kcf_wind
     plan->n_segs = n_segs;
     plan->n_tiles = tiles;
     plan->n_positions = positions;
+    plan->ref_generation = ctx->ref_generation;
     int rc = KCF_OK;
 #define PL_CUDA(call)                                                                                   \
     do {                                                                                                \
@@ -778,8 +659,8 @@ extern "C" int kcf_plan_create(kcf_ctx *ctx, int32_t kmer_length, const kcf_wind
         const uint64_t nw = std::max<uint64_t>(n_wins, 1), ns = std::max<uint64_t>(n_segs, 1);
         const uint64_t b_wins = up(nw * sizeof(kcf_window_t)), b_segs = up(ns * sizeof(kcf_segment_t)), b_off = up(ns * 4), b_len = up(nw * 4),
                        b_tf = up((n_wins + 1) * 8), b_ts = up(std::max<uint64_t>(tiles, 1) * sizeof(KcfGap) + 8), // +8: the tile counter lives at the end
-                       b_out = up(nw * sizeof(kcf_result_t));
-        const size_t total = b_wins + b_segs + b_off + b_len + b_tf + b_ts + b_out;
+                       b_out = up(nw * sizeof(kcf_result_t)), b_flags = up(FLAG_COUNT * sizeof(uint32_t));
+        const size_t total = b_wins + b_segs + b_off + b_len + b_tf + b_ts + b_out + b_flags;
         uint8_t *base = (uint8_t *)kcf_pool_get(ctx, total);
         if (!base && rc == KCF_OK) rc = kcf_fail(ctx, KCF_ERR_NOMEM, "device memory for a plan of %llu windows", (unsigned long long)n_wins);
         plan->d_block = base;
@@ -798,6 +679,8 @@ extern "C" int kcf_plan_create(kcf_ctx *ctx, int32_t kmer_length, const kcf_wind
             plan->d_tile_sum = reinterpret_cast<KcfGap *>(base);
             base += b_ts;
             plan->d_out = reinterpret_cast<kcf_result_t *>(base);
+            base += b_out;
+            plan->d_flags = reinterpret_cast<uint32_t *>(base);
         }
     }
     if (rc == KCF_OK && n_wins) {
@@ -827,6 +710,8 @@ int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t min_coun
     const bool owned = d_owned_hit != nullptr;
     if (!extract && !owned && db->part_world > 1)
         return kcf_fail(ctx, KCF_ERR_ARG, "this database holds slice %d of %d: screen it through the exchange calls (kcf_xchg_*)", db->part_rank, db->part_world);
+    if (plan->ref_generation != ctx->ref_generation)
+        return kcf_fail(ctx, KCF_ERR_ARG, "plan was created before kcf_ref_clear: its segments refer to sequences that no longer exist");
     int rc = kcf_sync_seqs(ctx);
     if (rc != KCF_OK) return rc;
     unsigned long long *d_counter = reinterpret_cast<unsigned long long *>(
@@ -862,16 +747,19 @@ int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t min_coun
     const size_t smem = 0; // the per-warp buffers are static shared memory
     void (*kern)(KcfScreenParams, KcfTableGeom);
     const int S = (int)db->geom.S;
-#define KCF_PICK(MODE) (S == 13 ? kcf_screen_kernel<13, MODE> : (S == 12 ? kcf_screen_kernel<12, MODE> : kcf_screen_kernel<10, MODE>))
+    // the common geometry (both-strands database, 4 <= w <= 13) runs the kernels that have it compiled in
+    const bool spec = db->geom.both_strands && db->geom.w >= 4 && db->geom.w <= 13;
+#define KCF_PICK_S(MODE, SP) (S == 13 ? kcf_screen_kernel<13, MODE, SP> : (S == 12 ? kcf_screen_kernel<12, MODE, SP> : kcf_screen_kernel<10, MODE, SP>))
+#define KCF_PICK(MODE) (spec ? KCF_PICK_S(MODE, true) : KCF_PICK_S(MODE, false))
     if (extract) kern = KCF_PICK(KCF_MODE_EXTRACT);
     else if (owned) kern = KCF_PICK(KCF_MODE_OWNED);
     else if (d_counts) kern = KCF_PICK(KCF_MODE_COUNTS);
     else kern = KCF_PICK(KCF_MODE_SCREEN);
 #undef KCF_PICK
+#undef KCF_PICK_S
     int per_sm = 0;
     KCF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * KCF_WPC, smem));
     const uint64_t n = tile_end - tile_begin;
-    if (const char *e = getenv("KCF_TUNE_WARPS")) per_sm = std::min(per_sm, std::max(atoi(e) / KCF_WPC, 1)); // occupancy experiments
     const unsigned grid = (unsigned)std::min<uint64_t>((n + KCF_WPC - 1) / KCF_WPC, (uint64_t)ctx->sm_count * std::max(per_sm, 1));
     if (grid) kern<<<grid, 32 * KCF_WPC, smem, ctx->stream>>>(p, db->geom);
     KCF_CUDA(ctx, cudaGetLastError());
@@ -884,14 +772,14 @@ extern "C" int kcf_plan_run(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t mi
     if (min_count < 1) return kcf_fail(ctx, KCF_ERR_ARG, "Minimum kmer count should be at least 1"); // GetVariants.java:383-385
     if (plan->k != db->info.kmer_length) return kcf_fail(ctx, KCF_ERR_ARG, "plan built for k=%d, database has k=%d", plan->k, db->info.kmer_length);
     KCF_CUDA(ctx, cudaSetDevice(ctx->device));
-    KCF_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, FLAG_COUNT * sizeof(uint32_t), ctx->stream));
+    KCF_CUDA(ctx, cudaMemsetAsync(plan->d_flags, 0, FLAG_COUNT * sizeof(uint32_t), ctx->stream)); // per plan: several may be queued before a fetch
     if (ctx->profiling) cudaEventRecord(ctx->ev[0], ctx->stream);
     int rc = kcf_launch_screen(ctx, db, plan, min_count, 0, plan->n_tiles, nullptr, false, nullptr, nullptr);
     if (rc != KCF_OK) return rc;
     if (ctx->profiling) cudaEventRecord(ctx->ev[1], ctx->stream);
     if (plan->n_wins) {
         kcf_finalize_kernel<<<(unsigned)((plan->n_wins + 127) / 128), 128, 0, ctx->stream>>>(
-            plan->d_tile_sum, plan->d_tile_first, plan->n_wins, (uint32_t)plan->k, w[0], w[1], w[2], plan->d_out, ctx->d_flags);
+            plan->d_tile_sum, plan->d_tile_first, plan->n_wins, (uint32_t)plan->k, w[0], w[1], w[2], plan->d_out, plan->d_flags);
         KCF_CUDA(ctx, cudaGetLastError());
     }
     if (ctx->profiling) {
@@ -909,11 +797,12 @@ extern "C" int kcf_plan_run(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t mi
 extern "C" int kcf_plan_finalize(kcf_ctx *ctx, kcf_plan *plan, const double w[3])
 {
     if (!ctx || !plan || !w || plan->ctx != ctx) return KCF_ERR_ARG;
+    if (plan->ref_generation != ctx->ref_generation) return kcf_fail(ctx, KCF_ERR_ARG, "plan was created before kcf_ref_clear");
     KCF_CUDA(ctx, cudaSetDevice(ctx->device));
-    KCF_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, FLAG_COUNT * sizeof(uint32_t), ctx->stream));
+    KCF_CUDA(ctx, cudaMemsetAsync(plan->d_flags, 0, FLAG_COUNT * sizeof(uint32_t), ctx->stream));
     if (plan->n_wins) {
         kcf_finalize_kernel<<<(unsigned)((plan->n_wins + 127) / 128), 128, 0, ctx->stream>>>(
-            plan->d_tile_sum, plan->d_tile_first, plan->n_wins, (uint32_t)plan->k, w[0], w[1], w[2], plan->d_out, ctx->d_flags);
+            plan->d_tile_sum, plan->d_tile_first, plan->n_wins, (uint32_t)plan->k, w[0], w[1], w[2], plan->d_out, plan->d_flags);
         KCF_CUDA(ctx, cudaGetLastError());
     }
     plan->weights[0] = w[0];
@@ -930,7 +819,7 @@ extern "C" int kcf_plan_fetch(kcf_ctx *ctx, kcf_plan *plan, kcf_result_t *out)
     KCF_CUDA(ctx, cudaSetDevice(ctx->device));
     uint32_t flags[FLAG_COUNT] = {0};
     if (plan->n_wins) KCF_CUDA(ctx, cudaMemcpyAsync(out, plan->d_out, plan->n_wins * sizeof(kcf_result_t), cudaMemcpyDeviceToHost, ctx->stream));
-    KCF_CUDA(ctx, cudaMemcpyAsync(flags, ctx->d_flags, sizeof flags, cudaMemcpyDeviceToHost, ctx->stream));
+    KCF_CUDA(ctx, cudaMemcpyAsync(flags, plan->d_flags, sizeof flags, cudaMemcpyDeviceToHost, ctx->stream));
     KCF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     // Data.java:101-103 — evaluated only for windows that reach the formula, left to right in double
     if (flags[FLAG_SCORE_USED] && plan->weights[0] + plan->weights[1] + plan->weights[2] != 1.0)

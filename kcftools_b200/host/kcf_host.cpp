@@ -877,13 +877,35 @@ int getVariations(GetVariantsOptions o)
     std::vector<std::string> sampleNames = java_split(o.sampleName, ',');
     const bool multi = prefixes.size() > 1;
     const bool multiDevice = multi && o.devices.size() > 1;
+    const bool shardedJob = !multi && o.devices.size() > 1; // ONE database, windows cut over the GPUs (GetVariants.java:129-151)
     if (multi && sampleNames.size() != prefixes.size())
         Logger::error(GV_CLASS, "Number of sample names (" + std::to_string(sampleNames.size()) + ") differs from the number of KMC databases (" +
                                     std::to_string(prefixes.size()) + ")");
     if (!multi) sampleNames = {o.sampleName};
     for (std::string &s : sampleNames) s = cleanSampleName(s);
     Device dev;
-    if (kcf_init(multiDevice ? o.device : restrictToDevice(o.device), &dev.ctx) != KCF_OK) Logger::error("KMC", std::string(kcf_last_error(nullptr)));
+    // sharded job: the other GPUs open the same database while this thread opens it on the first one
+    std::vector<std::unique_ptr<Device>> peers;
+    std::vector<std::thread> openers;
+    std::vector<std::string> openFailure(o.devices.size());
+    if (shardedJob)
+        for (size_t g = 1; g < o.devices.size(); ++g) {
+            peers.emplace_back(new Device());
+            Device *pd = peers.back().get();
+            openers.emplace_back([&, g, pd] {
+                if (kcf_init(o.devices[g], &pd->ctx) != KCF_OK) openFailure[g] = kcf_last_error(nullptr);
+                else if (kcf_db_open(pd->ctx, prefixes[0].c_str(), 0, &pd->db) != KCF_OK) openFailure[g] = kcf_last_error(pd->ctx);
+            });
+        }
+    struct JoinGuard {
+        std::vector<std::thread> &t;
+        ~JoinGuard()
+        {
+            for (std::thread &x : t)
+                if (x.joinable()) x.join();
+        }
+    } joinGuard{openers};
+    if (kcf_init((multiDevice || shardedJob) ? o.device : restrictToDevice(o.device), &dev.ctx) != KCF_OK) Logger::error("KMC", std::string(kcf_last_error(nullptr)));
     if (kcf_db_open(dev.ctx, prefixes[0].c_str(), 0, &dev.db) != KCF_OK) dev.fail("KMC");
     kcf_db_info_t info;
     kcf_db_info(dev.db, &info);
@@ -920,7 +942,7 @@ int getVariations(GetVariantsOptions o)
             if (kcf_ref_add_async(dv.ctx, bytes, n, (uint32_t)e.lineBases, (uint32_t)e.lineWidth, (uint64_t)e.length, &sid) != KCF_OK) dv.fail(FAI_CLASS);
         }
     };
-    uploadReference(dev);
+    if (!shardedJob) uploadReference(dev);
     const double weights[3] = {o.innerDistanceWeight, o.tailDistanceWeight, o.kmerRatioWeight}; // getWeights(), :388-390
     // per sequence: the order the reference writes (stable sort by start, GetVariants.java:169-171)
     std::vector<std::vector<size_t>> sorted(perSeq.size());
@@ -932,7 +954,44 @@ int getVariations(GetVariantsOptions o)
     std::ofstream out(o.outFile, std::ios::binary);
     if (!out) throw FatalError("java.io.FileNotFoundException: " + o.outFile + " (No such file or directory)");
 
-    if (!multi) {
+    if (shardedJob) {
+        // one job, several GPUs: the library cuts the window list into one contiguous range per device (balanced on bases),
+        // every device uploads only the stretches of the reference its range touches and the rows come back in window order
+        for (std::thread &t : openers) t.join();
+        for (size_t g = 1; g < o.devices.size(); ++g)
+            if (!openFailure[g].empty()) Logger::error("KMC", openFailure[g]);
+        std::vector<kcf_ctx *> ctxs{dev.ctx};
+        std::vector<kcf_db *> dbs{dev.db};
+        for (auto &pd : peers) {
+            ctxs.push_back(pd->ctx);
+            dbs.push_back(pd->db);
+        }
+        std::vector<kcf_host_seq_t> hseqs;
+        for (const FastaIndexEntry &e : index.entries()) {
+            uint64_t n = 0;
+            const uint8_t *bytes = index.seqBytes(e.seqId, &n);
+            hseqs.push_back(kcf_host_seq_t{bytes, n, (uint32_t)e.lineBases, (uint32_t)e.lineWidth, (uint64_t)e.length});
+        }
+        std::vector<kcf_window_t> wins;
+        std::vector<kcf_segment_t> segs;
+        for (const auto &ws : perSeq)
+            for (const Window &w : ws) {
+                wins.push_back(kcf_window_t{(uint32_t)segs.size(), (uint32_t)w.segments.size()});
+                segs.insert(segs.end(), w.segments.begin(), w.segments.end());
+            }
+        std::vector<kcf_result_t> rows(std::max<size_t>(wins.size(), 1));
+        const int rc = kcf_screen_sharded(ctxs.data(), dbs.data(), (int)ctxs.size(), hseqs.data(), (uint32_t)hseqs.size(), wins.data(), wins.size(),
+                                          segs.data(), segs.size(), o.minKmerCount, weights, rows.data());
+        if (rc == KCF_ERR_WEIGHTS) Logger::error("Data", "Weights should sum to 1.0");
+        if (rc != KCF_OK) dev.fail(rc == KCF_ERR_RANGE || rc == KCF_ERR_FASTA ? FAI_CLASS : GV_CLASS);
+        Logger::info(GV_CLASS, "Screened " + std::to_string(totalWindows) + " windows on " + std::to_string(ctxs.size()) + " devices");
+        out << kcfHeaderText(o, sampleNames[0], index, kmerSize, (int)totalWindows, today());
+        size_t base = 0;
+        for (size_t s = 0; s < perSeq.size(); ++s) {
+            for (size_t i : sorted[s]) out << kcfRowText(perSeq[s][i], rows[base + i], weights) << "\n";
+            base += perSeq[s].size();
+        }
+    } else if (!multi) {
         screenAllSequences(dev, perSeq, kmerSize, o.minKmerCount, weights);
         std::vector<std::vector<kcf_result_t>> results(perSeq.size());
         for (size_t s = 0; s < perSeq.size(); ++s) {
@@ -1107,7 +1166,8 @@ const char *const USAGE =
     "  -c, --min-k-count=<minKmerCount> Minimum kmer count to consider [1]\n"
     "  -p, --step=<stepSize>        Step size for sliding window [window size]\n"
     "      --device=<cudaOrdinal>   CUDA device (this build; the database always lives in HBM, -m and -t are accepted)\n"
-    "      --devices=<a,b,...>      with several databases (-k x,y,... -s p,q,...): share them out over these CUDA devices\n";
+    "      --devices=<a,b,...>      several CUDA devices: one database -> its windows are cut over them (one job, rows as with one\n"
+    "                               device); several databases (-k x,y,... -s p,q,...) -> the databases are shared out over them\n";
 
 struct OptSpec {
     const char *shortName, *longName;

@@ -1,6 +1,6 @@
-"""tests/golden/small.npz (tools/make_golden.py): a fully materialised small case with the rows and KCF lines the CPU
-oracle produced for it.  Oracle-generated — it pins the oracle, the GPU path and the host formatting against
-regressions and against each other, NOT against the reference (which cannot run here)."""
+"""tests/fixtures_oracle/small.npz (tools/make_fixture.py): a fully materialised small case with the rows and KCF lines the CPU
+oracle produced for it.  NOT reference-authored golden data — the reference ships none and no JVM exists here (DESIGN.md §2,
+"parity unpinned") — it pins the oracle and the CUDA path against silent drift between commits, nothing more."""
 import os
 
 import numpy as np
@@ -11,7 +11,7 @@ from kcftools_b200._lib import RESULT_DTYPE, SEGMENT_DTYPE, WINDOW_DTYPE
 from oracle import binding as ob
 from oracle import pyhost
 
-G = np.load(os.path.join(os.path.dirname(__file__), "golden", "small.npz"))
+G = np.load(os.path.join(os.path.dirname(__file__), "fixtures_oracle", "small.npz"))
 MODES = ["window", "sliding", "gene", "transcript"]
 
 
@@ -27,7 +27,7 @@ def _seqs():
 
 
 @pytest.mark.parametrize("mode", MODES)
-def test_oracle_reproduces_golden_rows_and_text(mode):
+def test_oracle_reproduces_fixture_rows_and_text(mode):
     odb = ob.OracleKMC(G["kmc_pre"], G["kmc_suf"])
     wins, segs = G[f"{mode}_wins"].view(WINDOW_DTYPE), G[f"{mode}_segs"].view(SEGMENT_DTYPE)
     rc, res = odb.screen(_seqs(), wins, segs, threads=2)
@@ -46,7 +46,7 @@ def test_oracle_reproduces_golden_rows_and_text(mode):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", MODES)
-def test_gpu_reproduces_golden_rows(ctx, mode):
+def test_gpu_reproduces_fixture_rows(ctx, mode):
     from kcftools_b200.api import KMC
     ctx.ref_clear()
     for (raw, lb, lw, n) in _seqs():

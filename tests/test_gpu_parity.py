@@ -408,3 +408,91 @@ def test_random_window_layouts(ctx, sc_main, seed):
     assert_results_equal(got, want)
     assert (want["total_kmers"] == 0).any() and (want["obs"] > 0).any()  # the mix contains empty and observed windows
     db.close()
+
+
+@pytest.mark.parametrize("n_ctx,kind", [(1, "fixed"), (3, "fixed"), (2, "multi"), (4, "tiny")])
+def test_sharded_job_over_several_contexts(sc_main, n_ctx, kind):
+    """kcf_screen_sharded: ONE job cut over n contexts (here all on cuda:0; on the box one per GPU), sequences given as host
+    bytes, each context uploading only the line-aligned stretches its windows touch.  Rows must equal the oracle's for the
+    whole job, in window order, whatever the cut."""
+    from kcftools_b200.api import Context, screen_sharded, shard_windows
+    from kcftools_b200 import shard
+    sc = sc_main
+    if kind == "fixed":
+        wins, segs, *_ = fixed_windows(sc.seq_lens, 7_000, 0, 31)
+    elif kind == "tiny":  # fewer windows than contexts: some shards are empty
+        wins, segs = windows_from_lists([[(1, 100, 5_000)], [(0, 299_000, 1_000)]])
+    else:  # windows of several segments, out of order, across sequences, one shorter than k
+        rng = np.random.default_rng(3)
+        lists = [[(0, 100, 500), (0, 5_000, 40), (1, 10, 3_000)], [(1, 0, 20)], [(0, 0, 30_000), (1, 2_000, 9_000)], [(2, 0, 40)]]
+        for _ in range(60):
+            sid = int(rng.integers(0, 2))
+            n = sc.seq_lens[sid]
+            lists.append([(sid, int(rng.integers(0, n - 3_000)), int(rng.integers(1, 3_000))) for _ in range(int(rng.integers(1, 5)))])
+        wins, segs = windows_from_lists(lists)
+    rc, want = _oracle_screen(sc, wins, segs, min_count=2, w=(0.2, 0.3, 0.5))
+    assert rc == 0
+    bounds = shard_windows(wins, segs, n_ctx)
+    assert bounds[0] == 0 and bounds[-1] == wins.size and (np.diff(bounds.astype(np.int64)) >= 0).all()
+    # the library cuts where the Python host logic cuts (the torchrun bench shards with the latter)
+    assert [int(b) for b in bounds] == [r[0] for r in shard.partition(shard.window_lengths(wins, segs), n_ctx)] + [wins.size]
+    ctxs = [Context(0) for _ in range(n_ctx)]
+    dbs = [KMC(c, pre=sc.kmc.pre, suf=sc.kmc.suf) for c in ctxs]
+    try:
+        got = screen_sharded(ctxs, dbs, sc.seqs(), wins, segs, min_count=2, weights=(0.2, 0.3, 0.5))
+        assert_results_equal(got, want)
+        # errors surface with the reference's wording, whichever context hits them
+        bad_w, bad_s = windows_from_lists([[(0, 0, 100)], [(1, 123_400, 100)]])
+        with pytest.raises(KcfError) as e:
+            screen_sharded(ctxs, dbs, sc.seqs(), bad_w, bad_s)
+        assert e.value.code == -6 and "Invalid range" in e.value.msg
+    finally:
+        for d in dbs:
+            d.close()
+        for c in ctxs:
+            c.close()
+
+
+def test_sharded_job_pieces_of_a_long_sequence(ctx):
+    """a sequence longer than one upload piece (KCF_PIECE_BASES): windows straddling the piece boundaries become two
+    segments inside the library; lines of odd width, a final line without its newline is still fatal (Q9)"""
+    from kcftools_b200.api import screen_sharded
+    sc = Scenario(seq_lens=(26_000_000,), seed=77, n_bins=16, line=77, n_runs=6, snp=0.02)
+    db = KMC(ctx, pre=sc.kmc.pre, suf=sc.kmc.suf)
+    starts = np.concatenate([np.arange(0, 25_990_000, 1_300_000), [(24 << 20) // 77 * 77 - 40, (24 << 20) // 77 * 77 - 1, 25_990_000]])
+    wins, segs = windows_from_lists([[(0, int(s), 10_000)] for s in starts])
+    rc, want = _oracle_screen(sc, wins, segs)
+    assert rc == 0
+    got = screen_sharded([ctx], [db], sc.seqs(), wins, segs)
+    assert_results_equal(got, want)
+    db.close()
+
+
+def test_plans_do_not_outlive_their_sequences(ctx, sc_main):
+    """a plan addresses the sequences that were resident when it was created: after kcf_ref_clear it is refused instead of
+    reading recycled device memory; several plans queued before their fetches keep their own weight checks"""
+    sc = sc_main
+    sc.add_to(ctx)
+    db = KMC(ctx, pre=sc.kmc.pre, suf=sc.kmc.suf)
+    wins, segs, *_ = fixed_windows(sc.seq_lens, 50_000, 0, 31)
+    rc, want = _oracle_screen(sc, wins, segs)
+    a, b = ctx.plan(31, wins, segs), ctx.plan(31, wins[:2], segs[:2])
+    a.run(db, weights=(0.3, 0.3, 0.5))  # bad weights, queued first
+    b.run(db)                           # good weights, queued second
+    with pytest.raises(KcfError) as e:
+        a.fetch()
+    assert e.value.code == -8
+    assert_results_equal(b.fetch(), want[:2])
+    a.run(db)
+    assert_results_equal(a.fetch(), want)
+    sc.add_to(ctx)  # kcf_ref_clear + the same sequences again: the old plans are stale all the same
+    with pytest.raises(KcfError) as e:
+        a.run(db)
+    assert e.value.code == -5 and "kcf_ref_clear" in e.value.msg
+    a.close()
+    b.close()
+    c = ctx.plan(31, wins, segs)
+    c.run(db)
+    assert_results_equal(c.fetch(), want)
+    c.close()
+    db.close()

@@ -207,3 +207,25 @@ def test_getvariations_cli_writes_the_reference_kcf(cli, genome, mode):
     order = {n: i for i, n in enumerate(genome["names"])}
     assert starts == sorted(starts, key=lambda t: (order[t[0]], t[1]))
     assert any(":0.00" not in r for r in rows) and res["obs"].sum() > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["window", "gene"])
+def test_getvariations_one_database_over_several_devices(cli, genome, mode):
+    """--devices with ONE database: the windows are cut over the devices (here three contexts on device 0; on the box one per
+    GPU) and the KCF must be the single-device file byte for byte, ##date / ##CMD aside (GetVariants.java:129-151, 169-179)"""
+    d = genome["dir"]
+    qs = [synth.mutate(g, 900 + i, big_deletions=0, replace_len=0) for i, g in enumerate(genome["codes"])]
+    kmc = synth.kmc_image_from_genomes(qs, k=31, P=7, L=9, n_bins=32, counter_size=1, coverage=8.0, seed=6)
+    prefix = str(d / "sample_md")
+    kmc.write(prefix)
+    common = ["getVariations", "-r", genome["fa"], "-k", prefix, "-s", "S"]
+    common += ["-f", "window", "-w", "4000"] if mode == "window" else ["-f", "gene", "-g", genome["gtf"]]
+    one, three = str(d / f"md1_{mode}.kcf"), str(d / f"md3_{mode}.kcf")
+    run(cli, *common, "-o", one, "--device", "0")
+    p = run(cli, *common, "-o", three, "--devices", "0,0,0")
+    assert "on 3 devices" in p.stdout
+
+    def body(path):
+        return [l for l in open(path).read().split("\n") if not l.startswith("##date") and not l.startswith("##CMD")]
+    assert body(one) == body(three) and len(body(one)) > 30

@@ -10,5 +10,5 @@ timeout 300 python bench.py --workload c3s --no-cpu-baseline --steps 20 > $D/ben
 timeout 300 python bench.py --workload c3st --no-cpu-baseline --steps 20 > $D/bench_c3st.json 2> $D/bench_c3st.err
 timeout 600 python tools/pipeline_c5s.py --samples 4 > $D/pipeline_c5s.json 2> $D/pipeline_c5s.err
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_kcf_tools.py tests/test_gpu_parity.py -m gpu -x -q -k "device_results or scan_path or fixed_windows" > $D/sanitizer_memcheck.txt 2>&1; echo "memcheck rc=$?" >> $D/sanitizer_memcheck.txt
-timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_golden.py -m gpu -x -q > $D/sanitizer_racecheck.txt 2>&1; echo "racecheck rc=$?" >> $D/sanitizer_racecheck.txt
+timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_fixture_small.py -m gpu -x -q > $D/sanitizer_racecheck.txt 2>&1; echo "racecheck rc=$?" >> $D/sanitizer_racecheck.txt
 tail -3 $D/tests.log; cut -c1-300 $D/bench_c2.json; cat $D/pipeline_c5s.json; tail -4 $D/sanitizer_memcheck.txt $D/sanitizer_racecheck.txt

@@ -1,11 +1,13 @@
-"""Regenerates tests/golden/small.npz: a small, fully materialised getVariations case (FASTA image, KMC image, GTF,
+"""Regenerates tests/fixtures_oracle/small.npz: a small, fully materialised getVariations case (FASTA image, KMC image, GTF,
 window lists) together with the rows the CPU oracle computes for it and the KCF text lines oracle/pyhost.py renders.
 
 The reference itself cannot produce vectors here (Java, no JVM in the image; it ships no tests or fixtures), so these
 are ORACLE-generated: they pin the oracle, the GPU path and the host formatting against regressions and against each
 other, not against the reference (parity unpinned).
 
-    python tools/make_golden.py
+    python tools/make_fixture.py
+    python tools/make_fixture.py --write-files DIR    # the case's input FILES (ref.fa, sample.kmc_pre/.kmc_suf, ann.gtf) for a
+                                                      # run of the real reference (oracle/build_ref.sh), nothing else
 """
 import os
 import sys
@@ -42,6 +44,14 @@ def main():
     odb = ob.OracleKMC(kmc.pre, kmc.suf)
     out = {"fasta": img.data, "kmc_pre": kmc.pre, "kmc_suf": kmc.suf, "gtf": np.frombuffer(gtf_text.encode(), np.uint8),
            "lens": np.array(lens), "offsets": np.array(img.offsets)}
+    if len(sys.argv) == 3 and sys.argv[1] == "--write-files":
+        d = sys.argv[2]
+        os.makedirs(d, exist_ok=True)
+        img.write(os.path.join(d, "ref.fa"))
+        kmc.write(os.path.join(d, "sample"))
+        open(os.path.join(d, "ann.gtf"), "w").write(gtf_text)
+        print(d)
+        return
     w = (0.3, 0.3, 0.4)
     for mode, kw in [("window", dict(window=2000, step=0)), ("sliding", dict(window=1500, step=700)), ("gene", {}), ("transcript", {})]:
         feat = "window" if mode in ("window", "sliding") else mode
@@ -54,7 +64,7 @@ def main():
         out[f"{mode}_rows"] = res
         text = "\n".join(pyhost.kcf_row(x[1], x[2], x[3], x[0], res[i], w) for i, x in enumerate(ws)) + "\n"
         out[f"{mode}_kcf"] = np.frombuffer(text.encode(), np.uint8)
-    path = os.path.join(ROOT, "tests", "golden", "small.npz")
+    path = os.path.join(ROOT, "tests", "fixtures_oracle", "small.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes;", kmc.total, "records")
 
