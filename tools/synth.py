@@ -494,3 +494,94 @@ def kmc_image_from_strings(seqs: list[str], *, k: int, P: int, L: int, n_bins: i
         np.frombuffer(b"KMCP", np.uint8),
     ])
     return KmcImage(pre=pre, suf=suf, k=k, P=P, L=L, n_bins=n_bins, counter_size=counter_size, total=N, both_strands=both_strands)
+
+
+# ----------------------------------------------------------------------------------------
+# large databases (3e9 records and more): the same image, built one group of bins at a time so that the sort buffers of
+# a group — not of the whole database — have to fit the device
+# ----------------------------------------------------------------------------------------
+def kmc_image_from_genomes_grouped(genomes: list[torch.Tensor], *, k: int = 31, P: int = 7, L: int = 9, n_bins: int = 512,
+                                   counter_size: int = 1, coverage: float = 8.0, seed: int = 1, groups: int = 4,
+                                   both_strands: bool = True) -> KmcImage:
+    """as kmc_image_from_genomes (counter_size >= 1, default signature map), but the bins are processed in `groups`
+    contiguous ranges: every pass walks all genomes, keeps the k-mers whose bin falls in the range, sorts / deduplicates /
+    draws counts for those, and appends their records.  Bins are contiguous in `.kmc_suf` (KMC.java:61, 300-307), so the
+    concatenation of the groups IS the file."""
+    assert counter_size >= 1 and (k - P) % 4 == 0 and k <= 32
+    dev = genomes[0].device
+    norm = torch.from_numpy(norm_table(L)).to(dev)
+    sigmap = default_sigmap(L, n_bins)
+    smap = torch.from_numpy(sigmap.astype(np.int64)).to(dev)
+    sbits = 2 * (k - P)
+    nsb = (k - P) // 4
+    maxc = min((1 << (8 * counter_size)) - 1, 255 if counter_size == 1 else (1 << 31) - 1)
+    hist_all = torch.zeros(n_bins << (2 * P), dtype=torch.int64, device=dev)
+    parts = [np.frombuffer(b"KMCS", np.uint8)]
+    total = 0
+    for gi in range(groups):
+        b_lo, b_hi = n_bins * gi // groups, n_bins * (gi + 1) // groups
+        ks, bs = [], []
+        for gseq in genomes:
+            if gseq.numel() < k:
+                continue
+            f = kmers_fwd(gseq, k)
+            if both_strands:
+                rc = torch.flip(kmers_fwd(3 - torch.flip(gseq, [0]), k), [0])
+                can = torch.where((f ^ _SIGN) <= (rc ^ _SIGN), f, rc) if k == 32 else torch.minimum(f, rc)
+                del rc
+            else:
+                can = f
+            del f
+            bins = smap[signatures(gseq, k, L, norm).long()]
+            sel = (bins >= b_lo) & (bins < b_hi)
+            ks.append(can[sel])
+            bs.append(bins[sel].to(torch.int16))
+            del can, bins, sel
+        allk, allb = torch.cat(ks), torch.cat(bs)
+        del ks, bs
+        order = torch.argsort(allk ^ _SIGN if k == 32 else allk)
+        allk, allb = allk[order], allb[order]
+        del order
+        first = torch.ones(allk.numel(), dtype=torch.bool, device=dev)
+        first[1:] = allk[1:] != allk[:-1]
+        pos = torch.nonzero(first).flatten()
+        del first
+        mult = torch.diff(pos, append=torch.tensor([allk.numel()], device=dev))
+        uk, ub = allk[pos], allb[pos].to(torch.int64)
+        del allk, allb, pos
+        cnt = torch.clamp(torch.poisson(mult.to(torch.float32) * coverage, generator=_gen(seed + 1000 * gi, dev)).to(torch.int64), max=maxc)
+        del mult
+        keep = cnt > 0
+        uk, ub, cnt = uk[keep], ub[keep], cnt[keep]
+        del keep
+        o2 = torch.sort(ub, stable=True).indices  # bin, then k-mer value (already ascending)
+        uk, ub, cnt = uk[o2], ub[o2], cnt[o2]
+        del o2
+        prefix = (uk >> sbits) & ((1 << (2 * P)) - 1) if P > 0 else torch.zeros_like(uk)
+        hist_all += torch.bincount(ub * (1 << (2 * P)) + prefix, minlength=n_bins << (2 * P))
+        del prefix, ub
+        n = uk.numel()
+        rec = torch.empty((n, nsb + counter_size), dtype=torch.uint8, device=dev)
+        suffix = uk & ((1 << sbits) - 1) if sbits < 64 else uk
+        for j in range(nsb):
+            rec[:, j] = ((suffix >> (8 * (nsb - 1 - j))) & 0xFF).to(torch.uint8)
+        for j in range(counter_size):
+            rec[:, nsb + j] = ((cnt >> (8 * j)) & 0xFF).to(torch.uint8)
+        parts.append(rec.flatten().cpu().numpy())
+        total += n
+        del rec, suffix, uk, cnt
+    parts.append(np.frombuffer(b"KMCS", np.uint8))
+    suf = np.concatenate(parts)
+    del parts
+    lut = (torch.cumsum(hist_all, 0) - hist_all).cpu().numpy().astype("<u8")
+    header = struct.pack("<7IQB3x24xI", k, 0, counter_size, P, L, 1, max(maxc, 1), total, 0 if both_strands else 1, 0x200)
+    pre = np.concatenate([
+        np.frombuffer(b"KMCP", np.uint8),
+        lut.view(np.uint8),
+        np.frombuffer(struct.pack("<Q", total), np.uint8),
+        sigmap.astype("<u4").view(np.uint8),
+        np.frombuffer(header, np.uint8),
+        np.frombuffer(struct.pack("<I", 68), np.uint8),
+        np.frombuffer(b"KMCP", np.uint8),
+    ])
+    return KmcImage(pre=pre, suf=suf, k=k, P=P, L=L, n_bins=n_bins, counter_size=counter_size, total=total, both_strands=both_strands)
