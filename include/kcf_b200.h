@@ -265,6 +265,9 @@ int kcf_cohort_fetch(kcf_ctx *ctx, kcf_cohort *c, uint32_t sample, kcf_cell_t *c
 /* Random 32-byte-sector gather bandwidth of this GPU (the random-access roofline of SURVEY §8(d)):
  * n_loads independent 32-B loads from uniformly random sector addresses of a buffer of n_bytes. */
 int kcf_measure_random_sector_gbps(kcf_ctx *ctx, uint64_t n_bytes, uint64_t n_loads, int repeats, double *gbps_out);
+/* Random 128-byte LINE gather rate of this GPU (lines per second): 4 lanes read the 4 sectors of one uniformly random line
+ * with one coalesced request — the access pattern of this library's table, hence its memory-side bound. */
+int kcf_measure_random_line_rate(kcf_ctx *ctx, uint64_t n_bytes, uint64_t n_lines_read, int repeats, double *lines_per_s_out);
 /* Layout statistics: hist_out[n] = table lines (home + overflow) holding n keys, n = 0 .. 15. */
 int kcf_db_line_histogram(kcf_db *db, uint64_t hist_out[16]);
 /* Milliseconds of the screening kernel in the last kcf_plan_run when profiling is on. */

@@ -88,6 +88,7 @@ SYMBOLS = {
     "kcf_scan_owned": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_int32, _P, _P]),
     "kcf_scan_fold": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P, _P]),
     "kcf_measure_random_sector_gbps": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
+    "kcf_measure_random_line_rate": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
     "kcf_set_profiling": (C.c_int, [_P, C.c_int]),
     "kcf_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "kcf_version": (C.c_char_p, []),

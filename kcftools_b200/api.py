@@ -87,6 +87,12 @@ class Context:
         self._check(self._lib.kcf_measure_random_sector_gbps(self._h, n_bytes, n_loads, repeats, C.byref(out)))
         return out.value
 
+    def random_line_rate(self, n_bytes: int, n_lines_read: int, repeats: int = 5) -> float:
+        """random 128-byte lines per second this GPU serves (one coalesced request per line)"""
+        out = C.c_double()
+        self._check(self._lib.kcf_measure_random_line_rate(self._h, n_bytes, n_lines_read, repeats, C.byref(out)))
+        return out.value
+
     # -- reference sequences --
     def ref_add(self, seq_bytes: np.ndarray, line_bases: int, line_width: int, seq_len: int) -> int:
         """seq_bytes = the file bytes the reference maps for one sequence (FastaIndex.java:54-68)."""

@@ -423,11 +423,12 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         const double share = part_world > 1 ? 1.0 / part_world : 1.0;
-        const double steps[] = {0.15, 0.2, 0.3, 0.4, 0.5, 0.6};
+        const double steps[] = {0.15, 0.2, 0.3, 0.4, 0.5, 0.6, 0.75, 0.9};
         // against the device's TOTAL memory: every rank of a partitioned database must derive the same geometry
         for (double cand : steps) {
             lf = cand;
-            if ((double)N * share / (g.S * lf) * KCF_LINE_BYTES <= 0.4 * (double)total_b) break;
+            const double ov = std::max(0.125, 0.55 * lf * lf); // the overflow region grows with the density (below)
+            if ((double)N * share / (g.S * lf) * KCF_LINE_BYTES * (1.0 + ov) <= 0.4 * (double)total_b) break;
         }
     }
     uint64_t nb = cs == 0 ? 1 : (uint64_t)((double)N / (g.S * lf)) + 1;
@@ -441,7 +442,11 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
         g.line_lo = lo;
         g.n_local = hi - lo;
     }
-    g.n_ov = cs == 0 ? 1 : std::max<uint64_t>(g.n_local / 8, 32); // overflow region: 1/8 of the home lines
+    // overflow region.  The k-mers of one minimizer run arrive together (1 to w of them, 6 on average), so the share of keys that
+    // find their home line full grows with the density: 5 % at 0.15, 10 % at 0.3, 17 % at 0.5, 23 % at 0.7, 29 % at 0.9
+    // (tools/line_occupancy_model.py) — about 0.33 lf; held in lines filled to ~0.6 that is 0.55 lf^2 of the home lines,
+    // and never less than 1/8 of them
+    g.n_ov = cs == 0 ? 1 : std::max<uint64_t>((uint64_t)((double)g.n_local * std::max(0.125, 0.55 * lf * lf)), 32);
     nb = g.n_local + g.n_ov;                                       // lines allocated below
     if (nb >= 0xFFFFFFFFULL) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "%llu table lines do not fit a 32-bit line index; partition the database", (unsigned long long)nb);
     g.stash_mask = 0;

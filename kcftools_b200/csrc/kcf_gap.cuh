@@ -2,7 +2,7 @@
 // statistics of GetVariants.processWindow (GetVariants.java:217-252, getDistance :267-273).
 //
 // A KcfGap (kcf_internal.cuh) summarises a run of valid k-mers, each hit or miss; kcf_gap_combine is the in-order
-// concatenation of two runs and is associative, so 32 positions (bit tricks) -> warp (shuffle tree) -> tile -> window
+// concatenation of two runs and is associative, so 32 positions (bit tricks) -> warp (kcf_gap_fold_warp) -> tile -> window
 // reproduces the reference's sequential state machine bit for bit.  ONE definition: the replicated kernel
 // (kcf_screen.cu), the exchange fold and the scan fold (kcf_part.cu) all include this file.
 #pragma once
@@ -58,22 +58,6 @@ __device__ __forceinline__ KcfGap kcf_gap_combine(const KcfGap &a, const KcfGap 
     return r;
 }
 
-// every field but `sum` (Σ count is not tied to positions: callers reduce it as a plain sum)
-__device__ __forceinline__ KcfGap kcf_gap_shfl_down(const KcfGap &a, int delta)
-{
-    KcfGap r;
-    r.n = __shfl_down_sync(0xffffffffu, a.n, delta);
-    r.obs = __shfl_down_sync(0xffffffffu, a.obs, delta);
-    r.lead = __shfl_down_sync(0xffffffffu, a.lead, delta);
-    r.trail = __shfl_down_sync(0xffffffffu, a.trail, delta);
-    r.vin = __shfl_down_sync(0xffffffffu, a.vin, delta);
-    r.inner = __shfl_down_sync(0xffffffffu, a.inner, delta);
-    r.has = __shfl_down_sync(0xffffffffu, a.has, delta);
-    r.starts = __shfl_down_sync(0xffffffffu, a.starts, delta);
-    r.sum = 0;
-    return r;
-}
-
 // gap summary of 32 consecutive positions from their bitmaps (bit i = position i): `vw` marks the positions where a
 // k-mer ends, `hw` (a subset) the observed ones, `sw` the k-mers that open a valid stretch.  Positions without a k-mer
 // are transparent: a miss run continues across them (GetVariants.java:217-245 runs over the compacted k-mer list).
@@ -108,13 +92,48 @@ __device__ __forceinline__ KcfGap kcf_gap_from_bits(uint32_t hw, uint32_t vw, ui
     return a;
 }
 
-// ordered reduction of 32 per-lane summaries (lane order = position order); the result is meaningful in lane 0
-__device__ __forceinline__ KcfGap kcf_gap_warp_reduce(KcfGap a, uint32_t lane, uint32_t k)
+// Ordered reduction of the per-lane summaries of a warp (lane order = position order), without a combine tree: lane j holds the bitmaps of positions [32 j, 32 j + 32) (zero words for lanes past
+// the data).  The counting fields are plain warp sums; a miss run that crosses lanes is closed by the lane holding its left
+// hit, which fetches the next hit lane's leading misses and the k-mers in between (prefix sums of the per-lane k-mer
+// counts) — exactly what kcf_gap_combine does pairwise, since lanes without a hit only lengthen the open run.  About 50
+// warp instructions instead of five shuffle-and-combine rounds; the result is uniform over the warp (sum = 0).
+__device__ __forceinline__ KcfGap kcf_gap_fold_warp(uint32_t hw, uint32_t vw, uint32_t sw, uint32_t lane, uint32_t k)
 {
-#pragma unroll 1
+    const KcfGap a = kcf_gap_from_bits(hw, vw, sw, k);
+    uint32_t incl = a.n; // inclusive prefix sum of the k-mer counts over the lanes
+#pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const KcfGap b = kcf_gap_shfl_down(a, d);
-        if (lane + d < 32) a = kcf_gap_combine(a, b, k);
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += t;
     }
-    return a;
+    const uint32_t excl = incl - a.n, total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t hasmask = __ballot_sync(0xffffffffu, a.has != 0);
+    KcfGap r;
+    r.n = total;
+    r.obs = __reduce_add_sync(0xffffffffu, a.obs);
+    r.starts = __reduce_add_sync(0xffffffffu, a.starts);
+    r.sum = 0;
+    r.has = hasmask != 0;
+    if (!hasmask) { // warp uniform: no hit in the chunk
+        r.lead = r.trail = total;
+        r.vin = r.inner = 0;
+        return r;
+    }
+    const uint32_t above = hasmask & (0xFFFFFFFEu << lane);     // hit lanes after this one
+    const uint32_t nxt = above ? __ffs(above) - 1 : lane;       // the next of them (this lane when there is none)
+    const uint32_t lead_n = __shfl_sync(0xffffffffu, a.lead, nxt), excl_n = __shfl_sync(0xffffffffu, excl, nxt);
+    uint32_t vin = a.vin, inner = a.inner;
+    if (a.has && above) {
+        const uint32_t g = a.trail + (excl_n - incl) + lead_n; // misses between this lane's last hit and the next lane's first
+        if (g > 0) {
+            vin += 1;
+            inner += kcf_gap_distance(g, k);
+        }
+    }
+    r.vin = __reduce_add_sync(0xffffffffu, vin);
+    r.inner = __reduce_add_sync(0xffffffffu, inner);
+    const uint32_t f = __ffs(hasmask) - 1, l = 31 - __clz(hasmask);
+    r.lead = __shfl_sync(0xffffffffu, excl + a.lead, f);
+    r.trail = __shfl_sync(0xffffffffu, a.trail + (total - incl), l);
+    return r;
 }

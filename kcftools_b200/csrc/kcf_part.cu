@@ -140,10 +140,8 @@ __global__ void __launch_bounds__(128) kcf_part_fold_kernel(const uint32_t *__re
             else hw1 = hb;
         }
     }
-    KcfGap a = kcf_gap_from_bits(hw0, okw[t * WORDS + lane], start[t * WORDS + lane], k);
-    KcfGap b = kcf_gap_from_bits(hw1, okw[t * WORDS + 32 + lane], start[t * WORDS + 32 + lane], k);
-    a = kcf_gap_warp_reduce(a, lane, k);
-    b = kcf_gap_warp_reduce(b, lane, k);
+    const KcfGap a = kcf_gap_fold_warp(hw0, okw[t * WORDS + lane], start[t * WORDS + lane], lane, k);
+    const KcfGap b = kcf_gap_fold_warp(hw1, okw[t * WORDS + 32 + lane], start[t * WORDS + 32 + lane], lane, k);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, d);
     if (lane == 0) {
@@ -274,10 +272,8 @@ __global__ void __launch_bounds__(128) kcf_scan_fold_kernel(const uint32_t *__re
     constexpr int WORDS = KCF_TILE / 32; // 64
     const uint64_t w0 = t * WORDS + lane, w1 = w0 + 32;
     // a hit bit is only ever set where a k-mer ends; the mask keeps a corrupted reduction from inventing k-mers
-    KcfGap a = kcf_gap_from_bits(hit[w0] & okw[w0], okw[w0], start[w0], k);
-    KcfGap b = kcf_gap_from_bits(hit[w1] & okw[w1], okw[w1], start[w1], k);
-    a = kcf_gap_warp_reduce(a, lane, k);
-    b = kcf_gap_warp_reduce(b, lane, k);
+    const KcfGap a = kcf_gap_fold_warp(hit[w0] & okw[w0], okw[w0], start[w0], lane, k);
+    const KcfGap b = kcf_gap_fold_warp(hit[w1] & okw[w1], okw[w1], start[w1], lane, k);
     if (lane == 0) {
         KcfGap r = kcf_gap_combine(a, b, k);
         r.sum = sums[t];

@@ -60,7 +60,8 @@ enum { KCF_MODE_SCREEN = 0, KCF_MODE_COUNTS = 1, KCF_MODE_EXTRACT = 2, KCF_MODE_
 //            line's S low key words + filter + mask word requested together, confirm on the high word, read the
 //            count; k-mers whose home mask names other lines go to a queue
 //   queue    searched one item per lane, densely (continuation lines are rare per k-mer but not per warp)
-//   fold     hit / valid bitmaps (one ballot per 32 positions) -> gap summary by bit tricks -> one shuffle reduction;
+//   fold     hit / valid bitmaps (one ballot per 32 positions) -> gap summary per word by bit tricks -> warp sums plus one
+//            neighbour exchange for the miss runs that cross words (kcf_gap.cuh);
 //            the tile's running summary lives in shared memory, not in registers
 // ------------------------------------------------------------------------------------------------------------
 #ifndef KCF_CHUNK
@@ -421,8 +422,7 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
 
             // ---- fold: lane j summarises positions [32 j, 32 j + 32), one ordered shuffle reduction per chunk ----
             constexpr uint32_t NWORDS = KCF_CHUNK / 32;
-            KcfGap a = kcf_gap_from_bits(lane < NWORDS ? W.hit[lane] : 0u, lane < NWORDS ? W.okw[lane] : 0u, lane < NWORDS ? W.start[lane] : 0u, k);
-            a = kcf_gap_warp_reduce(a, lane, k);
+            KcfGap a = kcf_gap_fold_warp(lane < NWORDS ? W.hit[lane] : 0u, lane < NWORDS ? W.okw[lane] : 0u, lane < NWORDS ? W.start[lane] : 0u, lane, k);
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, d); // Σ count is not tied to positions: plain warp sum
             if (lane == 0) {
@@ -542,6 +542,68 @@ extern "C" int kcf_measure_random_sector_gbps(kcf_ctx *ctx, uint64_t n_bytes, ui
     cudaFree(sink);
     if (e != cudaSuccess) return kcf_fail(ctx, KCF_ERR_CUDA, "random sector kernel: %s", cudaGetErrorString(e));
     *gbps_out = best;
+    return KCF_OK;
+}
+
+// ---- random 128-byte LINE gather microbenchmark: the memory-side bound of THIS table (one coalesced line request per run
+// of k-mers sharing a minimizer).  Groups of 4 lanes read the 4 sectors of one uniformly random line in one instruction, 8
+// lines in flight per group (profiles/r1b_randline.txt, pattern T3).
+__global__ void __launch_bounds__(256) kcf_random_line_kernel(const uint64_t *__restrict__ buf, uint64_t n_lines, uint64_t iters, uint64_t seed,
+                                                              uint64_t *sink)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t x = ((t >> 2) + 1) * 0x9E3779B97F4A7C15ULL ^ seed; // the 4 lanes of a group draw the same lines
+    uint64_t acc = 0;
+    for (uint64_t it = 0; it < iters; ++it) {
+        uint64_t a[8], b[8], c[8], d[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            x ^= x >> 29;
+            x *= 0xBF58476D1CE4E5B9ULL;
+            x ^= x >> 32;
+            const uint64_t l = __umul64hi(x, n_lines);
+            kcf_ld_bucket(buf + l * 16 + (t & 3) * 4, a[j], b[j], c[j], d[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += a[j] ^ b[j] ^ c[j] ^ d[j];
+    }
+    if (acc == 0x1234567ULL) *sink = acc;
+}
+
+extern "C" int kcf_measure_random_line_rate(kcf_ctx *ctx, uint64_t n_bytes, uint64_t n_lines_read, int repeats, double *lines_per_s_out)
+{
+    if (!ctx || !lines_per_s_out || n_bytes < 4096 || n_lines_read == 0) return KCF_ERR_ARG;
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint64_t *buf = nullptr, *sink = nullptr;
+    const uint64_t n_lines = n_bytes / 128;
+    KCF_CUDA(ctx, cudaMalloc(&buf, n_lines * 128));
+    cudaError_t e = cudaMalloc(&sink, 8);
+    if (e != cudaSuccess) { cudaFree(buf); return kcf_fail(ctx, KCF_ERR_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    cudaMemsetAsync(buf, 1, n_lines * 128, ctx->stream);
+    const uint64_t iters = 8; // 64 lines per group of 4 lanes
+    const uint64_t groups = (n_lines_read + iters * 8 - 1) / (iters * 8);
+    const unsigned grid = (unsigned)((groups * 4 + 255) / 256);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    double best = 0;
+    for (int r = 0; r < std::max(repeats, 1) + 1; ++r) {
+        cudaEventRecord(a, ctx->stream);
+        kcf_random_line_kernel<<<grid, 256, 0, ctx->stream>>>(buf, n_lines, iters, 0x51ED27ULL * (r + 1), sink);
+        cudaEventRecord(b, ctx->stream);
+        e = cudaEventSynchronize(b);
+        if (e != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        const double rate = (double)grid * 64.0 * iters * 8.0 / (ms * 1e-3); // 64 groups per CTA
+        if (r > 0 && rate > best) best = rate; // first launch is the warm-up
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(buf);
+    cudaFree(sink);
+    if (e != cudaSuccess) return kcf_fail(ctx, KCF_ERR_CUDA, "random line kernel: %s", cudaGetErrorString(e));
+    *lines_per_s_out = best;
     return KCF_OK;
 }
 

@@ -53,17 +53,24 @@ def _finish(ctx, plan, weights):
     return plan.fetch()
 
 
-def screen_partitioned(ctx, db, plan, group=None, min_count: int = 1, weights=(0.3, 0.3, 0.4), batch_tiles: int = BATCH_TILES) -> np.ndarray:
+def screen_partitioned(ctx, db, plan, group=None, min_count: int = 1, weights=(0.3, 0.3, 0.4), batch_tiles: int = BATCH_TILES,
+                       phases: dict | None = None) -> np.ndarray:
     """one rank of a torch.distributed job: `db` was opened with placement=1 after ctx.set_partition(rank, world), `plan`
-    holds THIS rank's windows.  Returns this rank's rows."""
+    holds THIS rank's windows.  Returns this rank's rows.  `phases` (optional dict) accumulates seconds per phase —
+    a device synchronisation is then inserted after each — and the bytes this rank put on the wire (`_bytes_out`,
+    `_bytes_back`; `_n` counts the calls)."""
     import torch
     import torch.distributed as dist
     world, dev = dist.get_world_size(group), torch.device("cuda", ctx.device)
     # every rank takes part in every all-to-all: loop over the largest batch count
     import os
     import time
-    trace = os.environ.get("KCF_PART_TRACE") and dist.get_rank(group) == 0
-    tt = {"extract": 0.0, "a2a_keys": 0.0, "lookup": 0.0, "a2a_counts": 0.0, "fold": 0.0}
+    me = dist.get_rank(group)
+    trace = phases is not None or (os.environ.get("KCF_PART_TRACE") and me == 0)
+    tt = phases if phases is not None else {}
+    for k_ in ("extract", "a2a_keys", "lookup", "a2a_counts", "fold"):
+        tt.setdefault(k_, 0.0)
+    tt["_n"] = tt.get("_n", 0) + 1
 
     def lap(name, t):
         if trace:
@@ -85,6 +92,9 @@ def screen_partitioned(ctx, db, plan, group=None, min_count: int = 1, weights=(0
         rhomes = torch.empty(sum(rc), dtype=torch.int32, device=dev)
         dist.all_to_all_single(rkeys, keys, rc, sc, group=group)
         dist.all_to_all_single(rhomes, homes, rc, sc, group=group)
+        off_rank = sum(sc) - sc[me]  # what stays on this rank does not cross NVLink
+        tt["_bytes_out"] = tt.get("_bytes_out", 0) + 12 * off_rank
+        tt["_bytes_back"] = tt.get("_bytes_back", 0) + 4 * off_rank
         torch.cuda.current_stream(dev).synchronize()  # NCCL ran on torch's stream, the library has its own
         t = lap("a2a_keys", t)
         rcounts = _lookup(ctx, db, rkeys, rhomes, torch, dev)
@@ -95,8 +105,8 @@ def screen_partitioned(ctx, db, plan, group=None, min_count: int = 1, weights=(0
         t = lap("a2a_counts", t)
         _fold(ctx, plan, t0, t1, back, src, min_count)
         t = lap("fold", t)
-    if trace:
-        print("[partitioned] ms per phase:", {k: round(1e3 * v, 3) for k, v in tt.items()}, flush=True)
+    if phases is None and trace:
+        print("[partitioned] ms per phase:", {k: round(1e3 * v, 3) for k, v in tt.items() if not k.startswith("_")}, flush=True)
     return _finish(ctx, plan, weights)
 
 
@@ -139,22 +149,35 @@ def _scan_fold(ctx, plan, t0, t1, hit, sums):
     ctx._check(ctx._lib.kcf_scan_fold(ctx._h, plan._h, t0, t1, hit.data_ptr(), sums.data_ptr()))
 
 
-def screen_partitioned_scan(ctx, db, plan, group=None, min_count: int = 1, weights=(0.3, 0.3, 0.4), batch_tiles: int = 1 << 20) -> np.ndarray:
+def screen_partitioned_scan(ctx, db, plan, group=None, min_count: int = 1, weights=(0.3, 0.3, 0.4), batch_tiles: int = 1 << 20,
+                            phases: dict | None = None) -> np.ndarray:
     """one rank of a torch.distributed job: `db` was opened with placement=1 after ctx.set_partition(rank, world), `plan`
-    holds ALL windows (the same plan on every rank).  Returns all rows (identical on every rank)."""
+    holds ALL windows (the same plan on every rank).  Returns all rows (identical on every rank).  `phases` (optional dict)
+    accumulates seconds per phase; `_n` counts the calls."""
+    import time
     import torch
     import torch.distributed as dist
     on_gpu = dist.get_backend(group) == "nccl"  # gloo: the host-logic test on CPU (tests/test_shard.py)
     dev = torch.device("cuda", ctx.device) if on_gpu else torch.device("cpu")
+    tt = phases if phases is not None else {}
+    for k_ in ("scan_owned", "all_reduce", "fold"):
+        tt.setdefault(k_, 0.0)
+    tt["_n"] = tt.get("_n", 0) + 1
     for t0 in range(0, plan.n_tiles, batch_tiles):
         t1 = t0 + batch_tiles
-        hit, sums = _scan_owned(ctx, db, plan, t0, t1, min_count, torch, dev)
+        ta = time.perf_counter()
+        hit, sums = _scan_owned(ctx, db, plan, t0, t1, min_count, torch, dev)  # returns after the kernel (host-synchronous)
+        tb = time.perf_counter()
         # the owners' bitmaps are disjoint, so the sum is the union (no carries; NCCL has no bitwise reduction)
         dist.all_reduce(hit, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
         if on_gpu:
             torch.cuda.current_stream(dev).synchronize()  # NCCL ran on torch's stream, the library has its own
+        tc = time.perf_counter()
         _scan_fold(ctx, plan, t0, t1, hit, sums)
+        tt["scan_owned"] += tb - ta
+        tt["all_reduce"] += tc - tb
+        tt["fold"] += time.perf_counter() - tc
     return _finish(ctx, plan, weights)
 
 
