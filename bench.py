@@ -476,6 +476,7 @@ def main():
     ranges = shard.partition(shard.window_lengths(wl.wins, wl.segs), world)
     w0, w1 = ranges[rank]
     my_wins, my_segs = shard.local_slice(wl.wins, wl.segs, w0, w1)
+    ctx.ref_clear()  # the host-buffer calls above left their upload pieces as the context's sequences
     for (pb, lb, lw, sl) in pinned:
         ctx.ref_add(pb, lb, lw, sl)
     plan = ctx.plan(31, my_wins, my_segs)
@@ -666,6 +667,7 @@ def small_config_leg(torch, ctx, stream, device, host_cores: int, name: str) -> 
     rows = screen_sharded([ctx], [db], pinned, w.wins, w.segs)
     cold_s = time.perf_counter() - t1
     ms, rows2 = e2e_leg(torch, ctx, db, pinned, w.wins, w.segs, 5, torch.cuda.synchronize)
+    ctx.ref_clear()
     for (pb, lb, lw, sl) in pinned:
         ctx.ref_add(pb, lb, lw, sl)
     plan = ctx.plan(31, w.wins, w.segs)
@@ -709,8 +711,8 @@ def c3_leg(torch, ctx, stream, device, host_cores: int, rank: int) -> dict:
         res = plan.fetch()
         kmers = int(res["total_kmers"].sum())
         plan.close()
-        ctx_seqs = None
         ms, rows = e2e_leg(torch, ctx, db, pinned, wins, segs, 3, torch.cuda.synchronize)
+        ctx.ref_clear()
         for (pb, lb, lw, sl) in pinned:  # the e2e call replaced the resident sequences
             ctx.ref_add(pb, lb, lw, sl)
         nchk = min(wins.size, 3000)

@@ -141,6 +141,12 @@ extern "C" void kcf_shutdown(kcf_ctx *ctx)
         if (ctx->h2d_done[i]) cudaEventDestroy(ctx->h2d_done[i]);
     }
     if (ctx->plan_ready) cudaEventDestroy(ctx->plan_ready);
+    for (int i = 0; i < 8; ++i) {
+        if (ctx->ing_h[i]) cudaFreeHost(ctx->ing_h[i]);
+        if (ctx->ing_d[i]) cudaFree(ctx->ing_d[i]);
+        if (ctx->ing_free[i]) cudaEventDestroy(ctx->ing_free[i]);
+        if (ctx->ing_copied[i]) cudaEventDestroy(ctx->ing_copied[i]);
+    }
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     for (int i = 0; i < 4; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

@@ -19,31 +19,20 @@
 #include <unistd.h>
 #include "kcf_internal.cuh"
 #include "kcf_lookup.cuh"
+#include <atomic>
 #include <thread>
+#include <vector>
 
+// The records reach the device through a ring of pinned staging buffers kept by the context (pinned allocations cost
+// tens of milliseconds; a getVariations run opens one database, a cohort run many).  Filling a slot is a host memcpy out of
+// the page cache (or the caller's array): KCF_INGEST_FILLERS threads each fill whole chunks, KCF_INGEST_SLOTS chunks ahead
+// of the device, so the copy engine never waits for the host (one thread alone moves ~10 GB/s, PCIe 55).
 #ifndef KCF_INGEST_CHUNK_BYTES
-#define KCF_INGEST_CHUNK_BYTES (64ULL << 20) // staging chunk (two pinned + two device buffers of this size; 128 MB measured no faster)
+#define KCF_INGEST_CHUNK_BYTES (16ULL << 20)
 #endif
-
-// The records reach the device through two pinned staging buffers; filling them is a host memcpy out of the page cache
-// (or the caller's array), and one thread doing it (~11 GB/s) was slower than the ingest kernel it feeds.
-static void kcf_parallel_copy(uint8_t *dst, const uint8_t *src, size_t n)
-{
-    static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const unsigned nt = (unsigned)std::min<size_t>(std::min(hw > 2 ? hw - 2 : 1u, 12u), std::max<size_t>(n >> 22, 1)); // >= 4 MB per thread
-    if (nt <= 1) {
-        memcpy(dst, src, n);
-        return;
-    }
-    std::thread th[12];
-    const size_t per = ((n / nt) + 4095) & ~(size_t)4095;
-    for (unsigned t = 0; t < nt; ++t) {
-        const size_t a = std::min(n, (size_t)t * per), b = (t + 1 == nt) ? n : std::min(n, (size_t)(t + 1) * per);
-        th[t] = std::thread([=] { if (b > a) memcpy(dst + a, src + a, b - a); });
-    }
-    for (unsigned t = 0; t < nt; ++t) th[t].join();
-}
-
+#define KCF_INGEST_SLOTS 8
+#define KCF_INGEST_FILLERS 8
+static_assert(KCF_INGEST_SLOTS <= 8 && KCF_INGEST_FILLERS <= KCF_INGEST_SLOTS, "the context holds 8 staging slots; a filler owns a slot while it fills it");
 
 // ---- Signature.java:23-95 on the device: one thread per m-mer -----------------------------------
 __device__ __forceinline__ bool sig_allowed(uint32_t s, int L)
@@ -74,6 +63,43 @@ __global__ void kcf_norm_kernel(int L, uint32_t *__restrict__ norm)
     uint32_t a = sig_allowed(i, L) ? i : special;
     uint32_t b = sig_allowed(rev, L) ? rev : special;
     norm[i] = min(a, b);
+}
+
+// bit i = Signature.isAllowed(i): 32 m-mers per thread.  4^9 bits = 32 KB: the ingest kernel keeps it in shared memory and
+// computes norm(m) = min(allowed(m) ? m : 4^L, allowed(rc m) ? rc m : 4^L) (Signature.java:28-35) from it, instead of
+// gathering 23 words per record from the 1 MB norm table through L2.
+__global__ void kcf_allowed_kernel(int L, uint32_t *__restrict__ bits)
+{
+    const uint32_t n_words = (1u << (2 * L)) >> 5;
+    const uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= (n_words ? n_words : 1u)) return;
+    uint32_t v = 0;
+    for (uint32_t b = 0; b < 32; ++b) {
+        const uint32_t i = wi * 32 + b;
+        if (i < (1u << (2 * L)) && sig_allowed(i, L)) v |= 1u << b;
+    }
+    bits[wi] = v;
+}
+
+// signature of a k-mer (the reference's value): min norm over its k-L+1 m-mers, first base most significant
+// (Kmer.java:105-118), both strands of every m-mer rolled along
+template <typename BitsPtr>
+__device__ __forceinline__ uint32_t kcf_signature_from_bits(uint64_t kmer, uint32_t k, uint32_t L, BitsPtr A)
+{
+    const uint32_t special = 1u << (2 * L), mmask = special - 1u;
+    uint32_t m = (uint32_t)(kmer >> (2 * (k - L))) & mmask, rc = 0;
+    for (uint32_t j = 0, t = m; j < L; ++j, t >>= 2) rc = (rc << 2) | ((~t) & 3u);
+    uint32_t sig = 0xFFFFFFFFu;
+    for (uint32_t j = 0;; ++j) {
+        const uint32_t a = ((A[m >> 5] >> (m & 31u)) & 1u) ? m : special;
+        const uint32_t b = ((A[rc >> 5] >> (rc & 31u)) & 1u) ? rc : special;
+        sig = min(sig, min(a, b));
+        if (j == k - L) break;
+        const uint32_t nb = (uint32_t)(kmer >> (2 * (k - L - j - 1))) & 3u; // the base entering on the right
+        m = ((m << 2) | nb) & mmask;
+        rc = (rc >> 2) | ((3u - nb) << (2 * (L - 1)));
+    }
+    return sig;
 }
 
 // LUT must be non-decreasing and bounded by total (else the reference reads garbage ranges)
@@ -112,12 +138,13 @@ struct KcfIngestParams {
     uint64_t lut_len;
     const uint64_t *cta_bound; // per CTA of this chunk (+1): first LUT index whose value exceeds the CTA's first record
     const uint32_t *sigmap;
-    const uint32_t *norm;
+    const uint32_t *allowed;  // Signature.isAllowed bitmap, 4^L bits
+    uint32_t n_groups;        // groups of 256 consecutive records in this chunk
     uint32_t P, L, nsb, cs, rec_size;
     uint8_t *table;
     KcfStashEntry *ovf;      // overflow list
     uint64_t ovf_cap;
-    unsigned long long *counters; // [0] inserted, [1] unreachable, [2] overflow, [3] owned by another rank
+    unsigned long long *counters; // [0] inserted, [1] unreachable, [2] overflow (also the list's cursor), [3] owned by another rank
     uint32_t part_rank, part_world;
     uint32_t *flags;
 };
@@ -136,25 +163,23 @@ __device__ __forceinline__ void kcf_filter_add(uint8_t *home_line, uint64_t key,
     }
 }
 
-__global__ void __launch_bounds__(256) kcf_ingest_kernel(KcfIngestParams p, KcfTableGeom g)
+// one record: proof of reachability, then the insert.  Returns what became of it: 0 resident in a line, 1 unreachable,
+// 2 resident in the overflow list (stash), 3 homed in another rank's slice.
+template <typename BitsPtr>
+__device__ __forceinline__ int kcf_ingest_one(const KcfIngestParams &p, const KcfTableGeom &g, uint64_t t, uint32_t group, BitsPtr allowed)
 {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    // (bin, prefix) range holding record i: last idx with lut[idx] <= i.  The LUT is monotone, so the answers of a CTA's
-    // 256 consecutive records lie between those of its first record and of the next CTA's first record, which
-    // kcf_lut_bounds_kernel searched beforehand (23 dependent loads for 512 bins x 4^7 prefixes, once per CTA instead of
+    // (bin, prefix) range holding record i: last idx with lut[idx] <= i.  The LUT is monotone, so the answers of a group's
+    // 256 consecutive records lie between those of its first record and of the next group's first record, which
+    // kcf_lut_bounds_kernel searched beforehand (23 dependent loads for 512 bins x 4^7 prefixes, once per group instead of
     // once per record); what is left here is a search over the few entries in between.
-    if (t >= p.n_rec) return;
     const uint64_t i = p.rec0 + t;
-    uint64_t lo = p.cta_bound[blockIdx.x], hi = p.cta_bound[blockIdx.x + 1];
+    uint64_t lo = p.cta_bound[group], hi = p.cta_bound[group + 1];
     while (lo < hi) {
         uint64_t mid = (lo + hi) >> 1;
         if (p.lut[mid] <= i) lo = mid + 1;
         else hi = mid;
     }
-    if (lo == 0) {
-        atomicAdd(&p.counters[1], 1ULL);
-        return;
-    }
+    if (lo == 0) return 1;
     const uint64_t idx = lo - 1;
     const uint32_t bin = (uint32_t)(idx >> (2 * p.P));
     const uint64_t prefix = idx & ((1ULL << (2 * p.P)) - 1);
@@ -177,31 +202,13 @@ __global__ void __launch_bounds__(256) kcf_ingest_kernel(KcfIngestParams p, KcfT
         uint64_t rc = kcf_revcomp(kmer, g.kshift);
         if (kmer > rc) reachable = false; // a query is canonicalised first (GetVariants.java:222)
     }
-    if (reachable) {
-        // signature = min norm over the k-L+1 m-mers, first base most significant (Kmer.java:105-118)
-        const uint32_t mmask = (1u << (2 * p.L)) - 1u;
-        uint32_t sig = 0xFFFFFFFFu;
-        for (int j = 0; j <= (int)g.k - (int)p.L; ++j) {
-            uint32_t m = (uint32_t)(kmer >> (2 * (g.k - p.L - j))) & mmask;
-            sig = min(sig, p.norm[m]);
-        }
-        if (p.sigmap[sig] != bin) reachable = false; // KMC.java:300
-    }
-    if (!reachable) {
-        atomicAdd(&p.counters[1], 1ULL);
-        return;
-    }
-    if (p.cs == 0) { // Q7: a 0-byte counter reads as 0, never a hit; nothing to store
-        atomicAdd(&p.counters[0], 1ULL);
-        return;
-    }
+    if (reachable && p.sigmap[kcf_signature_from_bits(kmer, g.k, p.L, allowed)] != bin) reachable = false; // KMC.java:300
+    if (!reachable) return 1;
+    if (p.cs == 0) return 0; // Q7: a 0-byte counter reads as 0, never a hit; nothing to store
     // proof done in the reference's encoding; from here on the record is its table key (bit planes, kcf_lookup.cuh)
     const uint64_t tkey = kcf_table_key(kmer, g);
     const uint32_t home = kcf_home_line(kcf_minimizer_of_key(tkey, g), g);
-    if (p.part_world > 1 && kcf_line_owner(home, g.n_lines, p.part_world) != p.part_rank) { // another rank's slice
-        atomicAdd(&p.counters[3], 1ULL);
-        return;
-    }
+    if (p.part_world > 1 && kcf_line_owner(home, g.n_lines, p.part_world) != p.part_rank) return 3; // another rank's slice
     uint8_t *home_line = p.table + (uint64_t)kcf_line_wrap(home, 0, g) * KCF_LINE_BYTES;
     uint32_t *home_w31 = reinterpret_cast<uint32_t *>(home_line) + 31;
     if (KCF_KEY_IN_LINES(tkey)) {
@@ -243,13 +250,12 @@ __global__ void __launch_bounds__(256) kcf_ingest_kernel(KcfIngestParams p, KcfT
                     atomicAnd(w + (off >> 2), ~field | (count << sh));
                     atomicAnd(home_w31, ~(1u << (16 + d)));
                     if (d > 0) kcf_filter_add(home_line, tkey, g);
-                    atomicAdd(&p.counters[0], 1ULL);
                     placed = true;
                     break;
                 }
                 if (v == lo) dup = true;
             }
-            if (placed) return;
+            if (placed) return 0;
         }
     }
     atomicAnd(home_w31, ~(1u << (16 + KCF_STASH_BIT)));
@@ -259,7 +265,33 @@ __global__ void __launch_bounds__(256) kcf_ingest_kernel(KcfIngestParams p, KcfT
         p.ovf[pos].key = tkey;
         p.ovf[pos].meta = (1ULL << 63) | count;
     }
+    return 2;
 }
+
+// CTAs stride over the chunk's groups of 256 consecutive records; the allowed-m-mer bitmap is loaded into shared memory
+// once per CTA (SMEM_BITS: 4^L bits fit, i.e. L <= 9), the per-record outcomes are counted in shared memory and reach the
+// global counters with one atomic per CTA and outcome
+template <bool SMEM_BITS>
+__global__ void __launch_bounds__(256) kcf_ingest_kernel(KcfIngestParams p, KcfTableGeom g)
+{
+    extern __shared__ uint32_t s_allowed[];
+    __shared__ unsigned int s_cnt[4];
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    if (SMEM_BITS) {
+        const uint32_t n_words = (1u << (2 * p.L)) >> 5;
+        for (uint32_t i = threadIdx.x; i < (n_words ? n_words : 1u); i += blockDim.x) s_allowed[i] = p.allowed[i];
+    }
+    __syncthreads();
+    for (uint32_t group = blockIdx.x; group < p.n_groups; group += gridDim.x) {
+        const uint64_t t = (uint64_t)group * 256 + threadIdx.x;
+        if (t >= p.n_rec) continue;
+        const int what = SMEM_BITS ? kcf_ingest_one(p, g, t, group, (const uint32_t *)s_allowed) : kcf_ingest_one(p, g, t, group, p.allowed);
+        if (what != 2) atomicAdd(&s_cnt[what], 1u); // the overflow list counts its own entries
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(&p.counters[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+}
+
 
 __global__ void kcf_stash_build_kernel(const KcfStashEntry *__restrict__ ovf, uint64_t n, KcfStashEntry *stash, KcfTableGeom g)
 {
@@ -454,20 +486,20 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     kcf_db *db = new kcf_db();
     db->ctx = ctx;
     uint64_t *d_lut = nullptr;
-    uint32_t *d_sigmap = nullptr, *d_norm = nullptr;
-    uint8_t *d_stage[2] = {nullptr, nullptr};
-    uint8_t *h_stage[2] = {nullptr, nullptr};
+    uint32_t *d_sigmap = nullptr, *d_allowed = nullptr;
     KcfStashEntry *d_ovf = nullptr;
     unsigned long long *d_counters = nullptr;
-    uint64_t *d_bound = nullptr; // per-CTA LUT bounds of the chunk in flight
-    cudaEvent_t ev[2] = {nullptr, nullptr};    // ingest kernel of the chunk staged in buffer j done: both staging buffers j reusable
-    cudaEvent_t evc[2] = {nullptr, nullptr};   // H2D copy of buffer j done
+    uint64_t *d_bound = nullptr; // per-group LUT bounds of the chunk in flight
     int rc = KCF_OK;
-    const uint64_t chunk_rec = std::max<uint64_t>(1, (KCF_INGEST_CHUNK_BYTES) / std::max<uint32_t>(rec_size, 1));
+    const uint64_t chunk_rec = std::max<uint64_t>(256, (KCF_INGEST_CHUNK_BYTES) / std::max<uint32_t>(rec_size, 1) / 256 * 256);
     const uint64_t chunk_bytes = chunk_rec * std::max<uint32_t>(rec_size, 1);
-    uint64_t ovf_cap = N / 16 + 4096;
+    const uint64_t n_chunks = (N + chunk_rec - 1) / chunk_rec;
+    uint64_t ovf_cap = N / 64 + 4096; // a second pass follows if the list turns out longer (dense tables, colliding minimizers)
     unsigned long long counters[4] = {0, 0, 0, 0};
     uint32_t flags[FLAG_COUNT] = {0};
+    const bool smem_bits = L <= 9; // 4^9 bits = 32 KB of shared memory
+    const size_t bits_bytes = std::max<size_t>(((size_t)1 << (2 * L)) / 8, 4);
+    db->table_bytes = nb * KCF_LINE_BYTES;
 
 #define DB_CUDA(call)                                                                                         \
     do {                                                                                                      \
@@ -479,33 +511,45 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
         }                                                                                                     \
     } while (0)
 
-    if (cudaMalloc(&db->table, nb * KCF_LINE_BYTES) != cudaSuccess) { // give the context's recycled blocks back to the driver, try again
-        (void)cudaGetLastError();
-        kcf_pool_trim(ctx);
-        DB_CUDA(cudaMalloc(&db->table, nb * KCF_LINE_BYTES));
+    // the table comes from the context's block pool: a host that opens one database after the other (a cohort run) gets the
+    // previous table's memory back without a cudaFree / cudaMalloc round trip
+    db->table = (uint8_t *)kcf_pool_get(ctx, db->table_bytes);
+    if (!db->table) {
+        rc = kcf_fail(ctx, KCF_ERR_NOMEM, "device memory for a table of %llu lines (%.1f GB)", (unsigned long long)nb, (double)db->table_bytes / 1e9);
+        goto done;
     }
     DB_CUDA(cudaMemsetAsync(db->table, 0xFF, nb * KCF_LINE_BYTES, ctx->stream)); // empty keys, zero counts and masks (stored inverted)
+    if (ctx->ing_slot_bytes < chunk_bytes) { // the staging ring, allocated by the context's first open
+        for (int j = 0; j < KCF_INGEST_SLOTS; ++j) {
+            if (ctx->ing_h[j]) cudaFreeHost(ctx->ing_h[j]);
+            if (ctx->ing_d[j]) cudaFree(ctx->ing_d[j]);
+            ctx->ing_h[j] = ctx->ing_d[j] = nullptr;
+        }
+        ctx->ing_slot_bytes = 0;
+        for (int j = 0; j < KCF_INGEST_SLOTS; ++j) {
+            DB_CUDA(cudaHostAlloc(&ctx->ing_h[j], chunk_bytes, cudaHostAllocDefault));
+            DB_CUDA(cudaMalloc(&ctx->ing_d[j], chunk_bytes));
+            if (!ctx->ing_free[j]) DB_CUDA(cudaEventCreateWithFlags(&ctx->ing_free[j], cudaEventDisableTiming));
+            if (!ctx->ing_copied[j]) DB_CUDA(cudaEventCreateWithFlags(&ctx->ing_copied[j], cudaEventDisableTiming));
+        }
+        ctx->ing_slot_bytes = chunk_bytes;
+    }
     DB_CUDA(cudaMalloc(&d_lut, std::max<uint64_t>(lut_len, 1) * 8));
     DB_CUDA(cudaMalloc(&d_sigmap, sig_map_size * 4));
-    DB_CUDA(cudaMalloc(&d_norm, (1ULL << (2 * L)) * 4));
+    DB_CUDA(cudaMalloc(&d_allowed, bits_bytes));
     DB_CUDA(cudaMalloc(&d_counters, 4 * sizeof(unsigned long long)));
-    DB_CUDA(cudaMalloc(&d_bound, ((chunk_rec + 255) / 256 + 2) * sizeof(uint64_t)));
+    DB_CUDA(cudaMalloc(&d_bound, (chunk_rec / 256 + 2) * sizeof(uint64_t)));
     DB_CUDA(cudaMemsetAsync(d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
     DB_CUDA(cudaMemsetAsync(ctx->d_flags, 0, FLAG_COUNT * sizeof(uint32_t), ctx->stream));
     DB_CUDA(cudaMalloc(&d_ovf, ovf_cap * sizeof(KcfStashEntry)));
     if (lut_len) DB_CUDA(cudaMemcpyAsync(d_lut, pre + 4, lut_len * 8, cudaMemcpyHostToDevice, ctx->stream)); // KMC.java:153,159-163
     DB_CUDA(cudaMemcpyAsync(d_sigmap, pre + sig_map_start, sig_map_size * 4, cudaMemcpyHostToDevice, ctx->stream)); // :145-151
     {
-        uint32_t special = 1u << (2 * L);
-        kcf_norm_kernel<<<(special + 255) / 256, 256, 0, ctx->stream>>>(L, d_norm);
+        const uint32_t n_words = (uint32_t)(bits_bytes / 4);
+        kcf_allowed_kernel<<<(n_words + 255) / 256, 256, 0, ctx->stream>>>(L, d_allowed);
         if (lut_len) kcf_lut_check_kernel<<<(unsigned)((lut_len + 255) / 256), 256, 0, ctx->stream>>>(d_lut, lut_len, N, ctx->d_flags);
         DB_CUDA(cudaGetLastError());
-    }
-    for (int j = 0; j < 2; ++j) {
-        DB_CUDA(cudaMalloc(&d_stage[j], chunk_bytes));
-        DB_CUDA(cudaHostAlloc(&h_stage[j], chunk_bytes, cudaHostAllocDefault));
-        DB_CUDA(cudaEventCreateWithFlags(&ev[j], cudaEventDisableTiming));
-        DB_CUDA(cudaEventCreateWithFlags(&evc[j], cudaEventDisableTiming));
+        if (smem_bits) DB_CUDA(cudaFuncSetAttribute(kcf_ingest_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
     }
     for (int pass = 0; pass < 4; ++pass) {
         if (pass > 0) {
@@ -519,30 +563,54 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
             DB_CUDA(cudaMemsetAsync(d_counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
         }
         const uint8_t *recs = suf + 4; // KMC.java:94 — skip the KMCS marker
-        int j = 0;
-        for (uint64_t r0 = 0; r0 < N; r0 += chunk_rec, j ^= 1) {
-            uint64_t n = std::min<uint64_t>(chunk_rec, N - r0);
-            DB_CUDA(cudaEventSynchronize(ev[j])); // staging buffer j free again
-            kcf_parallel_copy(h_stage[j], recs + r0 * rec_size, n * rec_size); // page cache / caller memory -> pinned staging
-            // the copy rides the copy stream: chunk j+1 crosses PCIe while the ingest kernel of chunk j runs
-            DB_CUDA(cudaMemcpyAsync(d_stage[j], h_stage[j], n * rec_size, cudaMemcpyHostToDevice, ctx->copy_stream));
-            DB_CUDA(cudaEventRecord(evc[j], ctx->copy_stream));
-            DB_CUDA(cudaStreamWaitEvent(ctx->stream, evc[j], 0));
+        // ---- host side of the pipeline: filler threads copy whole chunks into the pinned ring, this thread queues the H2D
+        // copy (copy stream) and the ingest kernel (main stream) of every chunk in order.  Slot s = chunk % SLOTS is free
+        // again when the kernel of chunk - SLOTS has run (event ing_free[s], recorded by this thread: `launched` tells the
+        // fillers that it has been).
+        std::atomic<uint64_t> launched{0};
+        std::vector<std::atomic<int>> ready(n_chunks);
+        for (auto &r : ready) r.store(0, std::memory_order_relaxed);
+        std::atomic<int> abort_fill{0};
+        const unsigned n_fill = (unsigned)std::min<uint64_t>(KCF_INGEST_FILLERS, std::max<uint64_t>(n_chunks, 1));
+        std::vector<std::thread> fillers;
+        for (unsigned f = 0; f < n_fill; ++f)
+            fillers.emplace_back([&, f] {
+                cudaSetDevice(ctx->device);
+                for (uint64_t c = f; c < n_chunks; c += n_fill) {
+                    const int sl = (int)(c % KCF_INGEST_SLOTS);
+                    if (c >= KCF_INGEST_SLOTS) {
+                        while (launched.load(std::memory_order_acquire) + KCF_INGEST_SLOTS <= c && !abort_fill.load()) std::this_thread::yield();
+                        if (abort_fill.load()) return;
+                        cudaEventSynchronize(ctx->ing_free[sl]); // the kernel that last read this slot's device buffer (its H2D copy came before)
+                    }
+                    const uint64_t r0 = c * chunk_rec, n = std::min<uint64_t>(chunk_rec, N - r0);
+                    memcpy(ctx->ing_h[sl], recs + r0 * rec_size, n * rec_size); // page cache / caller memory -> pinned staging
+                    ready[c].store(1, std::memory_order_release);
+                }
+            });
+        cudaError_t perr = cudaSuccess;
+        for (uint64_t c = 0; c < n_chunks && perr == cudaSuccess; ++c) {
+            const int sl = (int)(c % KCF_INGEST_SLOTS);
+            const uint64_t r0 = c * chunk_rec, n = std::min<uint64_t>(chunk_rec, N - r0);
+            while (!ready[c].load(std::memory_order_acquire)) std::this_thread::yield();
+            // the copy rides the copy stream: later chunks cross PCIe while the ingest kernel of this one runs
+            perr = cudaMemcpyAsync(ctx->ing_d[sl], ctx->ing_h[sl], n * rec_size, cudaMemcpyHostToDevice, ctx->copy_stream);
+            if (perr == cudaSuccess) perr = cudaEventRecord(ctx->ing_copied[sl], ctx->copy_stream);
+            if (perr == cudaSuccess) perr = cudaStreamWaitEvent(ctx->stream, ctx->ing_copied[sl], 0);
+            if (perr != cudaSuccess) break;
             KcfIngestParams p{};
-            p.rec = d_stage[j];
+            p.rec = ctx->ing_d[sl];
             p.rec0 = r0;
             p.n_rec = n;
             memset(p.prev, 0, sizeof p.prev);
             if (r0 > 0) memcpy(p.prev, recs + (r0 - 1) * rec_size, std::min<uint32_t>(rec_size, 16));
             p.lut = d_lut;
             p.lut_len = lut_len;
-            {
-                const uint32_t n_cta = (uint32_t)((n + 255) / 256);
-                kcf_lut_bounds_kernel<<<(n_cta + 1 + 255) / 256, 256, 0, ctx->stream>>>(d_lut, lut_len, r0, n, n_cta, d_bound);
-            }
+            p.n_groups = (uint32_t)((n + 255) / 256);
+            kcf_lut_bounds_kernel<<<(p.n_groups + 1 + 255) / 256, 256, 0, ctx->stream>>>(d_lut, lut_len, r0, n, p.n_groups, d_bound);
             p.cta_bound = d_bound;
             p.sigmap = d_sigmap;
-            p.norm = d_norm;
+            p.allowed = d_allowed;
             p.P = (uint32_t)P;
             p.L = (uint32_t)L;
             p.nsb = nsb;
@@ -555,9 +623,20 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
             p.part_rank = part_rank;
             p.part_world = part_world;
             p.flags = ctx->d_flags;
-            kcf_ingest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(p, g);
-            DB_CUDA(cudaGetLastError());
-            DB_CUDA(cudaEventRecord(ev[j], ctx->stream));
+            const unsigned grid = (unsigned)std::min<uint64_t>(p.n_groups, (uint64_t)ctx->sm_count * 6);
+            if (smem_bits) kcf_ingest_kernel<true><<<grid, 256, 32768, ctx->stream>>>(p, g);
+            else kcf_ingest_kernel<false><<<grid, 256, 0, ctx->stream>>>(p, g);
+            perr = cudaGetLastError();
+            if (perr == cudaSuccess) perr = cudaEventRecord(ctx->ing_free[sl], ctx->stream);
+            launched.store(c + 1, std::memory_order_release);
+        }
+        if (perr != cudaSuccess) abort_fill.store(1);
+        launched.store(n_chunks + KCF_INGEST_SLOTS, std::memory_order_release); // releases fillers waiting on a chunk that will not be launched
+        for (std::thread &t : fillers) t.join();
+        if (perr != cudaSuccess) {
+            cudaStreamSynchronize(ctx->stream);
+            rc = kcf_fail(ctx, KCF_ERR_CUDA, "database ingest: %s", cudaGetErrorString(perr));
+            goto done;
         }
         DB_CUDA(cudaMemcpyAsync(counters, d_counters, sizeof counters, cudaMemcpyDeviceToHost, ctx->stream));
         DB_CUDA(cudaMemcpyAsync(flags, ctx->d_flags, sizeof flags, cudaMemcpyDeviceToHost, ctx->stream));
@@ -590,20 +669,17 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     db->geom = g;
 
 done:
-    for (int j = 0; j < 2; ++j) {
-        if (d_stage[j]) cudaFree(d_stage[j]);
-        if (h_stage[j]) cudaFreeHost(h_stage[j]);
-        if (ev[j]) cudaEventDestroy(ev[j]);
-        if (evc[j]) cudaEventDestroy(evc[j]);
-    }
     if (d_lut) cudaFree(d_lut);
     if (d_sigmap) cudaFree(d_sigmap);
-    if (d_norm) cudaFree(d_norm);
+    if (d_allowed) cudaFree(d_allowed);
     if (d_ovf) cudaFree(d_ovf);
     if (d_counters) cudaFree(d_counters);
     if (d_bound) cudaFree(d_bound);
     if (rc != KCF_OK) {
-        if (db->table) cudaFree(db->table);
+        if (db->table) {
+            cudaStreamSynchronize(ctx->stream);
+            kcf_pool_put(ctx, db->table, db->table_bytes);
+        }
         if (db->stash) cudaFree(db->stash);
         delete db;
         return rc;
@@ -661,7 +737,10 @@ extern "C" void kcf_db_close(kcf_db *db)
 {
     if (!db) return;
     cudaSetDevice(db->ctx->device);
-    if (db->table) cudaFree(db->table);
+    if (db->table) {
+        cudaStreamSynchronize(db->ctx->stream); // nothing queued may still read the table once its block can be handed out again
+        kcf_pool_put(db->ctx, db->table, db->table_bytes);
+    }
     if (db->stash) cudaFree(db->stash);
     delete db;
 }

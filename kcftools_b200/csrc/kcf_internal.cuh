@@ -164,6 +164,12 @@ struct kcf_ctx {
     float last_screen_ms = 0.f, last_finalize_ms = 0.f;
     bool ev_valid = false;
     uint32_t *d_flags = nullptr; // device error / status flags (database load)
+    // database ingest: ring of pinned host / device staging buffers, kept across kcf_db_open calls
+    uint8_t *ing_h[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint8_t *ing_d[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ing_free[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // kernel that read slot j done
+    cudaEvent_t ing_copied[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // H2D copy of slot j done
+    size_t ing_slot_bytes = 0;
     uint64_t ref_generation = 1; // bumped by kcf_ref_clear: plans remember the generation they were built against
 };
 
@@ -172,7 +178,8 @@ struct kcf_db {
     int part_rank = 0, part_world = 1; // > 1: this table holds one slice of the line space (placement 1)
     kcf_db_info_t info{};
     KcfTableGeom geom{};
-    uint8_t *table = nullptr;        // n_lines * 128 bytes
+    uint8_t *table = nullptr;        // n_lines * 128 bytes, from the context's block pool
+    size_t table_bytes = 0;
     KcfStashEntry *stash = nullptr;  // stash_mask + 1 entries
 };
 

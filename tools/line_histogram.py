@@ -7,7 +7,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import bench
 from kcftools_b200.api import Context, KMC
-fasta, kmc, window, _ = bench.build_workload("c2", "cuda:0")
+wl_ = bench.build_workload("c2", "cuda:0")
+fasta, kmc, window = wl_.fasta, wl_.kmc, wl_.window
 ctx = Context(0); db = KMC(ctx, pre=kmc.pre, suf=kmc.suf)
 h = np.zeros(16, np.uint64)
 ctx._check(ctx._lib.kcf_db_line_histogram(db._h, h.ctypes.data))

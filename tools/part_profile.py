@@ -14,7 +14,8 @@ from kcftools_b200.api import Context, KMC, fixed_windows  # noqa: E402
 from kcftools_b200.partitioned import screen_partitioned_local  # noqa: E402
 
 world = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-fasta, kmc, window, desc = bench.build_workload("c2s", "cuda:0")
+wl_ = bench.build_workload("c2s", "cuda:0")
+fasta, kmc, window, desc = wl_.fasta, wl_.kmc, wl_.window, wl_.desc
 wins, segs, *_ = fixed_windows(fasta.lengths, window, 0, 31)
 ranges = shard.partition(shard.window_lengths(wins, segs), world)
 ranks = []

@@ -39,7 +39,8 @@ def main():
     from kcftools_b200.api import KMC, Context, fixed_windows
     from tools import synth
     dev = "cuda:0"
-    fasta, kmc, window, _ = bench.build_workload(args.core, dev)
+    wl_ = bench.build_workload(args.core, dev)
+    fasta, kmc, window = wl_.fasta, wl_.kmc, wl_.window
     assert window == args.window
     core_len = fasta.lengths[0]
     n_core = len(fasta.names)
