@@ -453,7 +453,9 @@ def main():
             t2 = time.perf_counter()
             rows_ = screen_sharded([ctx], [db_], pinned, wl.wins, wl.segs)
             t3 = time.perf_counter()
-            cold["runs"].append({"seconds": t3 - t1, "db_open_s": t2 - t1, "screen_s": t3 - t2, "db_load_seconds_library": db_.info.load_seconds})
+            cold["runs"].append({"seconds": t3 - t1, "db_open_s": t2 - t1, "screen_s": t3 - t2, "db_load_seconds_library": db_.info.load_seconds,
+                                 "db_load_phase_s": {"setup": db_.info.load_phase_s[0], "stream": db_.info.load_phase_s[1], "drain": db_.info.load_phase_s[2],
+                                                     "device_ingest_kernels": db_.info.load_phase_s[3]}})
             cold_rows = rows_
             db_.close()
         k_ = int(cold_rows["total_kmers"].sum())
@@ -581,7 +583,7 @@ def main():
                             + ("; rows all-gathered over the ranks inside the timed region; h2d_* are rank 0's, h2d_copy_alone_ms = all ranks copying "
                                "their ranges at once, max over ranks" if world > 1 else "") + "; database resident (db_load_s)"},
             "gpu_launches": int(args.steps * plan.kernels_per_run),
-            "roofline": roof, "clocks": clocks, "db_load_s": db_load_s, "table": table, "checks": checks,
+            "roofline": roof, "clocks": clocks, "db_load_s": db_load_s, "db_load_phase_s": [round(x, 4) for x in db.info.load_phase_s], "table": table, "checks": checks,
             "kmers_per_step": job_kmers, "kmers_per_step_this_rank": my_kmers, "obs_fraction": float(res["obs"].sum() / max(my_kmers, 1))}
     if cold is not None:
         line["e2e_cold"] = cold

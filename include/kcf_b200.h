@@ -96,6 +96,9 @@ typedef struct kcf_db_info_t {
     int64_t n_buckets;          /* 128-byte table lines */
     double load_seconds;        /* wall time of the open call */
     int64_t elsewhere_kmers;    /* placement 1: reachable records whose home line belongs to another rank's slice */
+    double load_phase_s[4];     /* where load_seconds went: [0] allocations + table reset queued, [1] records streamed (host staging,
+                                 * H2D copies and ingest kernels queued), [2] wait for the device + stash build, [3] device time from the
+                                 * first to the last ingest kernel (CUDA events) */
 } kcf_db_info_t;
 
 /* ---- context ------------------------------------------------------------------------- */

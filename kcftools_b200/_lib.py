@@ -39,7 +39,7 @@ class DbInfo(C.Structure):
                 ("max_count", C.c_int32), ("n_bins", C.c_int32), ("total_kmers", C.c_int64),
                 ("resident_kmers", C.c_int64), ("unreachable_kmers", C.c_int64), ("stash_kmers", C.c_int64),
                 ("table_bytes", C.c_int64), ("n_buckets", C.c_int64), ("load_seconds", C.c_double),
-                ("elsewhere_kmers", C.c_int64)]
+                ("elsewhere_kmers", C.c_int64), ("load_phase_s", C.c_double * 4)]
 
 
 # every symbol include/kcf_b200.h declares: name -> (restype, argtypes)

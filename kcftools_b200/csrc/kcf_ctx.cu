@@ -148,6 +148,7 @@ extern "C" void kcf_shutdown(kcf_ctx *ctx)
         if (ctx->ing_copied[i]) cudaEventDestroy(ctx->ing_copied[i]);
     }
     if (ctx->d_flags) cudaFree(ctx->d_flags);
+    if (ctx->h_rows) cudaFreeHost(ctx->h_rows);
     for (int i = 0; i < 4; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

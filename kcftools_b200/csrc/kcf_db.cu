@@ -490,6 +490,8 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     KcfStashEntry *d_ovf = nullptr;
     unsigned long long *d_counters = nullptr;
     uint64_t *d_bound = nullptr; // per-group LUT bounds of the chunk in flight
+    cudaEvent_t ev_first = nullptr, ev_last = nullptr; // device time of the ingest kernels (kcf_db_info_t.load_phase_s)
+    std::chrono::steady_clock::time_point t_setup = t0, t_streamed = t0;
     int rc = KCF_OK;
     const uint64_t chunk_rec = std::max<uint64_t>(256, (KCF_INGEST_CHUNK_BYTES) / std::max<uint32_t>(rec_size, 1) / 256 * 256);
     const uint64_t chunk_bytes = chunk_rec * std::max<uint32_t>(rec_size, 1);
@@ -551,6 +553,9 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
         DB_CUDA(cudaGetLastError());
         if (smem_bits) DB_CUDA(cudaFuncSetAttribute(kcf_ingest_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
     }
+    cudaEventCreate(&ev_first);
+    cudaEventCreate(&ev_last);
+    t_setup = t_streamed = std::chrono::steady_clock::now();
     for (int pass = 0; pass < 4; ++pass) {
         if (pass > 0) {
             // the overflow list was too short (a table whose minimizers collide massively): the device counted
@@ -624,12 +629,15 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
             p.part_world = part_world;
             p.flags = ctx->d_flags;
             const unsigned grid = (unsigned)std::min<uint64_t>(p.n_groups, (uint64_t)ctx->sm_count * 6);
+            if (c == 0) cudaEventRecord(ev_first, ctx->stream);
             if (smem_bits) kcf_ingest_kernel<true><<<grid, 256, 32768, ctx->stream>>>(p, g);
             else kcf_ingest_kernel<false><<<grid, 256, 0, ctx->stream>>>(p, g);
             perr = cudaGetLastError();
             if (perr == cudaSuccess) perr = cudaEventRecord(ctx->ing_free[sl], ctx->stream);
             launched.store(c + 1, std::memory_order_release);
         }
+        cudaEventRecord(ev_last, ctx->stream);
+        t_streamed = std::chrono::steady_clock::now();
         if (perr != cudaSuccess) abort_fill.store(1);
         launched.store(n_chunks + KCF_INGEST_SLOTS, std::memory_order_release); // releases fillers waiting on a chunk that will not be launched
         for (std::thread &t : fillers) t.join();
@@ -665,10 +673,20 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     db->part_world = (int)part_world;
     info.table_bytes = (int64_t)(nb * KCF_LINE_BYTES + (db->stash ? (g.stash_mask + 1) * sizeof(KcfStashEntry) : 0));
     info.load_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    info.load_phase_s[0] = std::chrono::duration<double>(t_setup - t0).count();
+    info.load_phase_s[1] = std::chrono::duration<double>(t_streamed - t_setup).count();
+    info.load_phase_s[2] = info.load_seconds - info.load_phase_s[0] - info.load_phase_s[1];
+    {
+        float ms = 0;
+        if (N > 0 && cudaEventElapsedTime(&ms, ev_first, ev_last) == cudaSuccess) info.load_phase_s[3] = ms * 1e-3;
+        else (void)cudaGetLastError();
+    }
     db->info = info;
     db->geom = g;
 
 done:
+    if (ev_first) cudaEventDestroy(ev_first);
+    if (ev_last) cudaEventDestroy(ev_last);
     if (d_lut) cudaFree(d_lut);
     if (d_sigmap) cudaFree(d_sigmap);
     if (d_allowed) cudaFree(d_allowed);

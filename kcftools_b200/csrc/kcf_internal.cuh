@@ -170,6 +170,8 @@ struct kcf_ctx {
     cudaEvent_t ing_free[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // kernel that read slot j done
     cudaEvent_t ing_copied[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // H2D copy of slot j done
     size_t ing_slot_bytes = 0;
+    uint8_t *h_rows = nullptr; // pinned landing area for the rows of a sharded job (kcf_multi.cu): all plans fetched with one wait
+    size_t h_rows_cap = 0;
     uint64_t ref_generation = 1; // bumped by kcf_ref_clear: plans remember the generation they were built against
 };
 

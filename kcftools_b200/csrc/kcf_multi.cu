@@ -158,13 +158,42 @@ static int kcf_screen_shard(kcf_ctx *ctx, kcf_db *db, const kcf_host_seq_t *seqs
         rc = kcf_plan_run(ctx, db, plan, min_count, w);
         if (rc != KCF_OK) return cleanup(), rc;
     }
-    std::vector<kcf_result_t> rows;
-    for (size_t j = 0; j < plans.size(); ++j) {
-        rows.resize(plan_rows[j].second);
-        rc = kcf_plan_fetch(ctx, plans[j], rows.data());
-        if (rc != KCF_OK) return cleanup(), rc;
-        const std::vector<uint64_t> &ids = by_piece[plan_rows[j].first];
-        for (size_t i = 0; i < ids.size(); ++i) out[ids[i]] = rows[i];
+    // ---- all rows back with ONE wait: every plan's rows and status word are copied into a pinned landing area, then the
+    // stream is synchronised once (a fetch per plan would cost a host round trip per upload piece)
+    {
+        size_t total = 0;
+        for (auto &pr : plan_rows) total += pr.second * sizeof(kcf_result_t) + FLAG_COUNT * sizeof(uint32_t);
+        if (ctx->h_rows_cap < total) {
+            if (ctx->h_rows) cudaFreeHost(ctx->h_rows);
+            ctx->h_rows = nullptr;
+            ctx->h_rows_cap = 0;
+            const size_t cap = total + total / 4 + 4096;
+            if (cudaHostAlloc(&ctx->h_rows, cap, cudaHostAllocDefault) != cudaSuccess)
+                return cleanup(), kcf_fail(ctx, KCF_ERR_NOMEM, "pinned memory for %zu result bytes", total);
+            ctx->h_rows_cap = cap;
+        }
+        size_t off = 0;
+        cudaError_t e = cudaSuccess;
+        for (size_t j = 0; j < plans.size() && e == cudaSuccess; ++j) {
+            const size_t nb = plan_rows[j].second * sizeof(kcf_result_t);
+            e = cudaMemcpyAsync(ctx->h_rows + off, plans[j]->d_out, nb, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->h_rows + off + nb, plans[j]->d_flags, FLAG_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+            off += nb + FLAG_COUNT * sizeof(uint32_t);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) return cleanup(), kcf_fail(ctx, KCF_ERR_CUDA, "fetching the rows of a sharded job: %s", cudaGetErrorString(e));
+        off = 0;
+        for (size_t j = 0; j < plans.size(); ++j) {
+            const size_t nb = plan_rows[j].second * sizeof(kcf_result_t);
+            const kcf_result_t *rows = reinterpret_cast<const kcf_result_t *>(ctx->h_rows + off);
+            uint32_t flags[FLAG_COUNT];
+            memcpy(flags, ctx->h_rows + off + nb, sizeof flags);
+            // Data.java:101-103 — evaluated only for windows that reach the formula, left to right in double
+            if (flags[FLAG_SCORE_USED] && w[0] + w[1] + w[2] != 1.0) return cleanup(), kcf_fail(ctx, KCF_ERR_WEIGHTS, "Weights should sum to 1.0");
+            const std::vector<uint64_t> &ids = by_piece[plan_rows[j].first];
+            for (size_t i = 0; i < ids.size(); ++i) out[ids[i]] = rows[i];
+            off += nb + FLAG_COUNT * sizeof(uint32_t);
+        }
     }
     cleanup();
     return KCF_OK;

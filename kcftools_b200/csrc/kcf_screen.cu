@@ -331,6 +331,11 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
             };
 
             // ---- probe: lanes own consecutive positions ----
+            // minimizer of the k-mer ending at staged position q = min over the w m-mers ending at q-w+1 .. q -> home line
+            auto home_of = [&](uint32_t q) {
+                const uint32_t h0 = q - g.w + 1;
+                return kcf_home_line(FASTMIN ? W.hash[h0] : min(W.hash[h0], W.hash[h0 + g.w - P2]), g);
+            };
 #pragma unroll 1
             for (uint32_t j = 0; j < J; ++j) {
                 const uint32_t cpos = 32 * j + lane;  // chunk position of this lane's k-mer end
@@ -347,9 +352,7 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
                     if (BOTH) kcf_plane_canonical(klo, khi, kcf_plane_rc(klo, k, g.km), kcf_plane_rc(khi, k, g.km), klo, khi);
                 }
                 const uint64_t key = ((uint64_t)khi << 32) | klo;
-                // minimizer = min over the w m-mers ending at q-w+1 .. q -> home line
-                const uint32_t h0 = q - g.w + 1;
-                const uint32_t home = kcf_home_line(FASTMIN ? W.hash[h0] : min(W.hash[h0], W.hash[h0 + g.w - P2]), g);
+                const uint32_t home = home_of(q);
                 if (EXTRACT) {
                     const uint64_t base = (tile - p.tile_begin) * KCF_TILE + (uint64_t)chunk * KCF_CHUNK;
                     p.x_keys[base + cpos] = key;
