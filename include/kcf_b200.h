@@ -37,7 +37,7 @@ typedef enum kcf_status {
     KCF_ERR_CUDA = -1,          /* CUDA runtime failure or no device */
     KCF_ERR_IO = -2,            /* cannot read .kmc_pre / .kmc_suf */
     KCF_ERR_DB_FORMAT = -3,     /* not a KMC 0x200 database (KMC.java:139-141) or inconsistent sizes / LUT */
-    KCF_ERR_UNSUPPORTED = -4,   /* valid database outside the envelope (k > 32, (k-P) % 4 != 0, counter > 4 B, ...) */
+    KCF_ERR_UNSUPPORTED = -4,   /* valid database outside the envelope (k > 64, (k-P) % 4 != 0, counter > 4 B, k > 32 with a partitioned table, ...) */
     KCF_ERR_ARG = -5,           /* bad argument (null handle, min_count < 1 as GetVariants.java:383-385, ...) */
     KCF_ERR_RANGE = -6,         /* window segment outside its sequence (FastaIndex.java:132-135) or no segment (GetVariants.java:213-216) */
     KCF_ERR_FASTA = -7,         /* read past the mapped sequence bytes, e.g. no trailing newline (FastaIndex.java:175-177) */

@@ -91,9 +91,14 @@ void *kcf_pool_get(kcf_ctx *ctx, size_t bytes)
     void *p = nullptr;
     if (cudaMalloc(&p, bytes) != cudaSuccess) {
         // give the pooled blocks back to the driver and try once more
+        (void)cudaGetLastError(); // the failed allocation must not surface as the "last error" of a later launch check
+        cudaStreamSynchronize(ctx->stream);
         for (auto &b : ctx->pool) cudaFree(b.p);
         ctx->pool.clear();
-        if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return nullptr;
+        }
     }
     return p;
 }

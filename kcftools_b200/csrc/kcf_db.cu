@@ -263,6 +263,116 @@ __device__ __forceinline__ int kcf_ingest_one(const KcfIngestParams &p, const Kc
     unsigned long long pos = atomicAdd(&p.counters[2], 1ULL);
     if (pos < p.ovf_cap) {
         p.ovf[pos].key = tkey;
+        p.ovf[pos].key_hi = 0;
+        p.ovf[pos].meta = (1ULL << 63) | count;
+    }
+    return 2;
+}
+
+// ---- the same for k = 33 .. 64: the reference's value is 2k <= 128 bits (Kmer.java:232-252 keeps it in long[] words, first
+// base most significant; canonical = the lexicographically smaller strand, :72-79, 406-414 — for equal lengths the numeric
+// order of the right-aligned values), the table key two 64-bit planes, the home line a hash of the whole key
+__device__ __forceinline__ unsigned __int128 kcf_revcomp128(unsigned __int128 x, uint32_t k)
+{
+    const uint64_t hi = (uint64_t)(x >> 64), lo = (uint64_t)x;
+    const unsigned __int128 rev = ((unsigned __int128)kcf_pair_reverse64(~lo) << 64) | kcf_pair_reverse64(~hi);
+    return rev >> (128u - 2u * k); // the complemented padding falls off the low end
+}
+
+// record in the home line's filter that a 128-bit key lives outside it (32-bit filter; absent when fbits == 0)
+__device__ __forceinline__ void kcf_filter_add2(uint8_t *home_line, const KcfKey2 &key, const KcfTableGeom &g)
+{
+    if (g.fbits == 0) return;
+    const uint32_t h = kcf_filter_hash(key.p0 ^ (key.p1 * 0x9E3779B97F4A7C15ULL));
+    atomicAnd(reinterpret_cast<uint32_t *>(home_line + g.foff), ~((1u << (h >> 27)) | (1u << ((h >> 22) & 31u))));
+}
+
+template <typename BitsPtr>
+__device__ __forceinline__ int kcf_ingest_one2(const KcfIngestParams &p, const KcfTableGeom &g, uint64_t t, uint32_t group, BitsPtr allowed)
+{
+    typedef unsigned __int128 u128;
+    const uint64_t i = p.rec0 + t;
+    uint64_t lo = p.cta_bound[group], hi = p.cta_bound[group + 1];
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (p.lut[mid] <= i) lo = mid + 1;
+        else hi = mid;
+    }
+    if (lo == 0) return 1;
+    const uint64_t idx = lo - 1;
+    const uint32_t bin = (uint32_t)(idx >> (2 * p.P));
+    const uint64_t prefix = idx & ((1ULL << (2 * p.P)) - 1);
+    const uint8_t *r = p.rec + t * p.rec_size;
+    u128 suffix = 0;
+    for (uint32_t j = 0; j < p.nsb; ++j) suffix = (suffix << 8) | r[j]; // big-endian suffix bytes (Kmer.java:166), up to 16
+    uint32_t count = 0;
+    for (uint32_t j = 0; j < p.cs; ++j) count |= (uint32_t)r[p.nsb + j] << (8 * j); // KMC.java:395-401
+    if (i > p.lut[idx]) { // strict ascending order inside the range
+        const uint8_t *q = (t > 0) ? (r - p.rec_size) : p.prev;
+        u128 ps = 0;
+        for (uint32_t j = 0; j < p.nsb; ++j) ps = (ps << 8) | q[j];
+        if (ps >= suffix) atomicOr(&p.flags[FLAG_ORDER_BAD], 1u);
+    }
+    const uint32_t sbits = 8 * p.nsb;
+    const u128 kmer = (p.P > 0 ? ((u128)prefix << sbits) : (u128)0) | suffix;
+    bool reachable = true;
+    if (g.both_strands && kmer > kcf_revcomp128(kmer, g.k)) reachable = false; // a query is canonicalised first (GetVariants.java:222)
+    if (reachable) {
+        // signature (Kmer.java:105-118): min norm over the k-L+1 m-mers, both strands of each rolled along
+        const uint32_t L = p.L, special = 1u << (2 * L), mmask = special - 1u;
+        uint32_t m = (uint32_t)(kmer >> (2 * (g.k - L))) & mmask, rc = 0;
+        for (uint32_t j = 0, tt = m; j < L; ++j, tt >>= 2) rc = (rc << 2) | ((~tt) & 3u);
+        uint32_t sig = 0xFFFFFFFFu;
+        for (uint32_t j = 0;; ++j) {
+            const uint32_t a = ((allowed[m >> 5] >> (m & 31u)) & 1u) ? m : special;
+            const uint32_t b = ((allowed[rc >> 5] >> (rc & 31u)) & 1u) ? rc : special;
+            sig = min(sig, min(a, b));
+            if (j == g.k - L) break;
+            const uint32_t nb = (uint32_t)(kmer >> (2 * (g.k - L - j - 1))) & 3u;
+            m = ((m << 2) | nb) & mmask;
+            rc = (rc >> 2) | ((3u - nb) << (2 * (L - 1)));
+        }
+        if (p.sigmap[sig] != bin) reachable = false; // KMC.java:300
+    }
+    if (!reachable) return 1;
+    if (p.cs == 0) return 0;
+    const KcfKey2 key = kcf_table_key2(kmer, g);
+    const uint32_t home = kcf_home_line2(key, g);
+    if (p.part_world > 1 && kcf_line_owner(home, g.n_lines, p.part_world) != p.part_rank) return 3;
+    uint8_t *home_line = p.table + (uint64_t)kcf_line_wrap(home, 0, g) * KCF_LINE_BYTES;
+    uint32_t *home_w31 = reinterpret_cast<uint32_t *>(home_line) + 31;
+    const uint32_t klo = (uint32_t)key.p0;
+    if (klo != KCF_EMPTY_LO) {
+        for (uint32_t d = 0; d <= KCF_MAX_DISP; ++d) {
+            uint8_t *line = p.table + (uint64_t)kcf_line_wrap(home, d, g) * KCF_LINE_BYTES;
+            uint32_t *w = reinterpret_cast<uint32_t *>(line);
+            bool dup = false;
+            for (uint32_t s2 = 0; !dup && s2 < g.S; ++s2) {
+                uint32_t v = __ldcg(w + s2);
+                if (v == KCF_EMPTY_LO) v = atomicCAS(&w[s2], KCF_EMPTY_LO, klo); // claiming a slot and publishing the low word are one step
+                if (v == KCF_EMPTY_LO) {
+                    uint32_t *rw = w + g.S + 3 * s2;
+                    rw[0] = (uint32_t)(key.p0 >> 32);
+                    rw[1] = (uint32_t)key.p1;
+                    rw[2] = (uint32_t)(key.p1 >> 32);
+                    const uint32_t off = g.coff + g.cw * s2;
+                    const uint32_t sh = 8 * (off & 3u);
+                    const uint32_t field = g.cw == 4 ? 0xFFFFFFFFu : (((1u << (8 * g.cw)) - 1u) << sh);
+                    atomicAnd(w + (off >> 2), ~field | (count << sh));
+                    atomicAnd(home_w31, ~(1u << (16 + d)));
+                    if (d > 0) kcf_filter_add2(home_line, key, g);
+                    return 0;
+                }
+                if (v == klo) dup = true; // low words stay unique per line: try the next line
+            }
+        }
+    }
+    atomicAnd(home_w31, ~(1u << (16 + KCF_STASH_BIT)));
+    kcf_filter_add2(home_line, key, g);
+    unsigned long long pos = atomicAdd(&p.counters[2], 1ULL);
+    if (pos < p.ovf_cap) {
+        p.ovf[pos].key = key.p0;
+        p.ovf[pos].key_hi = key.p1;
         p.ovf[pos].meta = (1ULL << 63) | count;
     }
     return 2;
@@ -271,7 +381,7 @@ __device__ __forceinline__ int kcf_ingest_one(const KcfIngestParams &p, const Kc
 // CTAs stride over the chunk's groups of 256 consecutive records; the allowed-m-mer bitmap is loaded into shared memory
 // once per CTA (SMEM_BITS: 4^L bits fit, i.e. L <= 9), the per-record outcomes are counted in shared memory and reach the
 // global counters with one atomic per CTA and outcome
-template <bool SMEM_BITS>
+template <bool SMEM_BITS, int KW>
 __global__ void __launch_bounds__(256) kcf_ingest_kernel(KcfIngestParams p, KcfTableGeom g)
 {
     extern __shared__ uint32_t s_allowed[];
@@ -285,7 +395,9 @@ __global__ void __launch_bounds__(256) kcf_ingest_kernel(KcfIngestParams p, KcfT
     for (uint32_t group = blockIdx.x; group < p.n_groups; group += gridDim.x) {
         const uint64_t t = (uint64_t)group * 256 + threadIdx.x;
         if (t >= p.n_rec) continue;
-        const int what = SMEM_BITS ? kcf_ingest_one(p, g, t, group, (const uint32_t *)s_allowed) : kcf_ingest_one(p, g, t, group, p.allowed);
+        int what;
+        if (KW == 2) what = SMEM_BITS ? kcf_ingest_one2(p, g, t, group, (const uint32_t *)s_allowed) : kcf_ingest_one2(p, g, t, group, p.allowed);
+        else what = SMEM_BITS ? kcf_ingest_one(p, g, t, group, (const uint32_t *)s_allowed) : kcf_ingest_one(p, g, t, group, p.allowed);
         if (what != 2) atomicAdd(&s_cnt[what], 1u); // the overflow list counts its own entries
     }
     __syncthreads();
@@ -298,11 +410,12 @@ __global__ void kcf_stash_build_kernel(const KcfStashEntry *__restrict__ ovf, ui
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     KcfStashEntry e = ovf[t];
-    uint64_t i = kcf_mix64(e.key);
+    uint64_t i = kcf_mix64(e.key ^ (e.key_hi * 0x9E3779B97F4A7C15ULL));
     for (uint64_t k = 0;; ++k) {
         KcfStashEntry *s = &stash[(i + k) & g.stash_mask];
         if (atomicCAS((unsigned long long *)&s->meta, 0ULL, (unsigned long long)e.meta) == 0ULL) {
             s->key = e.key; // keys are distinct; nobody reads them before the build kernel ends
+            s->key_hi = e.key_hi;
             return;
         }
     }
@@ -315,7 +428,7 @@ __global__ void kcf_count_kernel(const char *__restrict__ ascii, uint64_t n, con
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const char *s = ascii + t * g.k;
-    uint64_t v = 0;
+    unsigned __int128 v = 0;
     bool ok = true;
     for (uint32_t j = 0; j < g.k; ++j) {
         uint32_t b = (uint8_t)s[j];
@@ -327,7 +440,13 @@ __global__ void kcf_count_kernel(const char *__restrict__ ascii, uint64_t n, con
         out[t] = 0;
         return;
     }
-    out[t] = (int32_t)kcf_lookup(table, stash, g, kcf_table_key(v, g)); // strand symmetric for a both-strands database
+    // the table keys are strand symmetric for a both-strands database: no canonicalisation needed here
+    if (g.kw == 2) {
+        const KcfKey2 key = kcf_table_key2(v, g);
+        out[t] = (int32_t)kcf_lookup2(table, stash, g, key, kcf_home_line2(key, g));
+    } else {
+        out[t] = (int32_t)kcf_lookup(table, stash, g, kcf_table_key((uint64_t)v, g));
+    }
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -397,7 +516,8 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     const int k = info.kmer_length, P = info.lut_prefix_length, L = info.signature_length, cs = info.counter_size;
     if (k < 1 || P < 0 || P > k || L < 1 || cs < 0 || info.total_kmers < 0)
         return kcf_fail(ctx, KCF_ERR_DB_FORMAT, "inconsistent header (k=%d P=%d L=%d counter=%d)", k, P, L, cs);
-    if (k > 32) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "k=%d > 32 is not supported by this build", k);
+    if (k > 64) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "k=%d > 64 is not supported by this build", k);
+    if (k > 32 && part_world > 1) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "k=%d > 32 with a partitioned table: the exchange moves 64-bit keys", k);
     if ((k - P) % 4 != 0) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "(k - lut_prefix_length) %% 4 != 0 (k=%d P=%d)", k, P);
     if (cs > 4) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "counter_size %d > 4", cs);
     if (L < 3 || L > 12 || L > k) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "signature length %d", L);
@@ -423,16 +543,28 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     const int kk2 = 2 * k;
     KcfTableGeom g{};
     g.k = (uint32_t)k;
-    g.kshift = 64 - kk2;
-    g.kmask = kk2 == 64 ? ~0ULL : ((1ULL << kk2) - 1);
+    g.kw = k > 32 ? 2u : 1u;
+    g.kshift = k > 32 ? 0u : 64 - kk2;
+    g.kmask = kk2 >= 64 ? ~0ULL : ((1ULL << kk2) - 1);
     g.km = k >= 32 ? 0xFFFFFFFFu : ((1u << k) - 1u);
+    g.km64 = k >= 64 ? ~0ULL : ((1ULL << k) - 1ULL);
     g.cw = cs <= 1 ? 1u : (cs == 2 ? 2u : 4u);
-    g.S = g.cw == 1 ? 13u : (g.cw == 2 ? 12u : 10u);
-    g.coff = g.cw == 1 ? 112u : 8u * g.S;
-    g.foff = g.cw == 1 ? 104u : 120u;
-    g.fbits = g.cw == 1 ? 64u : 32u;
+    if (g.kw == 2) { // 128-bit keys: 7 / 7 / 6 slots of 16 bytes (kcf_internal.cuh)
+        g.S = g.cw == 4 ? 6u : 7u;
+        g.coff = 16u * g.S;
+        g.foff = 120u;
+        g.fbits = g.cw == 2 ? 0u : 32u;
+    } else {
+        g.S = g.cw == 1 ? 13u : (g.cw == 2 ? 12u : 10u);
+        g.coff = g.cw == 1 ? 112u : 8u * g.S;
+        g.foff = g.cw == 1 ? 104u : 120u;
+        g.fbits = g.cw == 1 ? 64u : 32u;
+    }
     g.both_strands = (uint32_t)info.both_strands;
-    {
+    if (g.kw == 2) {
+        g.m = g.w = 0; // no minimizer: the home line is a hash of the whole key
+        g.mm = 0;
+    } else {
         // minimizer length: long enough that one m-mer value rarely names more than one locus of the sampled genome
         // (4^m >= 4 N) and that a run of k-mers sharing it fits one line (w = k-m+1 < S: a group larger than a line always
         // overflows), short enough that consecutive k-mers share it at all
@@ -551,7 +683,7 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
         kcf_allowed_kernel<<<(n_words + 255) / 256, 256, 0, ctx->stream>>>(L, d_allowed);
         if (lut_len) kcf_lut_check_kernel<<<(unsigned)((lut_len + 255) / 256), 256, 0, ctx->stream>>>(d_lut, lut_len, N, ctx->d_flags);
         DB_CUDA(cudaGetLastError());
-        if (smem_bits) DB_CUDA(cudaFuncSetAttribute(kcf_ingest_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
+        if (smem_bits) DB_CUDA(cudaFuncSetAttribute(g.kw == 2 ? kcf_ingest_kernel<true, 2> : kcf_ingest_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
     }
     cudaEventCreate(&ev_first);
     cudaEventCreate(&ev_last);
@@ -630,8 +762,11 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
             p.flags = ctx->d_flags;
             const unsigned grid = (unsigned)std::min<uint64_t>(p.n_groups, (uint64_t)ctx->sm_count * 6);
             if (c == 0) cudaEventRecord(ev_first, ctx->stream);
-            if (smem_bits) kcf_ingest_kernel<true><<<grid, 256, 32768, ctx->stream>>>(p, g);
-            else kcf_ingest_kernel<false><<<grid, 256, 0, ctx->stream>>>(p, g);
+            if (g.kw == 2) {
+                if (smem_bits) kcf_ingest_kernel<true, 2><<<grid, 256, 32768, ctx->stream>>>(p, g);
+                else kcf_ingest_kernel<false, 2><<<grid, 256, 0, ctx->stream>>>(p, g);
+            } else if (smem_bits) kcf_ingest_kernel<true, 1><<<grid, 256, 32768, ctx->stream>>>(p, g);
+            else kcf_ingest_kernel<false, 1><<<grid, 256, 0, ctx->stream>>>(p, g);
             perr = cudaGetLastError();
             if (perr == cudaSuccess) perr = cudaEventRecord(ctx->ing_free[sl], ctx->stream);
             launched.store(c + 1, std::memory_order_release);

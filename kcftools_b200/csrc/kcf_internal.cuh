@@ -59,11 +59,24 @@ struct KcfTableGeom {
     uint32_t foff;       // byte offset of the filter: 104 (64 bits) / 120 (32 bits)
     uint32_t fbits;      // 64 or 32
     uint32_t both_strands;
+    uint32_t kw;         // key width in 64-bit words: 1 (k <= 32) or 2 (k <= 64: two 64-bit planes, see below)
+    uint64_t km64;       // k one-bits as a 64-bit plane mask (kw = 2)
+};
+
+// k-mers of 33 .. 64 bases (kw = 2): the key is two 64-bit planes (p0 = bit 0 of every base code, p1 = bit 1, base j in
+// bit j) and a line holds S = 7 (1- and 2-byte counts) or 6 (4-byte counts) of them:
+//   S low words (p0 & 0xFFFFFFFF; 0xFFFFFFFF = empty) | S x 3 remaining key words (p0 >> 32, p1 low, p1 high) | counts |
+//   32-bit filter at byte 120 (absent for 2-byte counts: every miss then follows the mask) | 16-bit mask
+// The home line is chosen by a hash of the whole key, not by a minimizer (m = w = 0): a run of consecutive k-mers would
+// outnumber the slots of a line, so the locality trick of the short-k layout does not carry over.
+struct KcfKey2 {
+    uint64_t p0, p1;
 };
 
 struct KcfStashEntry {
-    uint64_t key;   // canonical k-mer value (right aligned)
-    uint64_t meta;  // bit 63 = occupied, low 32 bits = count
+    uint64_t key;    // table key (kw = 2: plane 0)
+    uint64_t key_hi; // kw = 2: plane 1
+    uint64_t meta;   // bit 63 = occupied, low 32 bits = count
 };
 
 // bijective 32-bit mixer (multiply / xorshift rounds)

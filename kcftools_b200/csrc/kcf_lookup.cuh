@@ -174,14 +174,14 @@ __device__ __forceinline__ bool kcf_line_find(const uint8_t *line, uint64_t key,
     return false;
 }
 
-static __device__ __noinline__ uint32_t kcf_stash_find(const KcfStashEntry *__restrict__ stash, const KcfTableGeom &g, uint64_t key)
+static __device__ __noinline__ uint32_t kcf_stash_find(const KcfStashEntry *__restrict__ stash, const KcfTableGeom &g, uint64_t key, uint64_t key_hi = 0)
 {
     if (stash == nullptr) return 0;
-    uint64_t i = kcf_mix64(key);
+    uint64_t i = kcf_mix64(key ^ (key_hi * 0x9E3779B97F4A7C15ULL));
     for (uint64_t n = 0; n <= g.stash_mask; ++n) {
         const KcfStashEntry e = stash[(i + n) & g.stash_mask];
         if (e.meta == 0) return 0;
-        if (e.key == key) return (uint32_t)e.meta;
+        if (e.key == key && e.key_hi == key_hi) return (uint32_t)e.meta;
     }
     return 0;
 }
@@ -260,4 +260,111 @@ __device__ __forceinline__ bool kcf_probe_line(const uint8_t *line, uint64_t key
     const uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
     const uint32_t d0 = S > 12 ? __ldg(reinterpret_cast<const uint32_t *>(line) + 12) : 0u;
     return kcf_match_line<S>(a, b, c, d0, line, key, count);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k = 33 .. 64 (kw = 2): 128-bit keys.  Same line discipline as above (low words distinct inside a line, overflow
+// lines named by the home line's mask, filter over the keys that live elsewhere, stash), different geometry.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t kcf_plane_rc64(uint64_t f, uint32_t n, uint64_t nm)
+{
+    return (__brevll(f) >> (64u - n)) ^ nm;
+}
+
+// table key of a k-mer given as the reference's value (2k bits, right aligned in 128)
+__device__ __forceinline__ KcfKey2 kcf_table_key2(unsigned __int128 kmer, const KcfTableGeom &g)
+{
+    // base-order reversal of the 64 pairs, then the 2k used bits moved down: base j in bits 2j, 2j+1
+    const uint64_t hi = (uint64_t)(kmer >> 64), lo = (uint64_t)kmer;
+    const unsigned __int128 rev = ((unsigned __int128)kcf_pair_reverse64(lo) << 64) | kcf_pair_reverse64(hi);
+    const unsigned __int128 E = rev >> (128u - 2u * g.k);
+    const uint64_t e0 = (uint64_t)E, e1 = (uint64_t)(E >> 64);
+    KcfKey2 f;
+    f.p0 = (uint64_t)kcf_even_bits(e0) | ((uint64_t)kcf_even_bits(e1) << 32);
+    f.p1 = (uint64_t)kcf_even_bits(e0 >> 1) | ((uint64_t)kcf_even_bits(e1 >> 1) << 32);
+    if (g.both_strands) {
+        const uint64_t r0 = kcf_plane_rc64(f.p0, g.k, g.km64), r1 = kcf_plane_rc64(f.p1, g.k, g.km64);
+        if (r1 < f.p1 || (r1 == f.p1 && r0 < f.p0)) {
+            f.p0 = r0;
+            f.p1 = r1;
+        }
+    }
+    return f;
+}
+
+__device__ __forceinline__ uint32_t kcf_key2_hash(const KcfKey2 &key)
+{
+    return kcf_filter_hash(key.p0) * 0x2545F491u ^ kcf_filter_hash(key.p1 ^ 0xD6E8FEB86659FD93ULL);
+}
+
+__device__ __forceinline__ uint32_t kcf_home_line2(const KcfKey2 &key, const KcfTableGeom &g)
+{
+    return __umulhi(kcf_mix32(kcf_key2_hash(key) ^ 0x9E3779B9u), (uint32_t)g.n_lines);
+}
+
+__device__ __forceinline__ bool kcf_filter_pass2(const uint8_t *home_line, const KcfKey2 &key, const KcfTableGeom &g)
+{
+    if (g.fbits == 0) return true; // no room for a filter in this geometry: every miss follows the mask
+    return kcf_filter_pass32(__ldg(reinterpret_cast<const uint32_t *>(home_line + g.foff)), key.p0 ^ (key.p1 * 0x9E3779B97F4A7C15ULL));
+}
+
+// search one line for a 128-bit key; the S low words sit in front, slot s keeps its other three words at 4 S + 12 s
+__device__ __forceinline__ bool kcf_line_find2(const uint8_t *line, const KcfKey2 &key, const KcfTableGeom &g, uint32_t &count)
+{
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(line);
+    const uint32_t lo = (uint32_t)key.p0;
+    for (uint32_t s = 0; s < g.S; ++s) {
+        const uint32_t v = __ldg(w + s);
+        if (v == lo) {
+            const uint32_t *r = w + g.S + 3 * s;
+            if (__ldg(r) != (uint32_t)(key.p0 >> 32) || __ldg(r + 1) != (uint32_t)key.p1 || __ldg(r + 2) != (uint32_t)(key.p1 >> 32)) return false;
+            count = kcf_slot_count(line, s, g);
+            return true;
+        }
+        if (v == KCF_EMPTY_LO) return false; // occupied slots form a prefix of the line
+    }
+    return false;
+}
+
+// full lookup of one 128-bit table key
+__device__ __forceinline__ uint32_t kcf_lookup2(const uint8_t *__restrict__ table, const KcfStashEntry *__restrict__ stash, const KcfTableGeom &g,
+                                                const KcfKey2 &key, uint32_t home)
+{
+    const uint8_t *L = table + (uint64_t)kcf_line_wrap(home, 0, g) * KCF_LINE_BYTES;
+    const bool inl = (uint32_t)key.p0 != KCF_EMPTY_LO;
+    uint32_t c;
+    if (inl && kcf_line_find2(L, key, g, c)) return c;
+    if (!kcf_filter_pass2(L, key, g)) return 0;
+    const uint32_t mask = kcf_mask_from_word31(__ldg(reinterpret_cast<const uint32_t *>(L) + 31));
+    if (inl)
+        for (uint32_t d = 1; d <= KCF_MAX_DISP; ++d)
+            if (((mask >> d) & 1u) && kcf_line_find2(table + (uint64_t)kcf_line_wrap(home, d, g) * KCF_LINE_BYTES, key, g, c)) return c;
+    if ((mask >> KCF_STASH_BIT) & 1u) return kcf_stash_find(stash, g, key.p0, key.p1);
+    return 0;
+}
+
+// Probe one table line for a 128-bit key (screening kernel): the S <= 7 low words arrive with two 16-byte loads; the
+// low-word match is the only candidate (low words are distinct inside a line) and is confirmed on its other three words,
+// which are read together with the count.
+template <int S>
+__device__ __forceinline__ bool kcf_probe_line2(const uint8_t *line, const KcfKey2 &key, const KcfTableGeom &g, uint32_t &count)
+{
+    const uint4 *q = reinterpret_cast<const uint4 *>(line);
+    const uint4 a = __ldg(q), b = __ldg(q + 1);
+    const uint32_t lo = (uint32_t)key.p0;
+    int idx = -1;
+    if (a.x == lo) idx = 0;
+    if (a.y == lo) idx = 1;
+    if (a.z == lo) idx = 2;
+    if (a.w == lo) idx = 3;
+    if (b.x == lo) idx = 4;
+    if (b.y == lo) idx = 5;
+    if (S > 6 && b.z == lo) idx = 6;
+    if (idx < 0) return false;
+    const uint32_t *r = reinterpret_cast<const uint32_t *>(line) + S + 3 * idx;
+    const uint32_t r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
+    const uint32_t c = kcf_slot_count(line, (uint32_t)idx, g);
+    if (r0 != (uint32_t)(key.p0 >> 32) || r1 != (uint32_t)key.p1 || r2 != (uint32_t)(key.p1 >> 32)) return false;
+    count = c;
+    return true;
 }

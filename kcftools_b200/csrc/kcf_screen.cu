@@ -80,6 +80,7 @@ static_assert(KCF_CHUNK == 512 && KCF_HALO == 64, "the hash phase gives every la
 
 struct KcfQueueItem {
     unsigned long long key;
+    unsigned long long key_hi; // plane 1 of a 128-bit key (k > 32)
     uint32_t home;  // home line
     uint32_t info;  // chunk position << 16 | home mask (bit 0 cleared)
 };
@@ -159,6 +160,8 @@ template <int S, int MODE, bool SPEC>
 __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_screen_kernel(const KcfScreenParams p, const KcfTableGeom g)
 {
     constexpr bool COUNTS = MODE == KCF_MODE_COUNTS, EXTRACT = MODE == KCF_MODE_EXTRACT, OWNED = MODE == KCF_MODE_OWNED;
+    constexpr int KW = S <= 7 ? 2 : 1; // 128-bit keys (k = 33 .. 64): 7 / 6 slots per line, home line by a hash of the key
+    static_assert(KW == 1 || (!EXTRACT && !OWNED), "partitioned tables move 64-bit keys");
     __shared__ __align__(16) KcfWarpSmem kcf_warp_smem[KCF_WPC];
     KcfWarpSmem &W = kcf_warp_smem[threadIdx.x >> 5]; // the warps of a CTA share nothing
 
@@ -222,6 +225,7 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
 
             // ---- order hash of the m-mer ending at every staged position from 32 on (the minimizer window of the chunk's
             // first k-mer starts at 65 - w >= 33) ----
+            if (KW == 1) {
             if (chunk > 0) W.hash[32 + lane] = carry_hash;
 #pragma unroll 1
             for (uint32_t r = chunk == 0 ? 0u : 1u; r < 2; ++r) // r = 0: the halo positions 32 .. 63 of a tile's first chunk (two lanes)
@@ -279,23 +283,41 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
                     sd *= four ? 4 : 2;
                 }
             }
+            } // KW == 1
             // validity of every k-mer of the chunk, 32 positions per lane: bit q of `run` is set iff the k staged validity
             // bits q-k+1 .. q are all set (Fasta.java:99-104), built from runs of 1, 2, 4, .. bits; a k-mer opens a valid
             // stretch when the one ending one position earlier is not valid (EFFLEN, Fasta.java:140-167)
             if (lane < KCF_CHUNK / 32) {
-                const uint64_t v64 = ((uint64_t)W.valid[KCF_HALO / 32 + lane] << 32) | W.valid[KCF_HALO / 32 - 1 + lane]; // top half = this lane's 32 positions
-                uint64_t a = v64, run = ~0ULL;
-                uint32_t pos = 0;
+                if (KW == 1) {
+                    const uint64_t v64 = ((uint64_t)W.valid[KCF_HALO / 32 + lane] << 32) | W.valid[KCF_HALO / 32 - 1 + lane]; // top half = this lane's 32 positions
+                    uint64_t a = v64, run = ~0ULL;
+                    uint32_t pos = 0;
 #pragma unroll
-                for (uint32_t b = 0; b < 6; ++b) {
-                    if ((k >> b) & 1u) {
-                        run &= a << pos;
-                        pos += 1u << b;
+                    for (uint32_t b = 0; b < 6; ++b) {
+                        if ((k >> b) & 1u) {
+                            run &= a << pos;
+                            pos += 1u << b;
+                        }
+                        a &= a << (1u << b);
                     }
-                    a &= a << (1u << b);
+                    W.okw[lane] = (uint32_t)(run >> 32);
+                    W.start[lane] = (uint32_t)((run & ~(run << 1)) >> 32);
+                } else { // k up to 64 looks back 63 positions: the two halo words and this lane's word, 96 bits
+                    typedef unsigned __int128 u128;
+                    const u128 v = ((u128)W.valid[KCF_HALO / 32 + lane] << 64) | ((u128)W.valid[KCF_HALO / 32 - 1 + lane] << 32) | W.valid[KCF_HALO / 32 - 2 + lane];
+                    u128 a = v, run = ~(u128)0;
+                    uint32_t pos = 0;
+#pragma unroll
+                    for (uint32_t b = 0; b < 7; ++b) {
+                        if ((k >> b) & 1u) {
+                            run &= a << pos;
+                            pos += 1u << b;
+                        }
+                        a &= a << (1u << b);
+                    }
+                    W.okw[lane] = (uint32_t)(run >> 64);
+                    W.start[lane] = (uint32_t)((run & ~(run << 1)) >> 64);
                 }
-                W.okw[lane] = (uint32_t)(run >> 32);
-                W.start[lane] = (uint32_t)((run & ~(run << 1)) >> 32);
                 W.hit[lane] = 0;
             }
             __syncwarp();
@@ -316,9 +338,11 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
                     while (m2 && !found) {
                         const uint32_t d = __ffs(m2) - 1;
                         m2 &= m2 - 1;
-                        found = kcf_probe_line<S>(p.table + (uint64_t)kcf_line_wrap(it.home, d, g) * KCF_LINE_BYTES, it.key, c2);
+                        const uint8_t *ol = p.table + (uint64_t)kcf_line_wrap(it.home, d, g) * KCF_LINE_BYTES;
+                        if (KW == 2) found = kcf_probe_line2<S>(ol, KcfKey2{it.key, it.key_hi}, g, c2);
+                        else found = kcf_probe_line<(KW == 2 ? 13 : S)>(ol, it.key, c2);
                     }
-                    if (!found && (it.info & (1u << KCF_STASH_BIT))) c2 = kcf_stash_find(p.stash, g, it.key);
+                    if (!found && (it.info & (1u << KCF_STASH_BIT))) c2 = kcf_stash_find(p.stash, g, it.key, KW == 2 ? it.key_hi : 0ULL);
                     const uint32_t pc = it.info >> 16;
                     if ((int32_t)c2 >= p.min_count) {
                         sum += c2;
@@ -344,15 +368,35 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
                 // table key: the k-mer's bit planes; for a both-strands database the smaller strand (kcf_lookup.cuh) — what the
                 // loader stored the record spelling this k-mer's canonical form under (Kmer.java:57-79)
                 uint32_t klo, khi;
-                {
+                uint64_t key, key_hi = 0;
+                uint32_t home;
+                if (KW == 1) {
                     const uint32_t b0 = q - k + 1, wi = b0 >> 5, sh = b0 & 31u;
                     const uint2 a = W.planes[wi], b = W.planes[wi + 1];
                     klo = __funnelshift_r(a.x, b.x, sh) & g.km;
                     khi = __funnelshift_r(a.y, b.y, sh) & g.km;
                     if (BOTH) kcf_plane_canonical(klo, khi, kcf_plane_rc(klo, k, g.km), kcf_plane_rc(khi, k, g.km), klo, khi);
+                    key = ((uint64_t)khi << 32) | klo;
+                    home = home_of(q);
+                } else { // two 64-bit planes cut out of three staged words each; the home line is a hash of the whole key
+                    const uint32_t b0 = q - k + 1, wi = b0 >> 5, sh = b0 & 31u;
+                    const uint2 a = W.planes[wi], b = W.planes[wi + 1], c = W.planes[wi + 2];
+                    KcfKey2 f;
+                    f.p0 = (((uint64_t)__funnelshift_r(b.x, c.x, sh) << 32) | __funnelshift_r(a.x, b.x, sh)) & g.km64;
+                    f.p1 = (((uint64_t)__funnelshift_r(b.y, c.y, sh) << 32) | __funnelshift_r(a.y, b.y, sh)) & g.km64;
+                    if (BOTH) {
+                        const uint64_t r0 = kcf_plane_rc64(f.p0, k, g.km64), r1 = kcf_plane_rc64(f.p1, k, g.km64);
+                        if (r1 < f.p1 || (r1 == f.p1 && r0 < f.p0)) {
+                            f.p0 = r0;
+                            f.p1 = r1;
+                        }
+                    }
+                    key = f.p0;
+                    key_hi = f.p1;
+                    klo = (uint32_t)f.p0;
+                    khi = 0;
+                    home = kcf_home_line2(f, g);
                 }
-                const uint64_t key = ((uint64_t)khi << 32) | klo;
-                const uint32_t home = home_of(q);
                 if (EXTRACT) {
                     const uint64_t base = (tile - p.tile_begin) * KCF_TILE + (uint64_t)chunk * KCF_CHUNK;
                     p.x_keys[base + cpos] = key;
@@ -375,14 +419,19 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
                     const uint32_t w31 = __ldg(reinterpret_cast<const uint32_t *>(L) + 31);
                     const unsigned long long fword = S == 13 ? __ldg(reinterpret_cast<const unsigned long long *>(L + 104))
                                                              : (unsigned long long)__ldg(reinterpret_cast<const uint32_t *>(L + 120));
-                    if (!(inl && kcf_probe_line<S>(L, key, cnt))) {
+                    bool found;
+                    if (KW == 2) found = inl && kcf_probe_line2<S>(L, KcfKey2{key, key_hi}, g, cnt);
+                    else found = inl && kcf_probe_line<(KW == 2 ? 13 : S)>(L, key, cnt);
+                    if (!found) {
                         cnt = 0;
                         // absent unless the home line's filter says a key like this one lives outside it
-                        const bool maybe = S == 13 ? kcf_filter_pass64(fword, key) : kcf_filter_pass32((uint32_t)fword, key);
+                        bool maybe;
+                        if (KW == 2) maybe = g.fbits == 0 || kcf_filter_pass32((uint32_t)fword, key ^ (key_hi * 0x9E3779B97F4A7C15ULL));
+                        else maybe = S == 13 ? kcf_filter_pass64(fword, key) : kcf_filter_pass32((uint32_t)fword, key);
                         if (maybe) {
                             mask = kcf_mask_from_word31(w31);
                             if (inl && (mask & 0x7FFEu)) pending = true;
-                            else if ((mask >> KCF_STASH_BIT) & 1u) cnt = kcf_stash_find(p.stash, g, key);
+                            else if ((mask >> KCF_STASH_BIT) & 1u) cnt = kcf_stash_find(p.stash, g, key, key_hi);
                         }
                     }
                 }
@@ -396,6 +445,7 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
                     if (pending) {
                         KcfQueueItem it;
                         it.key = key;
+                        if (KW == 2) it.key_hi = key_hi;
                         it.home = home;
                         it.info = (cpos << 16) | (mask & 0xFFFEu);
                         W.queue[qn + __popc(pb & ((1u << lane) - 1u))] = it;
@@ -667,7 +717,7 @@ extern "C" int kcf_plan_create(kcf_ctx *ctx, int32_t kmer_length, const kcf_wind
 {
     if (!ctx || !out || (!wins && n_wins) || (!segs && n_segs)) return KCF_ERR_ARG;
     *out = nullptr;
-    if (kmer_length < 3 || kmer_length > 32) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "k=%d outside 3..32", kmer_length);
+    if (kmer_length < 3 || kmer_length > 64) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "k=%d outside 3..64", kmer_length);
     if (n_wins >= (1ULL << 32) || n_segs >= (1ULL << 32)) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "too many windows / segments");
     KCF_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<uint32_t> seg_off(std::max<uint64_t>(n_segs, 1), 0);
@@ -812,11 +862,15 @@ int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t min_coun
     const size_t smem = 0; // the per-warp buffers are static shared memory
     void (*kern)(KcfScreenParams, KcfTableGeom);
     const int S = (int)db->geom.S;
+    if (db->geom.kw == 2 && (extract || owned)) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "k=%u > 32 with a partitioned table", db->geom.k);
     // the common geometry (both-strands database, 4 <= w <= 13) runs the kernels that have it compiled in
     const bool spec = db->geom.both_strands && db->geom.w >= 4 && db->geom.w <= 13;
 #define KCF_PICK_S(MODE, SP) (S == 13 ? kcf_screen_kernel<13, MODE, SP> : (S == 12 ? kcf_screen_kernel<12, MODE, SP> : kcf_screen_kernel<10, MODE, SP>))
 #define KCF_PICK(MODE) (spec ? KCF_PICK_S(MODE, true) : KCF_PICK_S(MODE, false))
-    if (extract) kern = KCF_PICK(KCF_MODE_EXTRACT);
+    if (db->geom.kw == 2) { // 128-bit keys: no minimizer, strandedness read at run time
+        if (d_counts) kern = S == 7 ? kcf_screen_kernel<7, KCF_MODE_COUNTS, false> : kcf_screen_kernel<6, KCF_MODE_COUNTS, false>;
+        else kern = S == 7 ? kcf_screen_kernel<7, KCF_MODE_SCREEN, false> : kcf_screen_kernel<6, KCF_MODE_SCREEN, false>;
+    } else if (extract) kern = KCF_PICK(KCF_MODE_EXTRACT);
     else if (owned) kern = KCF_PICK(KCF_MODE_OWNED);
     else if (d_counts) kern = KCF_PICK(KCF_MODE_COUNTS);
     else kern = KCF_PICK(KCF_MODE_SCREEN);

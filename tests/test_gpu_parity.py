@@ -496,3 +496,60 @@ def test_plans_do_not_outlive_their_sequences(ctx, sc_main):
     assert_results_equal(c.fetch(), want)
     c.close()
     db.close()
+
+
+@pytest.mark.parametrize("k,P,L,cs,both", [(33, 5, 9, 1, True), (48, 8, 9, 1, True), (63, 7, 9, 2, True), (64, 8, 9, 1, True), (64, 4, 7, 3, False),
+                                            (40, 0, 5, 1, True)])
+def test_kmers_longer_than_32_bases(ctx, k, P, L, cs, both):
+    """k = 33 .. 64 on the device (two 64-bit bit planes per key, 7 / 6 slots per line, home line by a hash of
+    the key) against the C oracle, which follows Kmer.java's long[] words (Kmer.java:232-252, 300-338, 406-414): windows with N
+    runs, lower case, an inverted stretch found through the other strand, several segments, per-k-mer counts, getCount of every
+    record's own text; k = 65 is refused."""
+    rng = np.random.default_rng(2000 + k + cs)
+    n = 9000
+    ref = "".join("ACGT"[c] for c in rng.integers(0, 4, n))
+    ref = ref[:700] + "NNNN" + ref[704:1500].lower() + "R" + ref[1501:5000] + "N" * 70 + ref[5070:]
+    qry = list(ref.upper().replace("N", "A").replace("R", "G"))
+    for pos in rng.integers(0, len(qry), 60):
+        qry[pos] = "ACGT"[(("ACGT".index(qry[pos])) + 1 + int(rng.integers(0, 3))) % 4]
+    qry = "".join(qry[:1800] + qry[1900:])
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    qry = qry[:400] + "".join(comp[c] for c in reversed(qry[400:900])) + qry[900:]
+    img = synth.kmc_image_from_strings([qry], k=k, P=P, L=L, n_bins=8, counter_size=cs, both_strands=both, seed=k)
+    rec = np.concatenate([np.frombuffer(b">chrL\n", np.uint8), np.frombuffer("".join(ref[i:i + 61] + "\n" for i in range(0, n, 61)).encode(), np.uint8)])
+    raw = rec[6:]
+    ctx.ref_clear()
+    ctx.ref_add(raw, 61, 62, n)
+    db = KMC(ctx, pre=img.pre, suf=img.suf)
+    assert db.getKmerLength() == k and db.info.resident_kmers == img.total and db.info.unreachable_kmers == 0
+    odb = ob.OracleKMC(img.pre, img.suf)
+    lists = [[(0, s, 1500)] for s in range(0, n - 1500, 1100)] + [[(0, 0, n)], [(0, 100, 40), (0, 300, 45), (0, 2000, 700)], [(0, 10, k - 1)], [(0, 20, k)]]
+    wins, segs = windows_from_lists(lists)
+    rc, want = odb.screen([(raw, 61, 62, n)], wins, segs, min_count=1, threads=4)
+    assert rc == 0 and 0 < want["obs"].sum() < want["total_kmers"].sum()
+    got = ctx.screen(db, wins, segs)
+    assert_results_equal(got, want)
+    rc, want2 = odb.screen([(raw, 61, 62, n)], wins, segs, min_count=3, w=(0.5, 0.25, 0.25), threads=4)
+    assert_results_equal(ctx.screen(db, wins, segs, min_count=3, weights=(0.5, 0.25, 0.25)), want2)
+    # per-k-mer counts of one window, and KMC.getCount of records under their own text (either strand)
+    plan = ctx.plan(k, wins, segs)
+    plan.run(db)
+    plan.fetch()
+    rc, text = ob.get_sequence(raw, 61, 62, n, 0, 1500)
+    rc, res, counts = odb.process_window(text, want_counts=True)
+    gotc = plan.window_counts(db, 0)
+    assert gotc.size == counts.size and (gotc == counts).all() and (counts > 0).any() and (counts == 0).any()
+    plan.close()
+    kms = [qry[i:i + k] for i in range(0, len(qry) - k, 53)]
+    wantc = np.array([odb.count(s) for s in kms], np.int32)
+    assert (db.getCounts(kms) == wantc).all()
+    if both:
+        assert (db.getCounts(["".join(comp[c] for c in reversed(s)) for s in kms]) == wantc).all() and (wantc > 0).all()
+    db.close()
+
+
+def test_k_above_64_is_refused(ctx):
+    img = synth.kmc_image_from_strings(["ACGT" * 100], k=65, P=5, L=9, n_bins=4, counter_size=1)
+    with pytest.raises(KcfError) as e:
+        KMC(ctx, pre=img.pre, suf=img.suf)
+    assert e.value.code == -4

@@ -149,7 +149,7 @@ def test_screen_threads_equal_single():
 @pytest.mark.parametrize("k,P,L,cs,both", [(33, 5, 9, 1, True), (41, 5, 7, 2, True), (64, 8, 9, 1, True), (65, 5, 9, 1, False), (100, 8, 11, 3, True),
                                             (31, 7, 9, 1, True)])
 def test_multiword_kmers_c_oracle_vs_python(k, P, L, cs, both):
-    """groundwork for SURVEY §8 row f4 (k > 32; the CUDA path stops at 32): the C restatement follows Kmer.java's long[]
+    """SURVEY §8 row f4 (k > 32; the CUDA path follows up to k = 64, tests/test_gpu_parity.py): the C restatement follows Kmer.java's long[]
     words (32 bases per word, word-by-word unsigned canonical compare) and agrees with the string-based Python restatement
     on databases written by the any-k generator — canonical orientation across word boundaries, signature, prefix / suffix
     bytes, binary search, gap statistics and score."""
