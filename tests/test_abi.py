@@ -31,7 +31,8 @@ def test_struct_sizes_match_header():
     assert _lib.RESULT_DTYPE.itemsize == 48
     assert _lib.RESULT_DTYPE.fields["kmer_count_sum"][1] == 32 and _lib.RESULT_DTYPE.fields["score"][1] == 40
     assert _lib.WINDOW_DTYPE.itemsize == 8 and _lib.SEGMENT_DTYPE.itemsize == 12
-    assert C.sizeof(_lib.DbInfo) == 96
+    assert C.sizeof(_lib.DbInfo) == 128 and _lib.DbInfo.load_phase_s.offset == 96  # kcf_db_info_t: load_phase_s[4] appended in round 2
+    assert C.sizeof(_lib.HostSeq) == 32  # kcf_host_seq_t
     assert _lib.CELL_DTYPE.itemsize == 40 and _lib.CELL_DTYPE.fields["kmer_count"][1] == 24 and _lib.CELL_DTYPE.fields["score"][1] == 32  # kcf_cell_t
 
 
@@ -67,14 +68,14 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
     src = tmp_path / "abi.c"
     src.write_text('#include <stdio.h>\n#include "kcf_b200.h"\n'
                    'int main(void) { kcf_ctx *c = NULL; int rc = kcf_init(0, &c);\n'
-                   '  printf("%s|%d|%zu|%zu|%zu|%zu\\n", kcf_version(), rc, sizeof(kcf_result_t), sizeof(kcf_cell_t), sizeof(kcf_window_t), sizeof(kcf_segment_t));\n'
+                   '  printf("%s|%d|%zu|%zu|%zu|%zu|%zu|%zu\\n", kcf_version(), rc, sizeof(kcf_result_t), sizeof(kcf_cell_t), sizeof(kcf_window_t), sizeof(kcf_segment_t), sizeof(kcf_db_info_t), sizeof(kcf_host_seq_t));\n'
                    '  if (rc != KCF_OK) { printf("%s\\n", kcf_last_error(NULL)); return 0; }\n  kcf_shutdown(c); return 0; }\n')
     exe = tmp_path / "abi"
     lib = os.path.join(ROOT, "kcftools_b200")
     subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src), "-L", lib, "-lkcfgpu", f"-Wl,-rpath,{lib}"])
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
     ver, rc, *sizes = out[0].split("|")
-    assert "sm_100a" in ver and [int(x) for x in sizes] == [48, 40, 8, 12]
+    assert "sm_100a" in ver and [int(x) for x in sizes] == [48, 40, 8, 12, 128, 32]
     import torch
     if torch.cuda.is_available():
         assert int(rc) == 0
