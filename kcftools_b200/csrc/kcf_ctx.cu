@@ -152,6 +152,11 @@ extern "C" void kcf_shutdown(kcf_ctx *ctx)
         if (ctx->ing_free[i]) cudaEventDestroy(ctx->ing_free[i]);
         if (ctx->ing_copied[i]) cudaEventDestroy(ctx->ing_copied[i]);
     }
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ing_proved[i]) cudaEventDestroy(ctx->ing_proved[i]);
+        if (ctx->ing_inserted[i]) cudaEventDestroy(ctx->ing_inserted[i]);
+    }
+    if (ctx->ing_stream) cudaStreamDestroy(ctx->ing_stream);
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     if (ctx->h_rows) cudaFreeHost(ctx->h_rows);
     for (int i = 0; i < 4; ++i)

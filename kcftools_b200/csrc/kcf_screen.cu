@@ -78,15 +78,27 @@ enum { KCF_MODE_SCREEN = 0, KCF_MODE_COUNTS = 1, KCF_MODE_EXTRACT = 2, KCF_MODE_
 #endif
 static_assert(KCF_CHUNK == 512 && KCF_HALO == 64, "the hash phase gives every lane 16 positions of a 512-position chunk; the halo is two words");
 
-struct KcfQueueItem {
+// a k-mer whose home line names other lines that may hold it: searched later, one item per lane
+template <int KW>
+struct KcfQueueItemT {
     unsigned long long key;
-    unsigned long long key_hi; // plane 1 of a 128-bit key (k > 32)
     uint32_t home;  // home line
     uint32_t info;  // chunk position << 16 | home mask (bit 0 cleared)
 };
+template <>
+struct KcfQueueItemT<2> {
+    unsigned long long key;
+    unsigned long long key_hi; // plane 1 of a 128-bit key (k > 32)
+    uint32_t home;
+    uint32_t info;
+};
 
-struct __align__(16) KcfWarpSmem {
-    KcfQueueItem queue[KCF_QCAP];
+// Per-warp shared memory.  Its size decides the L1 the SM has left: 20 CTAs of two warps at 8,256 bytes keep the carve-out at
+// 196 KB (60 KB of L1, which the second round of a probe — high word and count of the matching slot — hits); 1 KB more per CTA
+// tips it to 228 KB and costs 5 % of the step (measured, profiles/README.md).  Hence 16-byte queue items for 64-bit keys.
+template <int KW>
+struct __align__(16) KcfWarpSmemT {
+    KcfQueueItemT<KW> queue[KCF_QCAP];
     uint32_t hash[S_HASH_WORDS];
     uint2 planes[S_WORDS];          // .x = bit 0, .y = bit 1 of the base codes; staged position q = window position o - KCF_HALO + q
     uint32_t valid[S_WORDS];
@@ -138,7 +150,8 @@ __device__ __forceinline__ void kcf_stage_word(const KcfScreenParams &p, const k
 
 // order hashes of the m-mers ending at the 16 staged positions q0 .. q0 + 15 (q0 a multiple of 16, q0 >= m - 1): the lane
 // holds the bases it needs — staged bits [q0 - m + 1, q0 + 16) of both planes — in two 64-bit windows
-__device__ __forceinline__ void kcf_hash16(KcfWarpSmem &W, uint32_t q0, uint32_t m, uint32_t mm)
+template <typename WS>
+__device__ __forceinline__ void kcf_hash16(WS &W, uint32_t q0, uint32_t m, uint32_t mm)
 {
     const uint32_t s0 = q0 + 1u - m, wi = s0 >> 5, off = s0 & 31u;
     const uint2 a = W.planes[wi], b = W.planes[wi + 1], c = W.planes[wi + 2];
@@ -162,8 +175,8 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
     constexpr bool COUNTS = MODE == KCF_MODE_COUNTS, EXTRACT = MODE == KCF_MODE_EXTRACT, OWNED = MODE == KCF_MODE_OWNED;
     constexpr int KW = S <= 7 ? 2 : 1; // 128-bit keys (k = 33 .. 64): 7 / 6 slots per line, home line by a hash of the key
     static_assert(KW == 1 || (!EXTRACT && !OWNED), "partitioned tables move 64-bit keys");
-    __shared__ __align__(16) KcfWarpSmem kcf_warp_smem[KCF_WPC];
-    KcfWarpSmem &W = kcf_warp_smem[threadIdx.x >> 5]; // the warps of a CTA share nothing
+    __shared__ __align__(16) KcfWarpSmemT<KW> kcf_warp_smem[KCF_WPC];
+    KcfWarpSmemT<KW> &W = kcf_warp_smem[threadIdx.x >> 5]; // the warps of a CTA share nothing
 
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t k = g.k;
@@ -332,17 +345,20 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
                 __syncwarp();
 #pragma unroll 1
                 for (uint32_t t = lane; t < qn; t += 32) {
-                    const KcfQueueItem it = W.queue[t];
+                    const KcfQueueItemT<KW> it = W.queue[t];
                     uint32_t m2 = it.info & 0x7FFEu, c2 = 0;
                     bool found = false;
                     while (m2 && !found) {
                         const uint32_t d = __ffs(m2) - 1;
                         m2 &= m2 - 1;
                         const uint8_t *ol = p.table + (uint64_t)kcf_line_wrap(it.home, d, g) * KCF_LINE_BYTES;
-                        if (KW == 2) found = kcf_probe_line2<S>(ol, KcfKey2{it.key, it.key_hi}, g, c2);
-                        else found = kcf_probe_line<(KW == 2 ? 13 : S)>(ol, it.key, c2);
+                        if constexpr (KW == 2) found = kcf_probe_line2<S>(ol, KcfKey2{it.key, it.key_hi}, g, c2);
+                        else found = kcf_probe_line<S>(ol, it.key, c2);
                     }
-                    if (!found && (it.info & (1u << KCF_STASH_BIT))) c2 = kcf_stash_find(p.stash, g, it.key, KW == 2 ? it.key_hi : 0ULL);
+                    if (!found && (it.info & (1u << KCF_STASH_BIT))) {
+                        if constexpr (KW == 2) c2 = kcf_stash_find(p.stash, g, it.key, it.key_hi);
+                        else c2 = kcf_stash_find(p.stash, g, it.key);
+                    }
                     const uint32_t pc = it.info >> 16;
                     if ((int32_t)c2 >= p.min_count) {
                         sum += c2;
@@ -420,8 +436,8 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
                     const unsigned long long fword = S == 13 ? __ldg(reinterpret_cast<const unsigned long long *>(L + 104))
                                                              : (unsigned long long)__ldg(reinterpret_cast<const uint32_t *>(L + 120));
                     bool found;
-                    if (KW == 2) found = inl && kcf_probe_line2<S>(L, KcfKey2{key, key_hi}, g, cnt);
-                    else found = inl && kcf_probe_line<(KW == 2 ? 13 : S)>(L, key, cnt);
+                    if constexpr (KW == 2) found = inl && kcf_probe_line2<S>(L, KcfKey2{key, key_hi}, g, cnt);
+                    else found = inl && kcf_probe_line<S>(L, key, cnt);
                     if (!found) {
                         cnt = 0;
                         // absent unless the home line's filter says a key like this one lives outside it
@@ -443,9 +459,9 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
                 if (COUNTS) p.counts_out[(tile - p.counts_tile0) * KCF_TILE + chunk * KCF_CHUNK + cpos] = ok ? (int32_t)cnt : -1;
                 if (pb) {
                     if (pending) {
-                        KcfQueueItem it;
+                        KcfQueueItemT<KW> it;
                         it.key = key;
-                        if (KW == 2) it.key_hi = key_hi;
+                        if constexpr (KW == 2) it.key_hi = key_hi;
                         it.home = home;
                         it.info = (cpos << 16) | (mask & 0xFFFEu);
                         W.queue[qn + __popc(pb & ((1u << lane) - 1u))] = it;
