@@ -736,7 +736,7 @@ def placements_leg(torch, dist, ctx, stream, device, rank, world, args, barrier,
     """ONE job on a database of >= 3e9 records under every placement of its table (strong scaling over the N GPUs)"""
     from kcftools_b200 import shard
     from kcftools_b200.api import KMC
-    from kcftools_b200.partitioned import screen_partitioned, screen_partitioned_scan
+    from kcftools_b200.partitioned import screen_partitioned, screen_partitioned_a2a, screen_partitioned_scan
     torch.cuda.empty_cache()
     w = build_workload(args.placement_workload, device, rank)
     seqs = w.seqs()
@@ -825,16 +825,29 @@ def placements_leg(torch, dist, ctx, stream, device, rank, world, args, barrier,
         load_s = allmax(time.perf_counter() - t1)
         lw_, ls_ = shard.local_slice(w.wins, w.segs, *ranges[rank])
         plan = ctx.plan(31, lw_, ls_)
+        rows, wall_ms, _ = timed(lambda: screen_partitioned(ctx, db, plan))
         phases = {}
-        rows, wall_ms, _ = timed(lambda: screen_partitioned(ctx, db, plan, phases=phases))
+        screen_partitioned(ctx, db, plan, phases=phases)
         kmers = allsum(int(rows["total_kmers"].sum()))
         ok = baseline_rows is None or rows_equal(rows, baseline_rows)
         out["a2a"] = {"value": kmers / (wall_ms * 1e-3), "ms_per_step": wall_ms, "db_load_s": load_s, "table_bytes_per_gpu": int(db.info.table_bytes),
                       "rows_equal_replicated": bool(ok),
                       "nvlink_bytes_per_step": int(allsum(int(phases.get("_bytes_out", 0)) + int(phases.get("_bytes_back", 0))) / max(phases.get("_n", 1), 1)),
                       "phases_ms": {k_: allmax(v) / max(phases.get("_n", 1), 1) * 1e3 for k_, v in phases.items() if not k_.startswith("_")},
-                      "what": "table cut by home line in N slices, windows in N ranges; per batch: extract + group by owner, all-to-all of the keys, owners "
-                              "probe, all-to-all of the counts back, fold"}
+                      "phases_note": "per-phase times come from a run with a device synchronisation after every phase; ms_per_step from one without",
+                      "runs_per_step": int(allsum(int(phases.get("_runs", 0))) / max(phases.get("_n", 1), 1)),
+                      "what": "table cut by home line in N slices, windows in N ranges; exchange over peer memory (CUDA IPC + NVLink): per batch the "
+                              "screening kernel appends every RUN of k-mers sharing a home line (16 B for up to 11 k-mers: the bases they span) to "
+                              "its owner's inbox, barrier, owners fetch the run's line once, look the k-mers up and store a 16-B slot of counts into "
+                              "the requester's workspace, barrier, fold; nothing crosses the host inside a step"}
+        # the same exchange as NCCL all-to-all collectives over caller-owned buffers (round 1), for comparison
+        phases2 = {}
+        rows2, wall2, _ = timed(lambda: screen_partitioned_a2a(ctx, db, plan, phases=phases2))
+        out["a2a_nccl_collectives"] = {"value": kmers / (wall2 * 1e-3), "ms_per_step": wall2, "rows_equal_replicated": bool(baseline_rows is None or rows_equal(rows2, baseline_rows)),
+                                       "nvlink_bytes_per_step": int(allsum(int(phases2.get("_bytes_out", 0)) + int(phases2.get("_bytes_back", 0))) / max(phases2.get("_n", 1), 1)),
+                                       "phases_ms": {k_: allmax(v) / max(phases2.get("_n", 1), 1) * 1e3 for k_, v in phases2.items() if not k_.startswith("_")}}
+        if getattr(plan, "_exchange", None) is not None:
+            plan._exchange.close()
         plan.close()
         db.close()
     except Exception as e:

@@ -215,6 +215,30 @@ int kcf_xchg_fold(kcf_ctx *ctx, kcf_plan *plan, uint64_t tile_begin, uint64_t ti
 /* Requester, last: scores and rows from the tile summaries (Data.java:70-107); then kcf_plan_fetch. */
 int kcf_plan_finalize(kcf_ctx *ctx, kcf_plan *plan, const double w[3]);
 
+/* The same exchange over PEER MEMORY (NVLink): no host in the loop, no grouping pass, one byte back per k-mer.  Every rank
+ * creates a workspace (kcf_xg_create, sized for batches of batch_tiles tiles), exports it (kcf_xg_export: a 64-byte CUDA IPC
+ * handle for ranks in other processes, or the raw device pointer for ranks of the same process) and connects to the others'
+ * (kcf_xg_connect: handles = world x 64 bytes, or same_process_ptrs[world]).  Per batch of tiles, stream-ordered, no host
+ * synchronisation inside the library:
+ *   kcf_xg_send    requester: Fasta.getKmersList + home line of every k-mer (Fasta.java:90-127); RUNS of up to 11 consecutive k-mers
+ *                  sharing a home line (they share their minimizer) go as one 16-byte entry — the bases they span — straight
+ *                  into their owner's inbox
+ *   -- barrier over all ranks on kcf_stream (the caller's: e.g. a one-element NCCL all-reduce) --
+ *   kcf_xg_answer  owner: canonical k-mers of every run (Kmer.java:57-79) and KMC.getCount (KMC.java:292-326) against the run's line,
+ *                  fetched once; counts stored straight into the requesters' workspaces
+ *   -- barrier --
+ *   kcf_xg_fold    requester: gap summaries of the batch's tiles (GetVariants.java:217-252)
+ * then kcf_plan_finalize / kcf_plan_fetch.  kcf_xg_status synchronises and reports a workspace overflow (KCF_ERR_NOMEM). */
+typedef struct kcf_xg kcf_xg;
+int kcf_xg_create(kcf_ctx *ctx, kcf_db *db, int rank, int world, uint64_t batch_tiles, kcf_xg **out);
+int kcf_xg_export(kcf_xg *x, void *handle64_out, void **device_ptr_out, uint64_t *bytes_out);
+int kcf_xg_connect(kcf_xg *x, const void *handles, void *const *same_process_ptrs);
+void kcf_xg_destroy(kcf_xg *x);
+int kcf_xg_send(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, kcf_xg *x, uint64_t tile_begin, uint64_t tile_end);
+int kcf_xg_answer(kcf_ctx *ctx, kcf_db *db, kcf_xg *x);
+int kcf_xg_fold(kcf_ctx *ctx, kcf_plan *plan, kcf_xg *x, uint64_t tile_begin, uint64_t tile_end, int32_t min_count);
+int kcf_xg_status(kcf_xg *x, uint64_t *bytes_out_per_run, uint64_t *bytes_back_per_run, uint64_t *runs_sent_last_batch);
+
 /* Scan placement — the second way to screen against a partitioned table, without moving k-mers: the plan holds ALL
  * windows on every rank (the 2-bit reference is replicated; it is small next to the table), every rank runs
  * Fasta.getKmersList (Fasta.java:90-127) over tiles [tile_begin, tile_end) but does KMC.getCount (KMC.java:292-326)

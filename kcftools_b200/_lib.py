@@ -75,6 +75,14 @@ SYMBOLS = {
     "kcf_xchg_extract": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_int, _P, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "kcf_xchg_lookup": (C.c_int, [_P, _P, _P, _P, C.c_uint64, _P]),
     "kcf_xchg_fold": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P, _P, C.c_uint64, C.c_int32]),
+    "kcf_xg_create": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_uint64, C.POINTER(_P)]),
+    "kcf_xg_export": (C.c_int, [_P, _P, C.POINTER(_P), C.POINTER(C.c_uint64)]),
+    "kcf_xg_connect": (C.c_int, [_P, _P, _P]),
+    "kcf_xg_destroy": (None, [_P]),
+    "kcf_xg_send": (C.c_int, [_P, _P, _P, _P, C.c_uint64, C.c_uint64]),
+    "kcf_xg_answer": (C.c_int, [_P, _P, _P]),
+    "kcf_xg_fold": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_int32]),
+    "kcf_xg_status": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "kcf_plan_finalize": (C.c_int, [_P, _P, C.POINTER(C.c_double)]),
     "kcf_cohort_create": (C.c_int, [_P, C.c_uint64, C.c_uint32, _P, _P, C.POINTER(_P)]),
     "kcf_cohort_destroy": (None, [_P]),

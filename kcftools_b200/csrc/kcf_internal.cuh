@@ -232,6 +232,51 @@ struct kcf_plan {
     uint32_t *s_okw = nullptr, *s_start = nullptr;
 };
 
+// ------------------------------------------------------------------------------------------
+// k-mer exchange over peer memory (partitioned table).  Every rank owns one workspace block that its
+// peers map (CUDA IPC across processes, plain pointers inside one): an INBOX with one region per sender and a BACK
+// area with one region per owner.  The unit on the wire is not a k-mer but a RUN: up to 11 consecutive k-mers of a
+// window that share their home line (they share their minimizer, which is what picks the home line and therefore the
+// owner).  A run travels as the k + len - 1 bases it spans — two bit planes of at most 41 bits — plus its length and
+// home line, 16 bytes in all (2.7 bytes per k-mer at the average run of 6, against 12 for key + home line per k-mer);
+// the owner fetches the run's line once, cuts the len k-mers out of the planes, and stores their counts as one 16-byte
+// slot (1-byte counters) into the requester's BACK region.  The screening kernel appends straight into the owners'
+// inboxes over NVLink (no local copy, no grouping pass), and the requester folds through the run slot it noted per
+// position.  Nothing crosses the host between the three kernels of a batch but two barriers.
+// ------------------------------------------------------------------------------------------
+#define KCF_XG_MAX_WORLD 16
+#define KCF_XG_RUN 11          // k-mers per run at most: k + 10 <= 42 bases fit the entry's planes for k <= 32
+#define KCF_XG_SLAB 32u        // entries a warp reserves in an owner's region at a time (>= the runs of one warp step)
+struct KcfXgDev {
+    uint32_t world, me, cbytes, stride;  // cbytes: bytes per count on the wire (1 for 1-byte counters, else 4); stride: bytes per BACK slot (16 / 48)
+    uint64_t cap;                        // runs per (sender, owner) region
+    uint4 *in_runs[KCF_XG_MAX_WORLD];    // [o]: rank o's inbox, region of sender `me`
+    uint32_t *in_count[KCF_XG_MAX_WORLD];// [o]: where rank o reads how many runs `me` sent
+    uint8_t *back[KCF_XG_MAX_WORLD];     // [s]: rank s's BACK area, region of owner `me`
+    const uint4 *my_runs;                // this rank's inbox (regions indexed by sender)
+    const uint32_t *my_count;
+    const uint8_t *my_back;              // this rank's BACK area (regions indexed by owner)
+    uint32_t *pos_slot;                  // per position of the batch: run head: owner << 28 | run index; 0xFFFFFFFE: member of the run that
+                                         // heads to its left; 0xFFFFFFFF: no k-mer ends here
+    uint32_t *okw, *start;               // validity / stretch-start bitmaps of the batch
+    unsigned int *cursor;                // [world]: runs appended per owner so far
+    uint32_t *flags;                     // [0]: a region overflowed
+};
+
+// one run on the wire: a = plane 0 (k + len - 1 bits) | (len - 1) << 42 | (home & 0x3FFFF) << 46, b = plane 1 | (home >> 18) << 42
+__host__ __device__ __forceinline__ void kcf_xg_pack_run(uint64_t p0, uint64_t p1, uint32_t len, uint32_t home, uint64_t &a, uint64_t &b)
+{
+    a = p0 | ((uint64_t)(len - 1u) << 42) | ((uint64_t)(home & 0x3FFFFu) << 46);
+    b = p1 | ((uint64_t)(home >> 18) << 42);
+}
+__host__ __device__ __forceinline__ void kcf_xg_unpack_run(uint64_t a, uint64_t b, uint64_t &p0, uint64_t &p1, uint32_t &len, uint32_t &home)
+{
+    p0 = a & ((1ULL << 42) - 1ULL);
+    p1 = b & ((1ULL << 42) - 1ULL);
+    len = (uint32_t)((a >> 42) & 15u) + 1u;
+    home = (uint32_t)(a >> 46) | ((uint32_t)(b >> 42) << 18);
+}
+
 #define KCF_TILE 2048          // positions per tile = the unit of work one warp takes
 #define KCF_HALO 64            // bases staged before a chunk (>= k-1 + the minimizer window, word aligned)
 
@@ -245,7 +290,7 @@ void *kcf_pool_get(kcf_ctx *ctx, size_t bytes);
 void kcf_pool_put(kcf_ctx *ctx, void *p, size_t bytes);
 void kcf_pool_trim(kcf_ctx *ctx); // free every pooled block (called when a large allocation fails)
 int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t min_count, uint64_t tile_begin, uint64_t tile_end,
-                      int32_t *d_counts, bool extract, uint32_t *d_owned_hit, unsigned long long *d_owned_sum);
+                      int32_t *d_counts, bool extract, uint32_t *d_owned_hit, unsigned long long *d_owned_sum, const KcfXgDev *xsend = nullptr);
 #define KCF_CUDA(ctx, call)                                                                        \
     do {                                                                                           \
         cudaError_t e__ = (call);                                                                  \

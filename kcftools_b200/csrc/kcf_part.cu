@@ -334,3 +334,328 @@ extern "C" int kcf_scan_fold(kcf_ctx *ctx, kcf_plan *plan, uint64_t tile_begin, 
     KCF_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // the caller may reuse its buffers
     return KCF_OK;
 }
+
+// =========================================================================================================================
+// k-mer exchange over peer memory (KcfXgDev, kcf_internal.cuh): send -> [barrier] -> answer -> [barrier] -> fold, all
+// stream-ordered; the barriers are the caller's (a tiny NCCL collective on this context's stream, kcftools_b200/
+// partitioned.py), nothing else crosses the host.  What moves: 16 bytes out and 16 bytes back (1-byte counters; 48
+// otherwise) per RUN of up to 11 k-mers sharing a home line — about 5 bytes per k-mer — (world - 1) / world of it over
+// NVLink, written by the kernels themselves into the peers' memory.
+// =========================================================================================================================
+struct kcf_xg {
+    kcf_ctx *ctx = nullptr;
+    int rank = 0, world = 1;
+    uint64_t batch_positions = 0, cap = 0;
+    uint32_t cbytes = 4;
+    uint8_t *block = nullptr;      // exported: inbox runs | runs per sender | back
+    uint64_t block_bytes = 0, off_keys = 0, off_homes = 0, off_count = 0, off_back = 0; // off_keys: the run entries
+    uint8_t *local = nullptr;      // pos_slot | okw | start | cursor | flags
+    uint8_t *peer[KCF_XG_MAX_WORLD] = {nullptr};
+    bool opened[KCF_XG_MAX_WORLD] = {false};
+    bool connected = false;
+    KcfXgDev dev{};
+};
+
+// tell every owner how many runs this rank appended to its inbox region
+__global__ void kcf_xg_publish_kernel(KcfXgDev X)
+{
+    const uint32_t o = threadIdx.x;
+    if (o < X.world) {
+        const unsigned int n = X.cursor[o];
+        *X.in_count[o] = n < X.cap ? n : (uint32_t)X.cap;
+    }
+    __threadfence_system();
+}
+
+// owner: a warp takes 32 runs of a sender's region and spreads their k-mers over its lanes — lane l of a step looks up the
+// l-th k-mer of the block, found through the prefix sums of the run lengths — so that, as in the replicated kernel, the
+// lanes that share a run share its home line inside ONE load instruction and the coalescer fetches the line once.  (One
+// thread per run asked for the line's sectors one after the other: 84 ms per c4s step; a quad per run with a whole-line
+// prefetch: 50 ms — the later loads did not hit L1.)  Counts go out as bytes, consecutive k-mers of a run to consecutive
+// bytes of the run's slot in that sender's BACK region.
+template <int S>
+__global__ void __launch_bounds__(256) kcf_xg_answer_kernel(const uint8_t *__restrict__ table, const KcfStashEntry *__restrict__ stash, KcfTableGeom g, KcfXgDev X)
+{
+    const uint32_t s = blockIdx.y; // sender
+    const uint32_t n = X.my_count[s];
+    const uint4 *runs = X.my_runs + (uint64_t)s * X.cap;
+    uint8_t *back = X.back[s];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t i0 = warp * 32; i0 < n; i0 += n_warps * 32) {
+        uint64_t p0 = 0, p1 = 0;
+        uint32_t len = 0, home = 0;
+        if (i0 + lane < n) {
+            const uint4 e = __ldg(runs + i0 + lane);
+            if ((e.x & e.y) != 0xFFFFFFFFu) // else: the unused rest of a sender warp's slab
+                kcf_xg_unpack_run(((uint64_t)e.y << 32) | e.x, ((uint64_t)e.w << 32) | e.z, p0, p1, len, home);
+        }
+        uint32_t incl = len; // prefix sums of the run lengths over the lanes
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += t;
+        }
+        const uint32_t excl = incl - len, total = __shfl_sync(0xffffffffu, incl, 31);
+        for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+            const uint32_t kidx = t0 + lane;
+            const bool active = kidx < total;
+            uint32_t r = 0; // the run holding k-mer kidx: the last lane whose exclusive prefix is <= kidx
+#pragma unroll
+            for (uint32_t step = 16; step > 0; step >>= 1) {
+                const uint32_t ex = __shfl_sync(0xffffffffu, excl, r + step);
+                if (ex <= kidx) r += step;
+            }
+            const uint32_t j = kidx - __shfl_sync(0xffffffffu, excl, r);
+            const uint64_t q0 = __shfl_sync(0xffffffffu, p0, r), q1 = __shfl_sync(0xffffffffu, p1, r);
+            const uint32_t hm = __shfl_sync(0xffffffffu, home, r);
+            if (!active) continue;
+            uint32_t f0 = (uint32_t)(q0 >> j) & g.km, f1 = (uint32_t)(q1 >> j) & g.km;
+            if (g.both_strands) kcf_plane_canonical(f0, f1, kcf_plane_rc(f0, g.k, g.km), kcf_plane_rc(f1, g.k, g.km), f0, f1);
+            const uint64_t key = ((uint64_t)f1 << 32) | f0;
+            const uint8_t *L = table + (uint64_t)kcf_line_wrap(hm, 0, g) * KCF_LINE_BYTES;
+            uint32_t c = 0;
+            if (!(KCF_KEY_IN_LINES(key) && kcf_probe_line<S>(L, key, c))) {
+                c = 0;
+                if (kcf_filter_pass(L, key, g))
+                    c = kcf_probe_lines(table, stash, g, key, hm, kcf_mask_from_word31(__ldg(reinterpret_cast<const uint32_t *>(L) + 31)), 1);
+            }
+            uint8_t *dst = back + (i0 + r) * X.stride + (uint64_t)j * X.cbytes;
+            if (X.cbytes == 1) *dst = (uint8_t)c;
+            else *reinterpret_cast<uint32_t *>(dst) = c;
+        }
+    }
+}
+
+// requester: one warp per tile of the batch; a position finds its count through the run slot its head noted at send time
+__global__ void __launch_bounds__(128) kcf_xg_fold_kernel(KcfXgDev X, uint64_t n_tiles, uint32_t k, int32_t min_count, KcfGap *__restrict__ tile_sum)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= n_tiles) return;
+    constexpr int WORDS = KCF_TILE / 32; // 64
+    unsigned long long sum = 0;
+    uint32_t hw0 = 0, hw1 = 0;
+    for (int wd = 0; wd < WORDS; ++wd) {
+        const uint32_t slot = X.pos_slot[t * KCF_TILE + 32ULL * wd + lane];
+        const uint32_t headmask = __ballot_sync(0xffffffffu, slot < 0xFFFFFFFEu);
+        uint32_t c = 0;
+        const uint32_t below = headmask & (0xFFFFFFFFu >> (31u - lane)); // run heads at or before this lane (runs never cross a word)
+        const uint32_t hl = below ? 31u - __clz(below) : lane;
+        const uint32_t hs = __shfl_sync(0xffffffffu, slot, hl);
+        const bool has = slot != 0xFFFFFFFFu && below != 0u;
+        if (has) {
+            const uint64_t at = ((uint64_t)(hs >> 28) * X.cap + (hs & 0x0FFFFFFFu)) * X.stride + (uint64_t)(lane - hl) * X.cbytes; // lane - hl: place in the run
+            c = X.cbytes == 1 ? (uint32_t)X.my_back[at] : *reinterpret_cast<const uint32_t *>(X.my_back + at);
+        }
+        const bool hit = has && (int32_t)c >= min_count; // Java int compare (GetVariants.java:224)
+        if (hit) sum += c;
+        const uint32_t hb = __ballot_sync(0xffffffffu, hit);
+        if ((uint32_t)(wd & 31) == lane) {
+            if (wd < 32) hw0 = hb;
+            else hw1 = hb;
+        }
+    }
+    const KcfGap a = kcf_gap_fold_warp(hw0, X.okw[t * WORDS + lane], X.start[t * WORDS + lane], lane, k);
+    const KcfGap b = kcf_gap_fold_warp(hw1, X.okw[t * WORDS + 32 + lane], X.start[t * WORDS + 32 + lane], lane, k);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, d);
+    if (lane == 0) {
+        KcfGap r = kcf_gap_combine(a, b, k);
+        r.sum = sum;
+        tile_sum[t] = r;
+    }
+}
+
+static void kcf_xg_build_dev(kcf_xg *x)
+{
+    KcfXgDev &d = x->dev;
+    d.world = (uint32_t)x->world;
+    d.me = (uint32_t)x->rank;
+    d.cbytes = x->cbytes;
+    d.stride = x->cbytes == 1 ? 16u : 48u;
+    d.cap = x->cap;
+    for (int r = 0; r < x->world; ++r) {
+        uint8_t *b = x->peer[r];
+        d.in_runs[r] = reinterpret_cast<uint4 *>(b + x->off_keys) + (uint64_t)x->rank * x->cap;
+        d.in_count[r] = reinterpret_cast<uint32_t *>(b + x->off_count) + x->rank;
+        d.back[r] = b + x->off_back + (uint64_t)x->rank * x->cap * d.stride;
+    }
+    d.my_runs = reinterpret_cast<const uint4 *>(x->block + x->off_keys);
+    d.my_count = reinterpret_cast<const uint32_t *>(x->block + x->off_count);
+    d.my_back = x->block + x->off_back;
+    const uint64_t words = x->batch_positions / 32;
+    d.pos_slot = reinterpret_cast<uint32_t *>(x->local);
+    d.okw = d.pos_slot + x->batch_positions;
+    d.start = d.okw + words;
+    d.cursor = reinterpret_cast<unsigned int *>(d.start + words);
+    d.flags = reinterpret_cast<uint32_t *>(d.cursor + KCF_XG_MAX_WORLD);
+}
+
+extern "C" int kcf_xg_create(kcf_ctx *ctx, kcf_db *db, int rank, int world, uint64_t batch_tiles, kcf_xg **out)
+{
+    if (!ctx || !db || !out || db->ctx != ctx) return KCF_ERR_ARG;
+    *out = nullptr;
+    if (world < 1 || world > KCF_XG_MAX_WORLD || rank < 0 || rank >= world) return kcf_fail(ctx, KCF_ERR_ARG, "exchange: rank %d of %d (at most %d ranks)", rank, world, KCF_XG_MAX_WORLD);
+    if (db->part_world != world || db->part_rank != rank) return kcf_fail(ctx, KCF_ERR_ARG, "exchange: the database is slice %d of %d, not %d of %d", db->part_rank, db->part_world, rank, world);
+    if (db->geom.kw != 1) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "exchange: 64-bit keys only (k <= 32)");
+    if (batch_tiles == 0 || batch_tiles * KCF_TILE >= (1ULL << 31)) return kcf_fail(ctx, KCF_ERR_ARG, "exchange: batch of %llu tiles", (unsigned long long)batch_tiles);
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    kcf_xg *x = new kcf_xg();
+    x->ctx = ctx;
+    x->rank = rank;
+    x->world = world;
+    x->batch_positions = batch_tiles * KCF_TILE;
+    // A region holds RUNS (kcf_internal.cuh).  A sender's runs spread over the owners by a hash of their minimizer, 1/world
+    // each; a window of random sequence makes one run per ~5 positions (6 k-mers on average, cut at every 32nd position),
+    // the worst case — every k-mer alone — one per position.  Half the positions per owner share plus a fixed slack covers
+    // any real batch; an overflow is detected and reported (kcf_xg_status), never silent.
+    x->cap = std::min<uint64_t>(x->batch_positions, x->batch_positions / (2 * (uint64_t)world) + 65536);
+    if (x->cap >= (1ULL << 28)) { delete x; return kcf_fail(ctx, KCF_ERR_ARG, "exchange: batch too large for %d ranks (region of %llu runs)", world, (unsigned long long)x->cap); }
+    x->cbytes = db->geom.cw == 1 ? 1u : 4u;
+    auto up = [](uint64_t b) { return (b + 255) & ~255ULL; };
+    x->off_keys = 0;
+    x->off_homes = 0;
+    x->off_count = up(x->off_keys + (uint64_t)world * x->cap * 16);
+    x->off_back = up(x->off_count + (uint64_t)world * 4);
+    x->block_bytes = up(x->off_back + (uint64_t)world * x->cap * (x->cbytes == 1 ? 16 : 48));
+    const uint64_t local_bytes = x->batch_positions * 4 + 2 * (x->batch_positions / 32) * 4 + KCF_XG_MAX_WORLD * 4 + 64;
+    cudaError_t e = cudaMalloc(&x->block, x->block_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&x->local, local_bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(x->block, 0, x->block_bytes, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(x->local, 0, local_bytes, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        cudaFree(x->block);
+        cudaFree(x->local);
+        delete x;
+        return kcf_fail(ctx, e == cudaErrorMemoryAllocation ? KCF_ERR_NOMEM : KCF_ERR_CUDA, "exchange workspace: %s", cudaGetErrorString(e));
+    }
+    x->peer[rank] = x->block;
+    *out = x;
+    return KCF_OK;
+}
+
+extern "C" int kcf_xg_export(kcf_xg *x, void *handle64_out, void **device_ptr_out, uint64_t *bytes_out)
+{
+    if (!x) return KCF_ERR_ARG;
+    if (handle64_out) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        cudaError_t e = cudaIpcGetMemHandle(&h, x->block);
+        if (e != cudaSuccess) return kcf_fail(x->ctx, KCF_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+        memcpy(handle64_out, &h, 64);
+    }
+    if (device_ptr_out) *device_ptr_out = x->block;
+    if (bytes_out) *bytes_out = x->block_bytes;
+    return KCF_OK;
+}
+
+extern "C" int kcf_xg_connect(kcf_xg *x, const void *handles, void *const *same_process_ptrs)
+{
+    if (!x || (!handles && !same_process_ptrs && x->world > 1)) return KCF_ERR_ARG;
+    KCF_CUDA(x->ctx, cudaSetDevice(x->ctx->device));
+    for (int r = 0; r < x->world; ++r) {
+        if (r == x->rank) continue;
+        if (same_process_ptrs) {
+            x->peer[r] = (uint8_t *)same_process_ptrs[r];
+        } else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const uint8_t *)handles + 64 * r, 64);
+            void *pp = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&pp, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return kcf_fail(x->ctx, KCF_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+            x->peer[r] = (uint8_t *)pp;
+            x->opened[r] = true;
+        }
+        if (!x->peer[r]) return kcf_fail(x->ctx, KCF_ERR_ARG, "exchange: no workspace pointer for rank %d", r);
+    }
+    kcf_xg_build_dev(x);
+    x->connected = true;
+    return KCF_OK;
+}
+
+extern "C" void kcf_xg_destroy(kcf_xg *x)
+{
+    if (!x) return;
+    cudaSetDevice(x->ctx->device);
+    cudaStreamSynchronize(x->ctx->stream);
+    for (int r = 0; r < x->world; ++r)
+        if (x->opened[r]) cudaIpcCloseMemHandle(x->peer[r]);
+    cudaFree(x->block);
+    cudaFree(x->local);
+    delete x;
+}
+
+extern "C" int kcf_xg_send(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, kcf_xg *x, uint64_t tile_begin, uint64_t tile_end)
+{
+    if (!ctx || !db || !plan || !x || x->ctx != ctx || plan->ctx != ctx || db->ctx != ctx) return KCF_ERR_ARG;
+    if (!x->connected) return kcf_fail(ctx, KCF_ERR_ARG, "kcf_xg_send before kcf_xg_connect");
+    if (plan->k != db->info.kmer_length) return kcf_fail(ctx, KCF_ERR_ARG, "plan built for k=%d, database has k=%d", plan->k, db->info.kmer_length);
+    tile_end = std::min<uint64_t>(tile_end, plan->n_tiles);
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t nt = tile_begin < tile_end ? tile_end - tile_begin : 0;
+    if (nt * KCF_TILE > x->batch_positions) return kcf_fail(ctx, KCF_ERR_ARG, "exchange: batch of %llu tiles exceeds the workspace", (unsigned long long)nt);
+    KCF_CUDA(ctx, cudaMemsetAsync(x->dev.cursor, 0, KCF_XG_MAX_WORLD * sizeof(unsigned int), ctx->stream));
+    if (nt) {
+        // chunks past the end of a window are never visited: their positions must read "no k-mer"
+        KCF_CUDA(ctx, cudaMemsetAsync(x->dev.pos_slot, 0xFF, nt * KCF_TILE * 4, ctx->stream));
+        KCF_CUDA(ctx, cudaMemsetAsync(x->dev.okw, 0, nt * (KCF_TILE / 32) * 4, ctx->stream));
+        KCF_CUDA(ctx, cudaMemsetAsync(x->dev.start, 0, nt * (KCF_TILE / 32) * 4, ctx->stream));
+        int rc = kcf_launch_screen(ctx, db, plan, 1, tile_begin, tile_end, nullptr, true, nullptr, nullptr, &x->dev);
+        if (rc != KCF_OK) return rc;
+    }
+    kcf_xg_publish_kernel<<<1, 32, 0, ctx->stream>>>(x->dev); // every rank publishes every batch, empty or not
+    KCF_CUDA(ctx, cudaGetLastError());
+    return KCF_OK;
+}
+
+extern "C" int kcf_xg_answer(kcf_ctx *ctx, kcf_db *db, kcf_xg *x)
+{
+    if (!ctx || !db || !x || x->ctx != ctx || db->ctx != ctx || !x->connected) return KCF_ERR_ARG;
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    const dim3 grid((unsigned)std::min<uint64_t>((x->cap + 255) / 256, (uint64_t)ctx->sm_count * 8), (unsigned)x->world); // a warp per 32 runs, grid-stride
+    if (db->geom.S == 13) kcf_xg_answer_kernel<13><<<grid, 256, 0, ctx->stream>>>(db->table, db->stash, db->geom, x->dev);
+    else if (db->geom.S == 12) kcf_xg_answer_kernel<12><<<grid, 256, 0, ctx->stream>>>(db->table, db->stash, db->geom, x->dev);
+    else kcf_xg_answer_kernel<10><<<grid, 256, 0, ctx->stream>>>(db->table, db->stash, db->geom, x->dev);
+    KCF_CUDA(ctx, cudaGetLastError());
+    return KCF_OK;
+}
+
+extern "C" int kcf_xg_fold(kcf_ctx *ctx, kcf_plan *plan, kcf_xg *x, uint64_t tile_begin, uint64_t tile_end, int32_t min_count)
+{
+    if (!ctx || !plan || !x || x->ctx != ctx || plan->ctx != ctx || !x->connected) return KCF_ERR_ARG;
+    if (min_count < 1) return kcf_fail(ctx, KCF_ERR_ARG, "Minimum kmer count should be at least 1");
+    tile_end = std::min<uint64_t>(tile_end, plan->n_tiles);
+    if (tile_begin >= tile_end) return KCF_OK;
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t nt = tile_end - tile_begin;
+    kcf_xg_fold_kernel<<<(unsigned)((nt * 32 + 127) / 128), 128, 0, ctx->stream>>>(x->dev, nt, (uint32_t)plan->k, min_count, plan->d_tile_sum + tile_begin);
+    KCF_CUDA(ctx, cudaGetLastError());
+    return KCF_OK;
+}
+
+// synchronises the stream; KCF_ERR_NOMEM when a region overflowed in any batch since the last call
+extern "C" int kcf_xg_status(kcf_xg *x, uint64_t *bytes_out_per_kmer, uint64_t *bytes_back_per_kmer, uint64_t *runs_sent_last_batch)
+{
+    if (!x) return KCF_ERR_ARG;
+    kcf_ctx *ctx = x->ctx;
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint32_t f = 0;
+    unsigned int cur[KCF_XG_MAX_WORLD] = {0};
+    KCF_CUDA(ctx, cudaMemcpyAsync(&f, x->dev.flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    KCF_CUDA(ctx, cudaMemcpyAsync(cur, x->dev.cursor, sizeof cur, cudaMemcpyDeviceToHost, ctx->stream));
+    KCF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (runs_sent_last_batch) {
+        *runs_sent_last_batch = 0;
+        for (int r = 0; r < x->world; ++r) *runs_sent_last_batch += cur[r];
+    }
+    if (bytes_out_per_kmer) *bytes_out_per_kmer = 16;                              // per RUN
+    if (bytes_back_per_kmer) *bytes_back_per_kmer = x->cbytes == 1 ? 16 : 48;         // per RUN
+    if (f) {
+        cudaMemsetAsync(x->dev.flags, 0, 4, ctx->stream);
+        return kcf_fail(ctx, KCF_ERR_NOMEM, "exchange: an inbox region of %llu entries overflowed; use smaller batches", (unsigned long long)x->cap);
+    }
+    return KCF_OK;
+}

@@ -39,9 +39,11 @@ struct KcfScreenParams {
     // ranks, next to the validity / stretch-start bitmaps (identical on every rank)
     uint32_t *x_hit;
     unsigned long long *x_sum;
+    // XSEND mode (partitioned databases, exchange over peer memory): every k-mer is appended to its owner's inbox
+    KcfXgDev xg;
 };
 
-enum { KCF_MODE_SCREEN = 0, KCF_MODE_COUNTS = 1, KCF_MODE_EXTRACT = 2, KCF_MODE_OWNED = 3 };
+enum { KCF_MODE_SCREEN = 0, KCF_MODE_COUNTS = 1, KCF_MODE_EXTRACT = 2, KCF_MODE_OWNED = 3, KCF_MODE_XSEND = 4 };
 
 // ------------------------------------------------------------------------------------------------------------
 // K3/K4.  One warp takes a tile (KCF_TILE consecutive positions of one window) and walks it in chunks of KCF_CHUNK
@@ -93,7 +95,7 @@ struct KcfQueueItemT<2> {
     uint32_t info;
 };
 
-// Per-warp shared memory.  Its size decides the L1 the SM has left: 20 CTAs of two warps at 8,256 bytes keep the carve-out at
+// Per-warp shared memory.  Its size decides the L1 the SM has left: 20 CTAs of two warps at <= 9,000 bytes keep the carve-out at
 // 196 KB (60 KB of L1, which the second round of a probe — high word and count of the matching slot — hits); 1 KB more per CTA
 // tips it to 228 KB and costs 5 % of the step (measured, profiles/README.md).  Hence 16-byte queue items for 64-bit keys.
 template <int KW>
@@ -106,6 +108,7 @@ struct __align__(16) KcfWarpSmemT {
     uint32_t okw[KCF_CHUNK / 32];   // bit = a k-mer ends at this position
     uint32_t start[KCF_CHUNK / 32]; // bit = k-mer opens a valid stretch (EFFLEN)
     KcfGap acc;                     // summary of the tile's chunks done so far
+    uint32_t xg_next[KCF_XG_MAX_WORLD], xg_end[KCF_XG_MAX_WORLD]; // XSEND: this warp's slab of entries in every owner's inbox region
 };
 
 // 32 consecutive window positions [P, P + 32) as plane / validity words (bit i = position P + i).  Positions outside the
@@ -172,7 +175,7 @@ __device__ __forceinline__ void kcf_hash16(WS &W, uint32_t q0, uint32_t m, uint3
 template <int S, int MODE, bool SPEC>
 __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_screen_kernel(const KcfScreenParams p, const KcfTableGeom g)
 {
-    constexpr bool COUNTS = MODE == KCF_MODE_COUNTS, EXTRACT = MODE == KCF_MODE_EXTRACT, OWNED = MODE == KCF_MODE_OWNED;
+    constexpr bool COUNTS = MODE == KCF_MODE_COUNTS, XSEND = MODE == KCF_MODE_XSEND, EXTRACT = MODE == KCF_MODE_EXTRACT || XSEND, OWNED = MODE == KCF_MODE_OWNED;
     constexpr int KW = S <= 7 ? 2 : 1; // 128-bit keys (k = 33 .. 64): 7 / 6 slots per line, home line by a hash of the key
     static_assert(KW == 1 || (!EXTRACT && !OWNED), "partitioned tables move 64-bit keys");
     __shared__ __align__(16) KcfWarpSmemT<KW> kcf_warp_smem[KCF_WPC];
@@ -186,6 +189,8 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
     if (!SPEC)
         while (2 * P2 <= g.w) P2 *= 2;
 
+    if (XSEND && lane < KCF_XG_MAX_WORLD) W.xg_next[lane] = W.xg_end[lane] = 0;
+    __syncwarp();
     for (;;) {
         // ---- take a tile: KCF_TILE consecutive positions of one window ----
         uint64_t tile = 0;
@@ -413,6 +418,78 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
                     khi = 0;
                     home = kcf_home_line2(f, g);
                 }
+                if (XSEND) {
+                    // RUNS of k-mers sharing their home line go straight into the owners' inboxes (kcf_internal.cuh): a run's
+                    // head lane packs the bases the run spans and appends one 16-byte entry; the lanes bound for one owner take
+                    // consecutive entries of that owner's region for this sender (one cursor atomic per owner and warp step)
+                    const uint64_t base = (tile - p.tile_begin) * KCF_TILE + (uint64_t)chunk * KCF_CHUNK;
+                    const uint32_t prev_home = __shfl_up_sync(0xffffffffu, home, 1);
+                    const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
+                    const bool brk = ok && (lane == 0 || !((okmask >> (lane - 1)) & 1u) || prev_home != home); // a new home line (or the first k-mer after a gap)
+                    const uint32_t brkmask = __ballot_sync(0xffffffffu, brk);
+                    // runs longer than KCF_XG_RUN (two minimizers in a row hashing to one line) are cut
+                    const uint32_t since = ok ? lane - (31u - __clz(brkmask & (0xFFFFFFFFu >> (31u - lane)))) : 0u;
+                    const bool head = ok && (since % KCF_XG_RUN) == 0u;
+                    const uint32_t headmask = __ballot_sync(0xffffffffu, head);
+                    uint32_t slot = ok ? 0xFFFFFFFEu : 0xFFFFFFFFu;
+                    if (head) {
+                        const uint32_t above = lane == 31u ? 0u : ((headmask | ~okmask) & (0xFFFFFFFEu << lane)); // next head or next position without a k-mer
+                        const uint32_t len = (above ? __ffs(above) - 1u : 32u) - lane;
+                        // the k + len - 1 bases from the run's first base on, both planes
+                        const uint32_t b0 = q - k + 1, wi = b0 >> 5, sh = b0 & 31u;
+                        const uint2 pa = W.planes[wi], pb = W.planes[wi + 1], pc = W.planes[wi + 2];
+                        const uint64_t nm = (1ULL << (k + len - 1u)) - 1ULL;
+                        const uint64_t p0 = (((uint64_t)__funnelshift_r(pb.x, pc.x, sh) << 32) | __funnelshift_r(pa.x, pb.x, sh)) & nm;
+                        const uint64_t p1 = (((uint64_t)__funnelshift_r(pb.y, pc.y, sh) << 32) | __funnelshift_r(pa.y, pb.y, sh)) & nm;
+                        const uint32_t owner = kcf_line_owner(home, g.n_lines, p.xg.world);
+                        uint32_t todo = __activemask();
+                        const uint32_t heads = todo;
+                        while (todo) {
+                            const uint32_t leader = __ffs(todo) - 1;
+                            const uint32_t o = __shfl_sync(heads, owner, leader);
+                            const uint32_t same = __ballot_sync(heads, owner == o) & heads;
+                            // entries come out of this warp's slab of the owner's region; a slab that cannot take the step's runs
+                            // is closed (its rest marked empty) and a new one drawn from the region's cursor: one global atomic
+                            // per KCF_XG_SLAB runs and owner instead of one per warp step — every warp of the GPU adds to the same
+                            // `world` counters, and same-address atomics serialise (measured: 68 ms of a 98 ms step)
+                            const uint32_t need = __popc(same);
+                            uint32_t off = W.xg_next[o];
+                            const uint32_t end = W.xg_end[o];
+                            if (off + need > end) {
+                                if (owner == o) {
+                                    const uint32_t r = __popc(same & ((1u << lane) - 1u));
+                                    for (uint32_t h = off + r; h < end; h += need)
+                                        if (h < p.xg.cap) p.xg.in_runs[o][h] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                                }
+                                uint32_t nb = 0;
+                                if (lane == leader) nb = atomicAdd(&p.xg.cursor[o], (unsigned int)KCF_XG_SLAB);
+                                off = __shfl_sync(heads, nb, leader);
+                                if (lane == leader) W.xg_end[o] = off + KCF_XG_SLAB;
+                            }
+                            if (lane == leader) W.xg_next[o] = off + need;
+                            if (owner == o) {
+                                const uint32_t idx = off + __popc(same & ((1u << lane) - 1u));
+                                if (idx < p.xg.cap) {
+                                    uint64_t ea, eb;
+                                    kcf_xg_pack_run(p0, p1, len, home, ea, eb);
+                                    p.xg.in_runs[o][idx] = make_uint4((uint32_t)ea, (uint32_t)(ea >> 32), (uint32_t)eb, (uint32_t)(eb >> 32));
+                                    slot = (o << 28) | idx;
+                                } else {
+                                    p.xg.flags[0] = 1u; // region full: the host reports it (the run reads as absent meanwhile)
+                                    slot = 0xFFFFFFFFu;
+                                }
+                            }
+                            todo &= ~same;
+                        }
+                    }
+                    __syncwarp();
+                    p.xg.pos_slot[base + cpos] = slot;
+                    if (lane == 0) {
+                        p.xg.okw[(base >> 5) + j] = W.okw[j];
+                        p.xg.start[(base >> 5) + j] = W.start[j];
+                    }
+                    continue;
+                }
                 if (EXTRACT) {
                     const uint64_t base = (tile - p.tile_begin) * KCF_TILE + (uint64_t)chunk * KCF_CHUNK;
                     p.x_keys[base + cpos] = key;
@@ -504,6 +581,12 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
             if (lane == 0) p.x_sum[tile - p.tile_begin] = owned_sum;
         } else if (!EXTRACT && lane == 0) p.tile_sum[tile] = W.acc;
         __syncwarp();
+    }
+    if (XSEND) { // the unused rest of this warp's slabs reads "no run"
+        __syncwarp();
+        for (uint32_t o = 0; o < p.xg.world; ++o)
+            for (uint32_t h = W.xg_next[o] + lane; h < W.xg_end[o]; h += 32)
+                if (h < p.xg.cap) p.xg.in_runs[o][h] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
     }
 }
 
@@ -836,9 +919,10 @@ extern "C" int kcf_plan_create(kcf_ctx *ctx, int32_t kmer_length, const kcf_wind
 }
 
 int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t min_count, uint64_t tile_begin, uint64_t tile_end,
-                      int32_t *d_counts, bool extract, uint32_t *d_owned_hit, unsigned long long *d_owned_sum)
+                      int32_t *d_counts, bool extract, uint32_t *d_owned_hit, unsigned long long *d_owned_sum, const KcfXgDev *xsend)
 {
     const bool owned = d_owned_hit != nullptr;
+    if (xsend) extract = true;
     if (!extract && !owned && db->part_world > 1)
         return kcf_fail(ctx, KCF_ERR_ARG, "this database holds slice %d of %d: screen it through the exchange calls (kcf_xchg_*)", db->part_rank, db->part_world);
     if (plan->ref_generation != ctx->ref_generation)
@@ -869,6 +953,7 @@ int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t min_coun
     p.x_homes = plan->x_homes;
     p.x_okw = plan->x_okw;
     p.x_start = plan->x_start;
+    if (xsend) p.xg = *xsend;
     if (owned) {
         p.x_okw = plan->s_okw;
         p.x_start = plan->s_start;
@@ -886,7 +971,8 @@ int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t min_coun
     if (db->geom.kw == 2) { // 128-bit keys: no minimizer, strandedness read at run time
         if (d_counts) kern = S == 7 ? kcf_screen_kernel<7, KCF_MODE_COUNTS, false> : kcf_screen_kernel<6, KCF_MODE_COUNTS, false>;
         else kern = S == 7 ? kcf_screen_kernel<7, KCF_MODE_SCREEN, false> : kcf_screen_kernel<6, KCF_MODE_SCREEN, false>;
-    } else if (extract) kern = KCF_PICK(KCF_MODE_EXTRACT);
+    } else if (xsend) kern = KCF_PICK(KCF_MODE_XSEND);
+    else if (extract) kern = KCF_PICK(KCF_MODE_EXTRACT);
     else if (owned) kern = KCF_PICK(KCF_MODE_OWNED);
     else if (d_counts) kern = KCF_PICK(KCF_MODE_COUNTS);
     else kern = KCF_PICK(KCF_MODE_SCREEN);

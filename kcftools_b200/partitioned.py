@@ -10,9 +10,11 @@ walks all of them, probes only the k-mers whose home line it owns (kcf_scan_owne
 per-tile count sums are sum-reduced over the ranks (one bit per k-mer instead of 12-16 bytes each way), then folded
 (kcf_scan_fold, kcf_plan_finalize).  Every rank ends up with every row.
 
-`Exchange` is the communication seam: `DistExchange` = torch.distributed (NCCL over NVLink / NVSwitch on the GPU box,
-one process per GPU); `screen_partitioned_local` drives several contexts of ONE process in lockstep and moves the
-buffers by slicing — the single-GPU test of exactly the same library calls.
+`screen_partitioned` is the k-mer exchange over PEER MEMORY (kcf_xg_*: every rank's workspace is mapped by its peers through
+CUDA IPC; the screening kernel writes k-mers straight into their owners' inboxes over NVLink, the owners write counts straight
+back); `screen_partitioned_a2a` is the same exchange as NCCL all-to-all collectives (round 1, kept for comparison).  The
+`*_local` variants drive several contexts of ONE process in lockstep — the single-GPU tests of exactly the same library
+calls.
 """
 from __future__ import annotations
 
@@ -53,12 +55,13 @@ def _finish(ctx, plan, weights):
     return plan.fetch()
 
 
-def screen_partitioned(ctx, db, plan, group=None, min_count: int = 1, weights=(0.3, 0.3, 0.4), batch_tiles: int = BATCH_TILES,
-                       phases: dict | None = None) -> np.ndarray:
-    """one rank of a torch.distributed job: `db` was opened with placement=1 after ctx.set_partition(rank, world), `plan`
-    holds THIS rank's windows.  Returns this rank's rows.  `phases` (optional dict) accumulates seconds per phase —
-    a device synchronisation is then inserted after each — and the bytes this rank put on the wire (`_bytes_out`,
-    `_bytes_back`; `_n` counts the calls)."""
+def screen_partitioned_a2a(ctx, db, plan, group=None, min_count: int = 1, weights=(0.3, 0.3, 0.4), batch_tiles: int = BATCH_TILES,
+                           phases: dict | None = None) -> np.ndarray:
+    """the k-mer exchange as NCCL all-to-all collectives over caller-owned buffers (round-1 path, kept for comparison with the
+    peer-memory exchange below: five host-synchronous phases per batch, 12 B out + 4 B back per k-mer).  One rank of a
+    torch.distributed job: `db` was opened with placement=1 after ctx.set_partition(rank, world), `plan` holds THIS rank's
+    windows.  Returns this rank's rows.  `phases` (optional dict) accumulates seconds per phase — a device synchronisation is
+    then inserted after each — and the bytes this rank put on the wire (`_bytes_out`, `_bytes_back`; `_n` counts the calls)."""
     import torch
     import torch.distributed as dist
     world, dev = dist.get_world_size(group), torch.device("cuda", ctx.device)
@@ -110,7 +113,7 @@ def screen_partitioned(ctx, db, plan, group=None, min_count: int = 1, weights=(0
     return _finish(ctx, plan, weights)
 
 
-def screen_partitioned_local(ranks, min_count: int = 1, weights=(0.3, 0.3, 0.4), batch_tiles: int = BATCH_TILES) -> list[np.ndarray]:
+def screen_partitioned_a2a_local(ranks, min_count: int = 1, weights=(0.3, 0.3, 0.4), batch_tiles: int = BATCH_TILES) -> list[np.ndarray]:
     """`ranks` = [(ctx, db, plan), ...]: every slice of one database, each with its own window shard, all on GPUs this
     process can see (typically the same one).  Runs the ranks in lockstep; the all-to-all is done by slicing."""
     import torch
@@ -134,6 +137,146 @@ def screen_partitioned_local(ranks, min_count: int = 1, weights=(0.3, 0.3, 0.4),
             back = torch.cat(parts) if parts else torch.empty(0, dtype=torch.int32, device=devs[s])
             _fold(ctx, plan, t0, t1, back, ext[s][2], min_count)
     return [_finish(ctx, plan, weights) for (ctx, db, plan) in ranks]
+
+
+# ---- k-mer exchange over peer memory (kcf_xg_*) ----------------------------------------------------------------------------
+class Exchange:
+    """this rank's exchange workspace, connected to its peers'"""
+
+    def __init__(self, ctx, db, rank: int, world: int, batch_tiles: int):
+        self.ctx, self.rank, self.world, self.batch_tiles = ctx, rank, world, batch_tiles
+        self._h = C.c_void_p()
+        ctx._check(ctx._lib.kcf_xg_create(ctx._h, db._h, rank, world, batch_tiles, C.byref(self._h)))
+
+    def export(self) -> tuple[bytes, int]:
+        h = (C.c_uint8 * 64)()
+        p = C.c_void_p()
+        self.ctx._check(self.ctx._lib.kcf_xg_export(self._h, h, C.byref(p), None))
+        return bytes(h), p.value
+
+    def connect(self, handles: list[bytes] | None = None, pointers: list[int] | None = None):
+        if pointers is not None:
+            arr = (C.c_void_p * self.world)(*pointers)
+            self.ctx._check(self.ctx._lib.kcf_xg_connect(self._h, None, arr))
+        else:
+            blob = b"".join(handles)
+            self.ctx._check(self.ctx._lib.kcf_xg_connect(self._h, blob, None))
+
+    def status(self) -> tuple[int, int, int]:
+        """synchronises; raises on a workspace overflow.  Returns (bytes out per run, bytes back per run, runs sent in the last batch)"""
+        a, b, n = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.ctx._check(self.ctx._lib.kcf_xg_status(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.ctx._lib.kcf_xg_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+def _exchange_of(ctx, db, plan, rank, world, batch_tiles, connect):
+    """the workspace is kept on the plan: created and connected once, reused by every later call"""
+    x = getattr(plan, "_exchange", None)
+    if x is None or x.world != world or x.batch_tiles != batch_tiles:
+        if x is not None:
+            x.close()
+        x = Exchange(ctx, db, rank, world, batch_tiles)
+        connect(x)
+        plan._exchange = x
+    return x
+
+
+def screen_partitioned(ctx, db, plan, group=None, min_count: int = 1, weights=(0.3, 0.3, 0.4), batch_tiles: int = BATCH_TILES,
+                       phases: dict | None = None) -> np.ndarray:
+    """one rank of a torch.distributed job (NCCL, one process per GPU): `db` was opened with placement=1 after
+    ctx.set_partition(rank, world), `plan` holds THIS rank's windows.  Returns this rank's rows.
+
+    Per batch of tiles: kcf_xg_send (the screening kernel appends every RUN of k-mers sharing a home line — 16 bytes for up to
+    11 k-mers — to its owner's inbox over NVLink), a barrier, kcf_xg_answer (owners fetch a run's line once, look its k-mers up,
+    store the counts into the requesters' workspaces), a barrier, kcf_xg_fold.  Everything is
+    queued on the library's stream — the barriers are one-element all-reduces issued on that same stream — so the host
+    never waits inside the loop.  `phases` (optional dict) accumulates seconds per phase (a device synchronisation is then
+    inserted after each) and `_bytes_out` / `_bytes_back`, the bytes this rank put on the wire."""
+    import time
+    import torch
+    import torch.distributed as dist
+    world, me, dev = dist.get_world_size(group), dist.get_rank(group), torch.device("cuda", ctx.device)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    batch_tiles = int(min(batch_tiles, max(plan.n_tiles, 1)))
+    nb = torch.tensor([plan.n_tiles, batch_tiles], device=dev)
+    dist.all_reduce(nb, op=dist.ReduceOp.MAX, group=group)  # every rank takes part in every barrier: the largest tile count and batch
+    max_tiles, batch_tiles = int(nb[0].item()), int(nb[1].item())
+
+    def connect(x):
+        handle, _ = x.export()
+        handles = [None] * world
+        dist.all_gather_object(handles, handle, group=group)
+        x.connect(handles=handles)
+    x = _exchange_of(ctx, db, plan, me, world, batch_tiles, connect)
+    tt = phases if phases is not None else {}
+    for k_ in ("send", "barrier_1", "answer", "barrier_2", "fold"):
+        tt.setdefault(k_, 0.0)
+    tt["_n"] = tt.get("_n", 0) + 1
+    token = torch.zeros(1, device=dev)
+
+    def lap(name, t):
+        if phases is not None:
+            torch.cuda.synchronize(dev)
+            tt[name] += time.perf_counter() - t
+        return time.perf_counter()
+    with torch.cuda.stream(stream):
+        for t0 in range(0, max(max_tiles, 1), batch_tiles):
+            t1 = t0 + batch_tiles
+            t = time.perf_counter()
+            ctx._check(ctx._lib.kcf_xg_send(ctx._h, db._h, plan._h, x._h, t0, t1))
+            t = lap("send", t)
+            if phases is not None:  # what crosses NVLink: the runs of this batch that other ranks answer, there and back
+                out_b, back_b, runs = x.status()
+                tt["_runs"] = tt.get("_runs", 0) + runs
+                tt["_bytes_out"] = tt.get("_bytes_out", 0) + out_b * runs * (world - 1) // world
+                tt["_bytes_back"] = tt.get("_bytes_back", 0) + back_b * runs * (world - 1) // world
+                t = time.perf_counter()
+            dist.all_reduce(token, group=group)
+            t = lap("barrier_1", t)
+            ctx._check(ctx._lib.kcf_xg_answer(ctx._h, db._h, x._h))
+            t = lap("answer", t)
+            dist.all_reduce(token, group=group)
+            t = lap("barrier_2", t)
+            ctx._check(ctx._lib.kcf_xg_fold(ctx._h, plan._h, x._h, t0, t1, min_count))
+            t = lap("fold", t)
+    x.status()
+    return _finish(ctx, plan, weights)
+
+
+def screen_partitioned_local(ranks, min_count: int = 1, weights=(0.3, 0.3, 0.4), batch_tiles: int = BATCH_TILES) -> list[np.ndarray]:
+    """`ranks` = [(ctx, db, plan), ...]: every slice of one database, each with its own window shard, all contexts on GPUs
+    of THIS process (typically the same one).  The same library calls as screen_partitioned, the workspaces connected by
+    plain device pointers, the barriers replaced by device synchronisations."""
+    import torch
+    world = len(ranks)
+    batch_tiles = int(min(batch_tiles, max(max(r[2].n_tiles for r in ranks), 1)))
+    xs = [Exchange(ctx, db, i, world, batch_tiles) for i, (ctx, db, plan) in enumerate(ranks)]
+    ptrs = [x.export()[1] for x in xs]
+    for x in xs:
+        x.connect(pointers=ptrs)
+    n_tiles = max(r[2].n_tiles for r in ranks)
+    try:
+        for t0 in range(0, max(n_tiles, 1), batch_tiles):
+            t1 = t0 + batch_tiles
+            for x, (ctx, db, plan) in zip(xs, ranks):
+                ctx._check(ctx._lib.kcf_xg_send(ctx._h, db._h, plan._h, x._h, t0, t1))
+            torch.cuda.synchronize()
+            for x, (ctx, db, plan) in zip(xs, ranks):
+                ctx._check(ctx._lib.kcf_xg_answer(ctx._h, db._h, x._h))
+            torch.cuda.synchronize()
+            for x, (ctx, db, plan) in zip(xs, ranks):
+                ctx._check(ctx._lib.kcf_xg_fold(ctx._h, plan._h, x._h, t0, t1, min_count))
+        for x in xs:
+            x.status()
+        return [_finish(ctx, plan, weights) for (ctx, db, plan) in ranks]
+    finally:
+        for x in xs:
+            x.close()
 
 
 # ---- scan placement ---------------------------------------------------------------------------------------------------
