@@ -165,6 +165,42 @@ def build_workload(name: str, device, rank: int = 0) -> Workload:
     return wl
 
 
+def shared_workload(name: str, device, rank: int, world: int, dist) -> tuple[Workload, str | None]:
+    """N > 1, large workloads: rank 0 builds the images once and the other ranks map them from tmpfs — 8 ranks holding a 21 GB
+    .kmc_suf each (twice while it is assembled) would take a third of a terabyte of host memory.  Falls back to every rank
+    building its own copy when /dev/shm is too small.  Returns (workload, directory to remove at the end or None)."""
+    from tools import synth
+    n_chrom, clen, window, desc = WORKLOADS[name]
+    need = int(n_chrom * clen * 1.02) + int(n_chrom * clen * 8.5)  # FASTA + ~1 record of 8 bytes per base
+    ok = os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > need + (8 << 30)
+    flag = [ok]
+    dist.broadcast_object_list(flag, src=0)
+    if not flag[0]:
+        return build_workload(name, device, rank), None
+    d = f"/dev/shm/kcfbench_{os.environ.get('MASTER_PORT', '0')}_{name}"
+    if rank == 0:
+        shutil.rmtree(d, ignore_errors=True)
+        os.makedirs(d)
+        w = build_workload(name, device, rank)
+        np.save(os.path.join(d, "fasta.npy"), w.fasta.data)
+        np.save(os.path.join(d, "pre.npy"), w.kmc.pre)
+        np.save(os.path.join(d, "suf.npy"), w.kmc.suf)
+        json.dump({"names": w.fasta.names, "lengths": w.fasta.lengths, "offsets": w.fasta.offsets, "line_bases": w.fasta.line_bases,
+                   "line_width": w.fasta.line_width, "k": w.kmc.k, "P": w.kmc.P, "L": w.kmc.L, "n_bins": w.kmc.n_bins, "counter_size": w.kmc.counter_size,
+                   "total": w.kmc.total, "both_strands": w.kmc.both_strands}, open(os.path.join(d, "meta.json"), "w"))
+        del w
+    dist.barrier()
+    m = json.load(open(os.path.join(d, "meta.json")))
+    fasta = synth.FastaImage(np.load(os.path.join(d, "fasta.npy"), mmap_mode="r"), m["names"], m["lengths"], m["offsets"], m["line_bases"], m["line_width"])
+    kmc = synth.KmcImage(pre=np.load(os.path.join(d, "pre.npy"), mmap_mode="r"), suf=np.load(os.path.join(d, "suf.npy"), mmap_mode="r"), k=m["k"], P=m["P"],
+                         L=m["L"], n_bins=m["n_bins"], counter_size=m["counter_size"], total=m["total"], both_strands=m["both_strands"])
+    w = Workload(name, fasta, kmc, window, desc)
+    from kcftools_b200.api import fixed_windows
+    w.wins, w.segs, w.starts, w.ends, w.sids = fixed_windows(fasta.lengths, window, 0, 31)
+    log(f"[bench r{rank}] {name}: images mapped from {d}")
+    return w, (d if rank == 0 else None)
+
+
 def gtf_windows(fasta, feature: str, genes_per_chrom: int, seed: int = 31337):
     """gene / transcript window and segment arrays from the C++ host (kcftools_b200/host `_windows` hook: the product's own GTF
     logic) for a synthetic GTF over the workload's chromosomes.  The hook needs the sequence NAMES and LENGTHS only, so it gets
@@ -618,6 +654,9 @@ def main():
     # ---- N > 1: the placements of a table that does not have to fit one GPU
     if world > 1 and want("placements", not args.no_placements):
         del pinned
+        wl.fasta = wl.kmc = None  # the headline workload's images are no longer needed: give the host memory back
+        import gc
+        gc.collect()
         try:
             line["placements"] = placements_leg(torch, dist, ctx, stream, device, rank, world, args, barrier, allmax, allsum)
         except Exception as e:
@@ -738,7 +777,7 @@ def placements_leg(torch, dist, ctx, stream, device, rank, world, args, barrier,
     from kcftools_b200.api import KMC
     from kcftools_b200.partitioned import screen_partitioned, screen_partitioned_a2a, screen_partitioned_scan
     torch.cuda.empty_cache()
-    w = build_workload(args.placement_workload, device, rank)
+    w, shm_dir = shared_workload(args.placement_workload, device, rank, world, dist)
     seqs = w.seqs()
     out = {"workload": f"{w.name}: {w.desc}", "db_records": int(w.kmc.total), "windows": int(w.wins.size), "reference_bp": int(sum(w.fasta.lengths)),
            "steps": 3, "warmup": 1}
@@ -854,6 +893,9 @@ def placements_leg(torch, dist, ctx, stream, device, rank, world, args, barrier,
         out["a2a"] = {"error": repr(e)}
     ctx.set_partition(0, 1)
     ctx.ref_clear()
+    barrier()
+    if shm_dir:
+        shutil.rmtree(shm_dir, ignore_errors=True)
     return out
 
 

@@ -516,7 +516,11 @@ def kmc_image_from_genomes_grouped(genomes: list[torch.Tensor], *, k: int = 31, 
     nsb = (k - P) // 4
     maxc = min((1 << (8 * counter_size)) - 1, 255 if counter_size == 1 else (1 << 31) - 1)
     hist_all = torch.zeros(n_bins << (2 * P), dtype=torch.int64, device=dev)
-    parts = [np.frombuffer(b"KMCS", np.uint8)]
+    rec_size = nsb + counter_size
+    upper = sum(max(int(gq.numel()) - k + 1, 0) for gq in genomes)  # distinct k-mers cannot outnumber positions
+    buf = np.empty(8 + upper * rec_size, np.uint8)  # one buffer, filled group by group (untouched pages cost nothing)
+    buf[:4] = np.frombuffer(b"KMCS", np.uint8)
+    used = 4
     total = 0
     for gi in range(groups):
         b_lo, b_hi = n_bins * gi // groups, n_bins * (gi + 1) // groups
@@ -567,12 +571,12 @@ def kmc_image_from_genomes_grouped(genomes: list[torch.Tensor], *, k: int = 31, 
             rec[:, j] = ((suffix >> (8 * (nsb - 1 - j))) & 0xFF).to(torch.uint8)
         for j in range(counter_size):
             rec[:, nsb + j] = ((cnt >> (8 * j)) & 0xFF).to(torch.uint8)
-        parts.append(rec.flatten().cpu().numpy())
+        buf[used:used + n * rec_size] = rec.flatten().cpu().numpy()
+        used += n * rec_size
         total += n
         del rec, suffix, uk, cnt
-    parts.append(np.frombuffer(b"KMCS", np.uint8))
-    suf = np.concatenate(parts)
-    del parts
+    buf[used:used + 4] = np.frombuffer(b"KMCS", np.uint8)
+    suf = buf[:used + 4]
     lut = (torch.cumsum(hist_all, 0) - hist_all).cpu().numpy().astype("<u8")
     header = struct.pack("<7IQB3x24xI", k, 0, counter_size, P, L, 1, max(maxc, 1), total, 0 if both_strands else 1, 0x200)
     pre = np.concatenate([
