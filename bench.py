@@ -52,9 +52,10 @@ WORKLOADS = {
     "c3st": (9, 10_000_000, -1, "configs[2] / 28: synthetic 90 Mb / 9 chr reference + GTF (1,500 genes per chromosome), transcript windows"),
     "c3": (9, 278_000_000, 0, "configs[2]: synthetic 2.5 Gb / 9 chr reference + GTF (40,500 genes), gene and transcript windows, KMC DB of a mutated copy"),
     "c4s": (12, 250_000_000, 50_000, "configs[3] / 5: synthetic 3.0 Gb / 12 chr reference, 50 kb tiling windows, KMC DB of a mutated copy (~3e9 records)"),
+    "c4": (21, 714_000_000, 50_000, "configs[3]: synthetic 15 Gb / 21 chr reference, 50 kb tiling windows, KMC DB of a mutated copy (~1.5e10 records); tools/c4_full.py"),
 }
 GENES_PER_CHROM = {"c3s": 1500, "c3st": 1500, "c3": 4500}
-BIG = ("c3", "c4s")  # databases built one group of bins at a time (tools/synth.kmc_image_from_genomes_grouped)
+BIG = {"c3": 4, "c4s": 4, "c4": 16}  # databases built in this many groups of bins (tools/synth.kmc_image_from_genomes_grouped)
 
 
 def log(*a):
@@ -149,7 +150,7 @@ def build_workload(name: str, device, rank: int = 0) -> Workload:
     log(f"[bench r{rank}] {name} reference: {n_chrom} x {clen} bp, FASTA {fasta.data.size / 1e6:.0f} MB ({time.time() - t0:.1f}s)")
     t1 = time.time()
     if name in BIG:
-        kmc = synth.kmc_image_from_genomes_grouped(queries, k=31, P=7, L=9, n_bins=512, counter_size=1, coverage=8.0, seed=77, groups=4)
+        kmc = synth.kmc_image_from_genomes_grouped(queries, k=31, P=7, L=9, n_bins=512, counter_size=1, coverage=8.0, seed=77, groups=BIG[name])
     else:
         kmc = synth.kmc_image_from_genomes(queries, k=31, P=7, L=9, n_bins=512, counter_size=1, coverage=8.0, seed=77)
     del queries
