@@ -160,10 +160,37 @@ std::string java_format_2f(double v)
     return std::string(g.neg && !zero ? "-" : (g.neg ? "-" : "")) + ip + "." + fp;
 }
 
+// String.hashCode(): over the UTF-16 code units of the text.  The files are UTF-8: decode code points and feed Java's units
+// (a surrogate pair above U+FFFF); malformed bytes go in as they are, as ISO-8859-1 would read them.
 int32_t java_string_hash(const std::string &s)
 {
     uint32_t h = 0;
-    for (unsigned char c : s) h = 31u * h + c;
+    const size_t n = s.size();
+    for (size_t i = 0; i < n;) {
+        const unsigned char c = (unsigned char)s[i];
+        uint32_t cp = c;
+        size_t len = 1;
+        if (c >= 0xC2 && c <= 0xDF && i + 1 < n && ((unsigned char)s[i + 1] & 0xC0) == 0x80) {
+            cp = ((uint32_t)(c & 0x1F) << 6) | ((unsigned char)s[i + 1] & 0x3F);
+            len = 2;
+        } else if (c >= 0xE0 && c <= 0xEF && i + 2 < n && ((unsigned char)s[i + 1] & 0xC0) == 0x80 && ((unsigned char)s[i + 2] & 0xC0) == 0x80) {
+            cp = ((uint32_t)(c & 0x0F) << 12) | (((uint32_t)(unsigned char)s[i + 1] & 0x3F) << 6) | ((unsigned char)s[i + 2] & 0x3F);
+            len = 3;
+        } else if (c >= 0xF0 && c <= 0xF4 && i + 3 < n && ((unsigned char)s[i + 1] & 0xC0) == 0x80 && ((unsigned char)s[i + 2] & 0xC0) == 0x80 &&
+                   ((unsigned char)s[i + 3] & 0xC0) == 0x80) {
+            cp = ((uint32_t)(c & 0x07) << 18) | (((uint32_t)(unsigned char)s[i + 1] & 0x3F) << 12) | (((uint32_t)(unsigned char)s[i + 2] & 0x3F) << 6) |
+                 ((unsigned char)s[i + 3] & 0x3F);
+            len = 4;
+        }
+        if (cp >= 0x10000) {
+            const uint32_t v = cp - 0x10000;
+            h = 31u * h + (0xD800u + (v >> 10));
+            h = 31u * h + (0xDC00u + (v & 0x3FFu));
+        } else {
+            h = 31u * h + cp;
+        }
+        i += len;
+    }
     return (int32_t)h;
 }
 
@@ -1351,6 +1378,10 @@ int cliMain(int argc, const char *const *argv)
                     for (const kcf_segment_t &s : w.segments) std::printf("\t%d:%d:%d", s.seq_id, s.start0, s.len);
                     std::printf("\n");
                 }
+            return 0;
+        }
+        if (cmd == "_hash") { // test hook: String.hashCode() of the arguments (UTF-8 in, UTF-16 code units hashed)
+            for (int i = 2; i < argc; ++i) std::printf("%d\n", java_string_hash(argv[i]));
             return 0;
         }
         if (cmd == "_format") { // test hook: Java number formatting of the doubles given as hex bit patterns

@@ -76,9 +76,11 @@ def _i32(x: int) -> int:
 
 
 def java_string_hash(s: str) -> int:
+    """String.hashCode(): over the UTF-16 code units (a surrogate pair for code points above U+FFFF)"""
     h = 0
-    for ch in s:
-        h = (31 * h + ord(ch)) & 0xFFFFFFFF
+    units = s.encode("utf-16-le", "surrogatepass")
+    for i in range(0, len(units), 2):
+        h = (31 * h + (units[i] | (units[i + 1] << 8))) & 0xFFFFFFFF
     return _i32(h)
 
 

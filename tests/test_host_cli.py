@@ -229,3 +229,14 @@ def test_getvariations_one_database_over_several_devices(cli, genome, mode):
     def body(path):
         return [l for l in open(path).read().split("\n") if not l.startswith("##date") and not l.startswith("##CMD")]
     assert body(one) == body(three) and len(body(one)) > 30
+
+
+def test_java_string_hash_counts_utf16_units(cli):
+    """String.hashCode() runs over UTF-16 code units: known answers worked out by hand (31 * h + unit), ASCII, Latin-1, BMP and
+    a supplementary character (U+1D538 = D835 DD38), and the C++ host against the Python restatement"""
+    names = ["chr1", "é", "chrÄ1", "染色体1", "\U0001d538x"]
+    want = [pyhost.java_string_hash(s) for s in names]
+    assert want[0] == ((((ord("c") * 31 + ord("h")) * 31 + ord("r")) * 31 + ord("1")) & 0xFFFFFFFF)
+    assert want[1] == 233 and want[4] == ((31 * 0xD835 + 0xDD38) * 31 + ord("x"))
+    got = [int(x) for x in run(cli, "_hash", *names).stdout.split()]
+    assert got == want
