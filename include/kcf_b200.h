@@ -173,6 +173,9 @@ typedef struct kcf_host_seq_t {
     uint32_t line_width;
     uint64_t seq_len;
 } kcf_host_seq_t;
+/* Upper bound, in bases, of the stretches kcf_screen_sharded uploads one at a time (0 = default, 96 Mbases).  A tuning / test knob:
+ * results never depend on it. */
+int kcf_set_upload_piece(kcf_ctx *ctx, uint64_t bases);
 int kcf_shard_windows(const kcf_window_t *wins, uint64_t n_wins, const kcf_segment_t *segs, uint64_t n_segs, int n_shards,
                       uint64_t *bounds_out);
 int kcf_screen_sharded(kcf_ctx *const *ctxs, kcf_db *const *dbs, int n, const kcf_host_seq_t *seqs, uint32_t n_seqs,

@@ -63,6 +63,7 @@ SYMBOLS = {
     "kcf_ref_sync": (C.c_int, [_P]),
     "kcf_ref_clear": (C.c_int, [_P]),
     "kcf_screen": (C.c_int, [_P, _P, _P, C.c_uint64, _P, C.c_uint64, C.c_int32, C.POINTER(C.c_double), _P]),
+    "kcf_set_upload_piece": (C.c_int, [_P, C.c_uint64]),
     "kcf_shard_windows": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64, C.c_int, _P]),
     "kcf_screen_sharded": (C.c_int, [_P, _P, C.c_int, _P, C.c_uint32, _P, C.c_uint64, _P, C.c_uint64, C.c_int32, C.POINTER(C.c_double), _P]),
     "kcf_plan_create": (C.c_int, [_P, C.c_int32, _P, C.c_uint64, _P, C.c_uint64, C.POINTER(_P)]),

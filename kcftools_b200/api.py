@@ -70,6 +70,10 @@ class Context:
         """0 = automatic; a tuning / test knob of the table layout, results never depend on it"""
         self._check(self._lib.kcf_set_minimizer_length(self._h, m))
 
+    def set_upload_piece(self, bases: int):
+        """0 = default; upper bound of the stretches a sharded job uploads one at a time (a tuning / test knob)"""
+        self._check(self._lib.kcf_set_upload_piece(self._h, bases))
+
     def set_partition(self, rank: int, world: int):
         """slice kept by databases opened afterwards with placement=1 (kcftools_b200/partitioned.py)"""
         self._check(self._lib.kcf_set_partition(self._h, rank, world))

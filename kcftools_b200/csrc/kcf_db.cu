@@ -801,6 +801,23 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
 
     // the table comes from the context's block pool: a host that opens one database after the other (a cohort run) gets the
     // previous table's memory back without a cudaFree / cudaMalloc round trip
+    // a pooled table of another size is of no use to this database and would sit next to the new one (two 70 GB tables do
+    // not fit one GPU): give large pooled blocks that cannot serve this request back to the driver first
+    {
+        bool freed = false;
+        for (size_t i = 0; i < ctx->pool.size();) {
+            const size_t b = ctx->pool[i].bytes;
+            const bool fits = b >= db->table_bytes && b <= db->table_bytes + db->table_bytes / 8 + 4096;
+            if (b >= (256ULL << 20) && !fits) {
+                if (!freed) cudaStreamSynchronize(ctx->stream);
+                freed = true;
+                cudaFree(ctx->pool[i].p);
+                ctx->pool.erase(ctx->pool.begin() + i);
+            } else {
+                ++i;
+            }
+        }
+    }
     db->table = (uint8_t *)kcf_pool_get(ctx, db->table_bytes);
     if (!db->table) {
         rc = kcf_fail(ctx, KCF_ERR_NOMEM, "device memory for a table of %llu lines (%.1f GB)", (unsigned long long)nb, (double)db->table_bytes / 1e9);
@@ -976,7 +993,14 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
         uint64_t cap = 64;
         while (cap < 2 * counters[2]) cap <<= 1;
         g.stash_mask = cap - 1;
-        DB_CUDA(cudaMalloc(&db->stash, cap * sizeof(KcfStashEntry)));
+        if (cudaMalloc(&db->stash, cap * sizeof(KcfStashEntry)) != cudaSuccess) {
+            (void)cudaGetLastError();
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            rc = kcf_fail(ctx, KCF_ERR_NOMEM, "device memory for a stash of %llu records (%.2f GB; %.1f of %.1f GB free; table %.1f GB at load factor %.2f)",
+                          counters[2], (double)(cap * sizeof(KcfStashEntry)) / 1e9, (double)free_b / 1e9, (double)total_b / 1e9, (double)db->table_bytes / 1e9, lf);
+            goto done;
+        }
         DB_CUDA(cudaMemsetAsync(db->stash, 0, cap * sizeof(KcfStashEntry), ctx->stream));
         kcf_stash_build_kernel<<<(unsigned)((counters[2] + 255) / 256), 256, 0, ctx->stream>>>(d_ovf, counters[2], db->stash, g);
         DB_CUDA(cudaGetLastError());

@@ -186,6 +186,7 @@ struct kcf_ctx {
     cudaStream_t ing_stream = nullptr;                 // insert kernels: they may run under the proof kernel of the next chunk
     cudaEvent_t ing_proved[2] = {nullptr, nullptr};    // proof kernel that filled staged buffer j done
     cudaEvent_t ing_inserted[2] = {nullptr, nullptr};  // insert kernel that read staged buffer j done
+    uint64_t piece_bases = 0;  // upload piece of a sharded job, 0 = default (kcf_set_upload_piece)
     uint8_t *h_rows = nullptr; // pinned landing area for the rows of a sharded job (kcf_multi.cu): all plans fetched with one wait
     size_t h_rows_cap = 0;
     uint64_t ref_generation = 1; // bumped by kcf_ref_clear: plans remember the generation they were built against

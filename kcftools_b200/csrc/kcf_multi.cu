@@ -15,9 +15,20 @@
 #include <vector>
 #include "kcf_internal.cuh"
 
+// upper bound of one uploaded piece, in bases (rounded down to whole FASTA lines).  Measured on C2 (75 Mb chromosomes): 19.9 ms
+// per job with 24 Mbase pieces, 18.5 with 48, 18.2 with 96 (the bare copy takes 16.5): a piece costs ~0.1 ms of host work
+// (plan, launches), the tail after the last upload only the screening of that piece
 #ifndef KCF_PIECE_BASES
-#define KCF_PIECE_BASES (24u << 20) // upper bound of one uploaded piece, in bases (rounded down to whole FASTA lines)
+#define KCF_PIECE_BASES (96u << 20)
 #endif
+
+extern "C" int kcf_set_upload_piece(kcf_ctx *ctx, uint64_t bases)
+{
+    if (!ctx) return KCF_ERR_ARG;
+    if (bases != 0 && (bases < 1024 || bases > (1ULL << 30))) return kcf_fail(ctx, KCF_ERR_ARG, "upload piece of %llu bases (0 = default, else 1024 .. 2^30)", (unsigned long long)bases);
+    ctx->piece_bases = bases;
+    return KCF_OK;
+}
 
 extern "C" int kcf_shard_windows(const kcf_window_t *wins, uint64_t n_wins, const kcf_segment_t *segs, uint64_t n_segs, int n_shards,
                                  uint64_t *bounds_out)
@@ -64,6 +75,7 @@ static int kcf_screen_shard(kcf_ctx *ctx, kcf_db *db, const kcf_host_seq_t *seqs
 {
     int rc = kcf_ref_clear(ctx);
     if (rc != KCF_OK || w0 >= w1) return rc;
+    const uint64_t piece_bases = ctx->piece_bases ? ctx->piece_bases : (uint64_t)KCF_PIECE_BASES;
     // ---- the stretch of every sequence this shard touches
     std::vector<uint64_t> lo(n_seqs, ~0ULL), hi(n_seqs, 0);
     for (uint64_t wi = w0; wi < w1; ++wi) {
@@ -89,13 +101,13 @@ static int kcf_screen_shard(kcf_ctx *ctx, kcf_db *db, const kcf_host_seq_t *seqs
         if (hi[s] == 0) continue;
         const uint64_t lb = seqs[s].line_bases;
         if (lb == 0 || seqs[s].line_width < lb) return kcf_fail(ctx, KCF_ERR_ARG, "bad .faidx line geometry (lineBases=%u lineWidth=%u)", seqs[s].line_bases, seqs[s].line_width);
-        const uint64_t step = std::max<uint64_t>((uint64_t)KCF_PIECE_BASES / lb, 1) * lb;
+        const uint64_t step = std::max<uint64_t>(piece_bases / lb, 1) * lb;
         for (uint64_t b0 = lo[s] / lb * lb; b0 < hi[s]; b0 += step) pieces.push_back(Piece{s, b0, std::min(b0 + step, hi[s])});
     }
     first_piece[n_seqs] = (uint32_t)pieces.size();
     auto piece_of = [&](uint32_t s, uint64_t base) { // index of the piece of sequence s holding `base`
         const uint64_t lb = seqs[s].line_bases;
-        const uint64_t step = std::max<uint64_t>((uint64_t)KCF_PIECE_BASES / lb, 1) * lb;
+        const uint64_t step = std::max<uint64_t>(piece_bases / lb, 1) * lb;
         return first_piece[s] + (uint32_t)((base - lo[s] / lb * lb) / step);
     };
     // ---- windows grouped by the last piece they need; segments cut at piece boundaries and re-based

@@ -457,17 +457,24 @@ def test_sharded_job_over_several_contexts(sc_main, n_ctx, kind):
 
 
 def test_sharded_job_pieces_of_a_long_sequence(ctx):
-    """a sequence longer than one upload piece (KCF_PIECE_BASES): windows straddling the piece boundaries become two
+    """a sequence longer than one upload piece (kcf_set_upload_piece): windows straddling the piece boundaries become two
     segments inside the library; lines of odd width, a final line without its newline is still fatal (Q9)"""
     from kcftools_b200.api import screen_sharded
-    sc = Scenario(seq_lens=(26_000_000,), seed=77, n_bins=16, line=77, n_runs=6, snp=0.02)
+    sc = Scenario(seq_lens=(3_000_000,), seed=77, n_bins=16, line=77, n_runs=6, snp=0.02)
     db = KMC(ctx, pre=sc.kmc.pre, suf=sc.kmc.suf)
-    starts = np.concatenate([np.arange(0, 25_990_000, 1_300_000), [(24 << 20) // 77 * 77 - 40, (24 << 20) // 77 * 77 - 1, 25_990_000]])
-    wins, segs = windows_from_lists([[(0, int(s), 10_000)] for s in starts])
+    piece = 1 << 20  # 13,617 whole lines of 77 bases: boundaries at 1,048,509 and 2,097,018
+    edge = piece // 77 * 77
+    starts = np.concatenate([np.arange(0, 2_990_000, 130_000), [edge - 40, edge - 1, 2 * edge - 9_999, 2_990_000]])
+    wins, segs = windows_from_lists([[(0, int(s), 10_000)] for s in starts] + [[(0, 100, 2_500_000)]])  # the last one spans all three pieces
     rc, want = _oracle_screen(sc, wins, segs)
     assert rc == 0
-    got = screen_sharded([ctx], [db], sc.seqs(), wins, segs)
+    ctx.set_upload_piece(piece)
+    try:
+        got = screen_sharded([ctx], [db], sc.seqs(), wins, segs)
+    finally:
+        ctx.set_upload_piece(0)
     assert_results_equal(got, want)
+    assert_results_equal(screen_sharded([ctx], [db], sc.seqs(), wins, segs), want)  # default piece: the whole sequence at once
     db.close()
 
 

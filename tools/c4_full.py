@@ -97,8 +97,26 @@ def main():
     groups = [dist.new_group(list(range(s * T, (s + 1) * T))) for s in range(n_shards)]
     part_rank, shard_id, _ = shard.grid_layout(rank, world, T)
     ctx.set_partition(part_rank, T)
+    torch.cuda.empty_cache()
+    bench.log(f"[c4 r{rank}] before the second open: {torch.cuda.mem_get_info(local_rank)[0] / 1e9:.1f} GB free")
     t0 = time.time()
-    db = KMC(ctx, pre=w.kmc.pre, suf=w.kmc.suf, placement=1)
+    err = None
+    try:
+        db = KMC(ctx, pre=w.kmc.pre, suf=w.kmc.suf, placement=1)
+    except Exception as e:  # every rank has to learn of it: the ranks that opened their slice would wait in the collectives for ever
+        err = repr(e)
+        bench.log(f"[c4 r{rank}] scan placement: {err}")
+    if allsum(int(err is not None)):
+        out["scan_T4"] = {"error": err or "another rank could not open its slice"}
+        ctx.close()
+        barrier()
+        if shm_dir:
+            import shutil
+            shutil.rmtree(shm_dir, ignore_errors=True)
+        dist.destroy_process_group()
+        if rank == 0:
+            bench.emit(out)
+        return
     load_s = allmax(time.time() - t0)
     rng = shard.partition(lengths, n_shards)[shard_id]
     lw_, ls_ = shard.local_slice(w.wins, w.segs, *rng)
