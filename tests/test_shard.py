@@ -184,3 +184,22 @@ def test_four_rank_gloo_scan_placement_groups(tmp_path):
     s.close()
     mp.spawn(_scan_worker, args=(4, port, str(tmp_path)), nprocs=4, join=True)
     assert all((tmp_path / f"scan{r}.ok").exists() for r in range(4))
+
+
+def test_library_cut_equals_python_cut():
+    """kcf_shard_windows (what kcf_screen_sharded and `getVariations --devices` use) makes the cut shard.partition makes (what
+    the torchrun bench uses): same ranges for fixed windows, multi-segment windows, more shards than windows.  Host arithmetic
+    only: no device is touched."""
+    from kcftools_b200 import shard
+    from kcftools_b200.api import fixed_windows, shard_windows
+    from common import windows_from_lists
+    rng = np.random.default_rng(9)
+    cases = [fixed_windows([1_000_003, 77, 250_000], 50_000, 0, 31)[:2],
+             windows_from_lists([[(0, int(rng.integers(0, 1000)), int(rng.integers(1, 5000))) for _ in range(int(rng.integers(1, 6)))] for _ in range(257)]),
+             windows_from_lists([[(0, 0, 10)], [(0, 5, 7)]])]
+    for wins, segs in cases:
+        for n in (1, 2, 3, 8, 16):
+            got = [int(b) for b in shard_windows(wins, segs, n)]
+            want = shard.partition(shard.window_lengths(wins, segs), n)
+            assert got == [r[0] for r in want] + [wins.size]
+            assert all(a <= b for a, b in zip(got, got[1:]))
