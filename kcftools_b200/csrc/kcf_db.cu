@@ -10,6 +10,7 @@
 // neither signatures nor the per-bin LUTs.
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -612,6 +613,13 @@ static int floor_log2_u64(uint64_t v)
     return r;
 }
 
+// overflow lines per home line for a table of load factor lf holding (a slice of) a database of n_total records
+static double kcf_overflow_share(double lf, uint64_t n_total)
+{
+    const double colliding = 1.0 - std::exp(-(double)n_total / 6.0 / 4294967296.0);
+    return std::max(0.125, 0.55 * lf * lf) + colliding * 0.35 * lf / 0.6;
+}
+
 extern "C" int kcf_set_load_factor(kcf_ctx *ctx, double lf)
 {
     if (!ctx) return KCF_ERR_ARG;
@@ -743,7 +751,7 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
         // against the device's TOTAL memory: every rank of a partitioned database must derive the same geometry
         for (double cand : steps) {
             lf = cand;
-            const double ov = std::max(0.125, 0.55 * lf * lf); // the overflow region grows with the density (below)
+            const double ov = kcf_overflow_share(lf, N); // the overflow region grows with the density (below)
             if ((double)N * share / (g.S * lf) * KCF_LINE_BYTES * (1.0 + ov) <= 0.4 * (double)total_b) break;
         }
     }
@@ -762,7 +770,11 @@ extern "C" int kcf_db_open_mem(kcf_ctx *ctx, const uint8_t *pre, uint64_t pre_le
     // find their home line full grows with the density: 5 % at 0.15, 10 % at 0.3, 17 % at 0.5, 23 % at 0.7, 29 % at 0.9
     // (tools/line_occupancy_model.py) — about 0.33 lf; held in lines filled to ~0.6 that is 0.55 lf^2 of the home lines,
     // and never less than 1/8 of them
-    g.n_ov = cs == 0 ? 1 : std::max<uint64_t>((uint64_t)((double)g.n_local * std::max(0.125, 0.55 * lf * lf)), 32);
+    // and never less than 1/8 of them.  A second term covers what the 32-bit minimizer hash costs very large databases: two
+    // different minimizers with the same hash share a home line for good, and with N / 6 minimizer runs in 2^32 values the
+    // share of runs that do is 1 - exp(-N / 6 / 2^32): 3 % at C2's 9e8 records, 9 % at 2.5e9, 44 % at C4's 1.5e10 — measured
+    // there (profiles/r2u_c4_full_8gpu.json) as 6-15 % of the records in the stash with the overflow region sized by density alone
+    g.n_ov = cs == 0 ? 1 : std::max<uint64_t>((uint64_t)((double)g.n_local * kcf_overflow_share(lf, N)), 32);
     nb = g.n_local + g.n_ov;                                       // lines allocated below
     if (nb >= 0xFFFFFFFFULL) return kcf_fail(ctx, KCF_ERR_UNSUPPORTED, "%llu table lines do not fit a 32-bit line index; partition the database", (unsigned long long)nb);
     g.stash_mask = 0;
