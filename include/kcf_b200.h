@@ -272,8 +272,11 @@ int kcf_cohort_create(kcf_ctx *ctx, uint64_t n_windows, uint32_t n_samples, cons
                       kcf_cohort **out);
 void kcf_cohort_destroy(kcf_cohort *c);
 /* Column `sample`, rows [window_offset, window_offset + plan windows) <- the results of a plan that has run (device to
- * device, asynchronous).  A sample whose TOTAL_KMERS / EFFLEN differ from the cohort's is "Windows mismatch"
- * (Cohort.java:92-94), reported by kcf_cohort_scores / kcf_cohort_fetch. */
+ * device, asynchronous).  A sample whose TOTAL_KMERS / EFFLEN differ from the cohort's is reported as "Windows mismatch"
+ * by kcf_cohort_scores / kcf_cohort_fetch.  This is an extra check of this path, NOT reference behaviour: Cohort.java:92-94
+ * raises the mismatch only for a window id missing from the first file and otherwise keeps the first file's totals
+ * silently (the file-based `cohort` of the host program does exactly that); plans made from one window list cannot differ
+ * there, so the check only fires on a caller's mistake. */
 int kcf_cohort_add_plan(kcf_ctx *ctx, kcf_cohort *c, uint32_t sample, uint64_t window_offset, kcf_plan *plan);
 /* Column `sample` <- n_windows cells parsed by the host (needs the totals given to kcf_cohort_create). */
 int kcf_cohort_set_sample(kcf_ctx *ctx, kcf_cohort *c, uint32_t sample, const kcf_cell_t *cells);

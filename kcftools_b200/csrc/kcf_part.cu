@@ -371,17 +371,40 @@ __global__ void kcf_xg_publish_kernel(KcfXgDev X)
 // l-th k-mer of the block, found through the prefix sums of the run lengths — so that, as in the replicated kernel, the
 // lanes that share a run share its home line inside ONE load instruction and the coalescer fetches the line once.  (One
 // thread per run asked for the line's sectors one after the other: 84 ms per c4s step; a quad per run with a whole-line
-// prefetch: 50 ms — the later loads did not hit L1.)  Counts go out as bytes, consecutive k-mers of a run to consecutive
-// bytes of the run's slot in that sender's BACK region.
+// prefetch: 50 ms — the later loads did not hit L1.)  The rest follows the replicated kernel too: filter and mask word
+// travel with the key words; a k-mer whose home line names other lines goes to a per-warp queue that is searched one item
+// per lane with whole-line probes (searching them where they turn up, slot by slot, ran 40 % of the kernel's instructions
+// at two active lanes: profiles/r2w_answer_*).  The counts of a run (one byte each while the database's counts fit a byte)
+// make the run's slot in that sender's BACK region; slots leave the SM whole, through shared memory: 512 contiguous bytes
+// of the requester's memory per store instruction.
+#define KCF_XG_QCAP 64
+#ifndef KCF_XG_ANSWER_BLOCKS
+#define KCF_XG_ANSWER_BLOCKS 6 // resident CTAs per SM the registers are held to (48 warps)
+#endif
+struct KcfXgItem {
+    unsigned long long key;
+    uint32_t home;
+    uint32_t info; // byte offset of the count in the warp's staged slots << 16 | home mask (bit 0 cleared)
+};
+
 template <int S>
-__global__ void __launch_bounds__(256) kcf_xg_answer_kernel(const uint8_t *__restrict__ table, const KcfStashEntry *__restrict__ stash, KcfTableGeom g, KcfXgDev X)
+__global__ void __launch_bounds__(256, KCF_XG_ANSWER_BLOCKS) kcf_xg_answer_kernel(const uint8_t *__restrict__ table, const KcfStashEntry *__restrict__ stash, const __grid_constant__ KcfTableGeom g, const __grid_constant__ KcfXgDev X)
 {
+    constexpr uint32_t CB = S == 13 ? 1u : 4u, STRIDE = CB == 1 ? 16u : 48u; // bytes per count / per run slot (= X.cbytes, X.stride)
+    __shared__ __align__(16) uint8_t stage_all[8][32 * STRIDE];
+    __shared__ __align__(16) KcfXgItem queue_all[8][KCF_XG_QCAP];
+    uint8_t *stage = stage_all[threadIdx.x >> 5];
+    KcfXgItem *queue = queue_all[threadIdx.x >> 5];
     const uint32_t s = blockIdx.y; // sender
     const uint32_t n = X.my_count[s];
     const uint4 *runs = X.my_runs + (uint64_t)s * X.cap;
     uint8_t *back = X.back[s];
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    auto put = [&](uint32_t at, uint32_t c) {
+        if (CB == 1) stage[at] = (uint8_t)c;
+        else *reinterpret_cast<uint32_t *>(stage + at) = c;
+    };
     for (uint64_t i0 = warp * 32; i0 < n; i0 += n_warps * 32) {
         uint64_t p0 = 0, p1 = 0;
         uint32_t len = 0, home = 0;
@@ -397,6 +420,26 @@ __global__ void __launch_bounds__(256) kcf_xg_answer_kernel(const uint8_t *__res
             if (lane >= (uint32_t)d) incl += t;
         }
         const uint32_t excl = incl - len, total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t qn = 0; // queue length (warp uniform)
+        auto flush_queue = [&]() {
+            __syncwarp();
+#pragma unroll 1
+            for (uint32_t t = lane; t < qn; t += 32) {
+                const KcfXgItem it = queue[t];
+                uint32_t m2 = it.info & 0x7FFEu, c2 = 0;
+                bool found = false;
+                while (m2 && !found) {
+                    const uint32_t d = __ffs(m2) - 1;
+                    m2 &= m2 - 1;
+                    found = kcf_probe_line<S>(table + (uint64_t)kcf_line_wrap(it.home, d, g) * KCF_LINE_BYTES, it.key, c2);
+                }
+                if (!found) c2 = (it.info & (1u << KCF_STASH_BIT)) ? kcf_stash_find(stash, g, it.key) : 0u;
+                put(it.info >> 16, c2);
+            }
+            qn = 0;
+            __syncwarp();
+        };
+#pragma unroll 1
         for (uint32_t t0 = 0; t0 < total; t0 += 32) {
             const uint32_t kidx = t0 + lane;
             const bool active = kidx < total;
@@ -409,21 +452,51 @@ __global__ void __launch_bounds__(256) kcf_xg_answer_kernel(const uint8_t *__res
             const uint32_t j = kidx - __shfl_sync(0xffffffffu, excl, r);
             const uint64_t q0 = __shfl_sync(0xffffffffu, p0, r), q1 = __shfl_sync(0xffffffffu, p1, r);
             const uint32_t hm = __shfl_sync(0xffffffffu, home, r);
-            if (!active) continue;
-            uint32_t f0 = (uint32_t)(q0 >> j) & g.km, f1 = (uint32_t)(q1 >> j) & g.km;
-            if (g.both_strands) kcf_plane_canonical(f0, f1, kcf_plane_rc(f0, g.k, g.km), kcf_plane_rc(f1, g.k, g.km), f0, f1);
-            const uint64_t key = ((uint64_t)f1 << 32) | f0;
-            const uint8_t *L = table + (uint64_t)kcf_line_wrap(hm, 0, g) * KCF_LINE_BYTES;
-            uint32_t c = 0;
-            if (!(KCF_KEY_IN_LINES(key) && kcf_probe_line<S>(L, key, c))) {
-                c = 0;
-                if (kcf_filter_pass(L, key, g))
-                    c = kcf_probe_lines(table, stash, g, key, hm, kcf_mask_from_word31(__ldg(reinterpret_cast<const uint32_t *>(L) + 31)), 1);
+            const uint32_t at = r * STRIDE + j * CB;
+            uint64_t key = 0;
+            uint32_t mask = 0;
+            bool pending = false;
+            if (active) {
+                uint32_t f0 = (uint32_t)(q0 >> j) & g.km, f1 = (uint32_t)(q1 >> j) & g.km;
+                if (g.both_strands) kcf_plane_canonical(f0, f1, kcf_plane_rc(f0, g.k, g.km), kcf_plane_rc(f1, g.k, g.km), f0, f1);
+                key = ((uint64_t)f1 << 32) | f0;
+                const uint8_t *L = table + (uint64_t)kcf_line_wrap(hm, 0, g) * KCF_LINE_BYTES;
+                // filter and mask words travel with the key words (a miss needs them; asked for after the compare they would
+                // cost a dependent round trip)
+                const uint32_t w31 = __ldg(reinterpret_cast<const uint32_t *>(L) + 31);
+                const unsigned long long fword = S == 13 ? __ldg(reinterpret_cast<const unsigned long long *>(L + 104))
+                                                         : (unsigned long long)__ldg(reinterpret_cast<const uint32_t *>(L + 120));
+                const bool inl = KCF_KEY_IN_LINES(key);
+                uint32_t c = 0;
+                if (!(inl && kcf_probe_line<S>(L, key, c))) {
+                    c = 0;
+                    if (S == 13 ? kcf_filter_pass64(fword, key) : kcf_filter_pass32((uint32_t)fword, key)) {
+                        mask = kcf_mask_from_word31(w31);
+                        if (inl && (mask & 0x7FFEu)) pending = true;
+                        else if ((mask >> KCF_STASH_BIT) & 1u) c = kcf_stash_find(stash, g, key);
+                    }
+                }
+                put(at, c);
             }
-            uint8_t *dst = back + (i0 + r) * X.stride + (uint64_t)j * X.cbytes;
-            if (X.cbytes == 1) *dst = (uint8_t)c;
-            else *reinterpret_cast<uint32_t *>(dst) = c;
+            const uint32_t pb = __ballot_sync(0xffffffffu, pending);
+            if (pb) {
+                if (pending) {
+                    KcfXgItem it;
+                    it.key = key;
+                    it.home = hm;
+                    it.info = (at << 16) | (mask & 0xFFFEu);
+                    queue[qn + __popc(pb & ((1u << lane) - 1u))] = it;
+                }
+                qn += __popc(pb);
+                if (qn + 32 > KCF_XG_QCAP) flush_queue();
+            }
         }
+        if (qn) flush_queue();
+        __syncwarp();
+        const uint32_t n16 = (uint32_t)min((uint64_t)32, n - i0) * (STRIDE / 16u); // bytes past a run's length are never read
+        uint4 *dst = reinterpret_cast<uint4 *>(back + i0 * STRIDE);
+        for (uint32_t q = lane; q < n16; q += 32) dst[q] = reinterpret_cast<const uint4 *>(stage)[q];
+        __syncwarp();
     }
 }
 

@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
         }
         if (OWNED) {
             if (lane == 0) p.x_sum[tile - p.tile_begin] = owned_sum;
-        } else if (!EXTRACT && lane == 0) p.tile_sum[tile] = W.acc;
+        } else if (!EXTRACT && !COUNTS && lane == 0) p.tile_sum[tile] = W.acc; // the COUNTS pass (min_count = 1) leaves the run's tile sums alone
         __syncwarp();
     }
     if (XSEND) { // the unused rest of this warp's slabs reads "no run"

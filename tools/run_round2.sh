@@ -12,7 +12,7 @@ timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytes
 timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > $D/bench_c2.json 2> $D/bench_c2.err
 timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > $D/bench_reference_arm.json 2> $D/bench_reference_arm.err
 # ncu: launch list (shares), DRAM bytes of the screening kernel, one full capture of it
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:kcf_ -c 400 --csv --log-file $D/launches_c2.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:kcf_(screen|finalize|pack|plan|tile)" -c 400 --csv --log-file $D/launches_c2.csv \
     python bench.py --only resident,e2e --steps 3 --warmup 3 --e2e-steps 1 > $D/ncu_launch.log 2>&1
 timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:kcf_screen_kernel -s 3 -c 1 --csv \
     --log-file $D/traffic_c2.csv python bench.py --only resident --steps 2 --warmup 3 > $D/ncu_traffic.log 2>&1
