@@ -262,6 +262,9 @@ struct KcfXgDev {
     uint32_t *okw, *start;               // validity / stretch-start bitmaps of the batch
     unsigned int *cursor;                // [world]: runs appended per owner so far
     uint32_t *flags;                     // [0]: a region overflowed
+    // owner of a home line without the 64-bit division of kcf_line_owner: own_mul = floor(2^32 world / n_lines) gives an
+    // estimate that is never too high, own_bound[r] = the first home line of rank r's slice corrects it
+    uint32_t own_mul, own_bound[KCF_XG_MAX_WORLD + 1];
 };
 
 // one run on the wire: a = plane 0 (k + len - 1 bits) | (len - 1) << 42 | (home & 0x3FFFF) << 46, b = plane 1 | (home >> 18) << 42

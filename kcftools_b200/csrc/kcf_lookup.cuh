@@ -125,6 +125,14 @@ __host__ __device__ __forceinline__ uint32_t kcf_line_owner(uint32_t home, uint6
     return (uint32_t)(((uint64_t)home * world) / n_lines);
 }
 
+// the same value from the precomputed map of an exchange workspace (exact: the estimate is a lower bound, the slice bounds decide)
+__device__ __forceinline__ uint32_t kcf_line_owner_mapped(uint32_t home, const KcfXgDev &x)
+{
+    uint32_t e = __umulhi(home, x.own_mul);
+    while (home >= x.own_bound[e + 1]) ++e;
+    return e;
+}
+
 // the 16-bit mask of a home line (stored inverted so that the table can be initialised with 0xFF bytes)
 __device__ __forceinline__ uint32_t kcf_mask_from_word31(uint32_t w31) { return (~w31) >> 16; }
 

@@ -347,6 +347,7 @@ struct kcf_xg {
     int rank = 0, world = 1;
     uint64_t batch_positions = 0, cap = 0;
     uint32_t cbytes = 4;
+    uint64_t n_lines = 0;          // of the whole table (all slices)
     uint8_t *block = nullptr;      // exported: inbox runs | runs per sender | back
     uint64_t block_bytes = 0, off_keys = 0, off_homes = 0, off_count = 0, off_back = 0; // off_keys: the run entries
     uint8_t *local = nullptr;      // pos_slot | okw | start | cursor | flags
@@ -548,6 +549,9 @@ static void kcf_xg_build_dev(kcf_xg *x)
     d.cbytes = x->cbytes;
     d.stride = x->cbytes == 1 ? 16u : 48u;
     d.cap = x->cap;
+    d.own_mul = (uint32_t)std::min<uint64_t>(((uint64_t)x->world << 32) / x->n_lines, 0xFFFFFFFFULL);
+    for (int r = 0; r <= KCF_XG_MAX_WORLD; ++r) // first home line with kcf_line_owner >= r
+        d.own_bound[r] = r >= x->world ? 0xFFFFFFFFu : (uint32_t)(((uint64_t)r * x->n_lines + (uint64_t)x->world - 1) / (uint64_t)x->world);
     for (int r = 0; r < x->world; ++r) {
         uint8_t *b = x->peer[r];
         d.in_runs[r] = reinterpret_cast<uint4 *>(b + x->off_keys) + (uint64_t)x->rank * x->cap;
@@ -579,6 +583,7 @@ extern "C" int kcf_xg_create(kcf_ctx *ctx, kcf_db *db, int rank, int world, uint
     x->rank = rank;
     x->world = world;
     x->batch_positions = batch_tiles * KCF_TILE;
+    x->n_lines = db->geom.n_lines;
     // A region holds RUNS (kcf_internal.cuh).  A sender's runs spread over the owners by a hash of their minimizer, 1/world
     // each; a window of random sequence makes one run per ~5 positions (6 k-mers on average, cut at every 32nd position),
     // the worst case — every k-mer alone — one per position.  Half the positions per owner share plus a fixed slack covers

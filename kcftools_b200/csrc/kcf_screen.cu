@@ -441,45 +441,37 @@ __global__ void __launch_bounds__(32 * KCF_WPC, KCF_MIN_WARPS / KCF_WPC) kcf_scr
                         const uint64_t nm = (1ULL << (k + len - 1u)) - 1ULL;
                         const uint64_t p0 = (((uint64_t)__funnelshift_r(pb.x, pc.x, sh) << 32) | __funnelshift_r(pa.x, pb.x, sh)) & nm;
                         const uint64_t p1 = (((uint64_t)__funnelshift_r(pb.y, pc.y, sh) << 32) | __funnelshift_r(pa.y, pb.y, sh)) & nm;
-                        const uint32_t owner = kcf_line_owner(home, g.n_lines, p.xg.world);
-                        uint32_t todo = __activemask();
-                        const uint32_t heads = todo;
-                        while (todo) {
-                            const uint32_t leader = __ffs(todo) - 1;
-                            const uint32_t o = __shfl_sync(heads, owner, leader);
-                            const uint32_t same = __ballot_sync(heads, owner == o) & heads;
-                            // entries come out of this warp's slab of the owner's region; a slab that cannot take the step's runs
-                            // is closed (its rest marked empty) and a new one drawn from the region's cursor: one global atomic
-                            // per KCF_XG_SLAB runs and owner instead of one per warp step — every warp of the GPU adds to the same
-                            // `world` counters, and same-address atomics serialise (measured: 68 ms of a 98 ms step)
-                            const uint32_t need = __popc(same);
-                            uint32_t off = W.xg_next[o];
-                            const uint32_t end = W.xg_end[o];
-                            if (off + need > end) {
-                                if (owner == o) {
-                                    const uint32_t r = __popc(same & ((1u << lane) - 1u));
-                                    for (uint32_t h = off + r; h < end; h += need)
-                                        if (h < p.xg.cap) p.xg.in_runs[o][h] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-                                }
-                                uint32_t nb = 0;
-                                if (lane == leader) nb = atomicAdd(&p.xg.cursor[o], (unsigned int)KCF_XG_SLAB);
-                                off = __shfl_sync(heads, nb, leader);
-                                if (lane == leader) W.xg_end[o] = off + KCF_XG_SLAB;
-                            }
-                            if (lane == leader) W.xg_next[o] = off + need;
-                            if (owner == o) {
-                                const uint32_t idx = off + __popc(same & ((1u << lane) - 1u));
-                                if (idx < p.xg.cap) {
-                                    uint64_t ea, eb;
-                                    kcf_xg_pack_run(p0, p1, len, home, ea, eb);
-                                    p.xg.in_runs[o][idx] = make_uint4((uint32_t)ea, (uint32_t)(ea >> 32), (uint32_t)eb, (uint32_t)(eb >> 32));
-                                    slot = (o << 28) | idx;
-                                } else {
-                                    p.xg.flags[0] = 1u; // region full: the host reports it (the run reads as absent meanwhile)
-                                    slot = 0xFFFFFFFFu;
-                                }
-                            }
-                            todo &= ~same;
+                        const uint32_t owner = kcf_line_owner_mapped(home, p.xg);
+                        // the heads bound for one owner find each other with one match instruction (a loop over the owners
+                        // present cost one round of shuffles and ballots per owner) and take
+                        // consecutive entries of this warp's slab of that owner's region; a slab that cannot take the step's
+                        // runs is closed (its rest marked empty) and a new one drawn from the region's cursor: one global
+                        // atomic per KCF_XG_SLAB runs and owner instead of one per warp step — every warp of the GPU adds to the
+                        // same `world` counters, and same-address atomics serialise (measured: 68 ms of a 98 ms step)
+                        const uint32_t heads = headmask; // every run head of this step is here
+                        const uint32_t same = __match_any_sync(heads, owner);
+                        const uint32_t leader = __ffs(same) - 1, need = __popc(same), rk = __popc(same & ((1u << lane) - 1u));
+                        uint32_t off = W.xg_next[owner];
+                        const uint32_t end = W.xg_end[owner];
+                        if (off + need > end) { // uniform over the owner's heads
+                            for (uint32_t h = off + rk; h < end; h += need)
+                                if (h < p.xg.cap) p.xg.in_runs[owner][h] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                            uint32_t nb = 0;
+                            if (lane == leader) nb = atomicAdd(&p.xg.cursor[owner], (unsigned int)KCF_XG_SLAB);
+                            off = __shfl_sync(same, nb, leader); // also: every head of the group has read the old slab bounds by now
+                            if (lane == leader) W.xg_end[owner] = off + KCF_XG_SLAB;
+                        }
+                        __syncwarp(heads); // the bounds are read by all before any leader moves them
+                        if (lane == leader) W.xg_next[owner] = off + need;
+                        const uint32_t idx = off + rk;
+                        if (idx < p.xg.cap) {
+                            uint64_t ea, eb;
+                            kcf_xg_pack_run(p0, p1, len, home, ea, eb);
+                            p.xg.in_runs[owner][idx] = make_uint4((uint32_t)ea, (uint32_t)(ea >> 32), (uint32_t)eb, (uint32_t)(eb >> 32));
+                            slot = (owner << 28) | idx;
+                        } else {
+                            p.xg.flags[0] = 1u; // region full: the host reports it (the run reads as absent meanwhile)
+                            slot = 0xFFFFFFFFu;
                         }
                     }
                     __syncwarp();
