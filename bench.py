@@ -886,8 +886,8 @@ def placements_leg(torch, dist, ctx, stream, device, rank, world, args, barrier,
         out["a2a_nccl_collectives"] = {"value": kmers / (wall2 * 1e-3), "ms_per_step": wall2, "rows_equal_replicated": bool(baseline_rows is None or rows_equal(rows2, baseline_rows)),
                                        "nvlink_bytes_per_step": int(allsum(int(phases2.get("_bytes_out", 0)) + int(phases2.get("_bytes_back", 0))) / max(phases2.get("_n", 1), 1)),
                                        "phases_ms": {k_: allmax(v) / max(phases2.get("_n", 1), 1) * 1e3 for k_, v in phases2.items() if not k_.startswith("_")}}
-        if getattr(plan, "_exchange", None) is not None:
-            plan._exchange.close()
+        for x_ in getattr(plan, "_exchange", None) or []:
+            x_.close()
         plan.close()
         db.close()
     except Exception as e:

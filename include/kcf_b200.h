@@ -241,6 +241,13 @@ int kcf_xg_send(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, kcf_xg *x, uint64_t ti
 int kcf_xg_answer(kcf_ctx *ctx, kcf_db *db, kcf_xg *x);
 int kcf_xg_fold(kcf_ctx *ctx, kcf_plan *plan, kcf_xg *x, uint64_t tile_begin, uint64_t tile_end, int32_t min_count);
 int kcf_xg_status(kcf_xg *x, uint64_t *bytes_out_per_run, uint64_t *bytes_back_per_run, uint64_t *runs_sent_last_batch);
+/* Pipelining with two workspaces: after kcf_xg_pipeline the sends of this workspace run on a stream of their own, on at most
+ * send_ctas_per_sm resident CTAs per SM (0 = no cap), ordered after what the context's stream held when kcf_xg_send was
+ * called; kcf_xg_join makes the context's stream wait for the workspace's last send.  Per batch b a rank then queues
+ * send(b + 1, other workspace), answer(b), join(other), barrier, fold(b): one barrier per batch, the send of the next batch
+ * beside the answers of this one. */
+int kcf_xg_pipeline(kcf_xg *x, uint32_t send_ctas_per_sm);
+int kcf_xg_join(kcf_ctx *ctx, kcf_xg *x);
 
 /* Scan placement — the second way to screen against a partitioned table, without moving k-mers: the plan holds ALL
  * windows on every rank (the 2-bit reference is replicated; it is small next to the table), every rank runs

@@ -84,6 +84,8 @@ SYMBOLS = {
     "kcf_xg_answer": (C.c_int, [_P, _P, _P]),
     "kcf_xg_fold": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_int32]),
     "kcf_xg_status": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "kcf_xg_pipeline": (C.c_int, [_P, C.c_uint32]),
+    "kcf_xg_join": (C.c_int, [_P, _P]),
     "kcf_plan_finalize": (C.c_int, [_P, _P, C.POINTER(C.c_double)]),
     "kcf_cohort_create": (C.c_int, [_P, C.c_uint64, C.c_uint32, _P, _P, C.POINTER(_P)]),
     "kcf_cohort_destroy": (None, [_P]),

@@ -293,8 +293,10 @@ int kcf_fail(kcf_ctx *ctx, int code, const char *fmt, ...);
 void *kcf_pool_get(kcf_ctx *ctx, size_t bytes);
 void kcf_pool_put(kcf_ctx *ctx, void *p, size_t bytes);
 void kcf_pool_trim(kcf_ctx *ctx); // free every pooled block (called when a large allocation fails)
+int kcf_sync_seqs(kcf_ctx *ctx); // uploads the sequence table when it changed (on the context's stream)
 int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t min_count, uint64_t tile_begin, uint64_t tile_end,
-                      int32_t *d_counts, bool extract, uint32_t *d_owned_hit, unsigned long long *d_owned_sum, const KcfXgDev *xsend = nullptr);
+                      int32_t *d_counts, bool extract, uint32_t *d_owned_hit, unsigned long long *d_owned_sum, const KcfXgDev *xsend = nullptr,
+                      cudaStream_t on_stream = nullptr, uint32_t ctas_per_sm_cap = 0);
 #define KCF_CUDA(ctx, call)                                                                        \
     do {                                                                                           \
         cudaError_t e__ = (call);                                                                  \

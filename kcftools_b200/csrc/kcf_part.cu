@@ -355,6 +355,10 @@ struct kcf_xg {
     bool opened[KCF_XG_MAX_WORLD] = {false};
     bool connected = false;
     KcfXgDev dev{};
+    // pipelined use (kcf_xg_pipeline): sends run on their own stream with a capped grid, beside the answers of the batch before
+    cudaStream_t send_stream = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_sent = nullptr;
+    uint32_t send_ctas = 0;
 };
 
 // tell every owner how many runs this rank appended to its inbox region
@@ -661,6 +665,12 @@ extern "C" void kcf_xg_destroy(kcf_xg *x)
     cudaStreamSynchronize(x->ctx->stream);
     for (int r = 0; r < x->world; ++r)
         if (x->opened[r]) cudaIpcCloseMemHandle(x->peer[r]);
+    if (x->send_stream) {
+        cudaStreamSynchronize(x->send_stream);
+        cudaStreamDestroy(x->send_stream);
+        cudaEventDestroy(x->ev_main);
+        cudaEventDestroy(x->ev_sent);
+    }
     cudaFree(x->block);
     cudaFree(x->local);
     delete x;
@@ -675,17 +685,53 @@ extern "C" int kcf_xg_send(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, kcf_xg *x, 
     KCF_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint64_t nt = tile_begin < tile_end ? tile_end - tile_begin : 0;
     if (nt * KCF_TILE > x->batch_positions) return kcf_fail(ctx, KCF_ERR_ARG, "exchange: batch of %llu tiles exceeds the workspace", (unsigned long long)nt);
-    KCF_CUDA(ctx, cudaMemsetAsync(x->dev.cursor, 0, KCF_XG_MAX_WORLD * sizeof(unsigned int), ctx->stream));
+    cudaStream_t st = ctx->stream;
+    int rcs = kcf_sync_seqs(ctx); // (queues on the context's stream when the sequence table changed)
+    if (rcs != KCF_OK) return rcs;
+    if (x->send_stream) { // after everything queued on the context's stream so far (the fold that last read this workspace among it)
+        st = x->send_stream;
+        KCF_CUDA(ctx, cudaEventRecord(x->ev_main, ctx->stream));
+        KCF_CUDA(ctx, cudaStreamWaitEvent(st, x->ev_main, 0));
+    }
+    KCF_CUDA(ctx, cudaMemsetAsync(x->dev.cursor, 0, KCF_XG_MAX_WORLD * sizeof(unsigned int), st));
     if (nt) {
         // chunks past the end of a window are never visited: their positions must read "no k-mer"
-        KCF_CUDA(ctx, cudaMemsetAsync(x->dev.pos_slot, 0xFF, nt * KCF_TILE * 4, ctx->stream));
-        KCF_CUDA(ctx, cudaMemsetAsync(x->dev.okw, 0, nt * (KCF_TILE / 32) * 4, ctx->stream));
-        KCF_CUDA(ctx, cudaMemsetAsync(x->dev.start, 0, nt * (KCF_TILE / 32) * 4, ctx->stream));
-        int rc = kcf_launch_screen(ctx, db, plan, 1, tile_begin, tile_end, nullptr, true, nullptr, nullptr, &x->dev);
+        KCF_CUDA(ctx, cudaMemsetAsync(x->dev.pos_slot, 0xFF, nt * KCF_TILE * 4, st));
+        KCF_CUDA(ctx, cudaMemsetAsync(x->dev.okw, 0, nt * (KCF_TILE / 32) * 4, st));
+        KCF_CUDA(ctx, cudaMemsetAsync(x->dev.start, 0, nt * (KCF_TILE / 32) * 4, st));
+        int rc = kcf_launch_screen(ctx, db, plan, 1, tile_begin, tile_end, nullptr, true, nullptr, nullptr, &x->dev, x->send_stream, x->send_ctas);
         if (rc != KCF_OK) return rc;
     }
-    kcf_xg_publish_kernel<<<1, 32, 0, ctx->stream>>>(x->dev); // every rank publishes every batch, empty or not
+    kcf_xg_publish_kernel<<<1, 32, 0, st>>>(x->dev); // every rank publishes every batch, empty or not
     KCF_CUDA(ctx, cudaGetLastError());
+    if (x->send_stream) KCF_CUDA(ctx, cudaEventRecord(x->ev_sent, st));
+    return KCF_OK;
+}
+
+// Pipelined use: from now on kcf_xg_send of this workspace runs on a stream of its own, on at most send_ctas_per_sm resident
+// CTAs per SM (0 = no cap), ordered after whatever the context's stream holds at the time of the call; kcf_xg_join makes the
+// context's stream wait for the last send.  With two workspaces a rank sends batch b + 1 while it answers batch b.
+extern "C" int kcf_xg_pipeline(kcf_xg *x, uint32_t send_ctas_per_sm)
+{
+    if (!x) return KCF_ERR_ARG;
+    kcf_ctx *ctx = x->ctx;
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!x->send_stream) {
+        KCF_CUDA(ctx, cudaStreamCreateWithFlags(&x->send_stream, cudaStreamNonBlocking));
+        KCF_CUDA(ctx, cudaEventCreateWithFlags(&x->ev_main, cudaEventDisableTiming));
+        KCF_CUDA(ctx, cudaEventCreateWithFlags(&x->ev_sent, cudaEventDisableTiming));
+        KCF_CUDA(ctx, cudaEventRecord(x->ev_sent, x->send_stream));
+    }
+    x->send_ctas = send_ctas_per_sm;
+    return KCF_OK;
+}
+
+extern "C" int kcf_xg_join(kcf_ctx *ctx, kcf_xg *x)
+{
+    if (!ctx || !x || x->ctx != ctx) return KCF_ERR_ARG;
+    if (!x->send_stream) return KCF_OK;
+    KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    KCF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, x->ev_sent, 0));
     return KCF_OK;
 }
 
@@ -720,6 +766,7 @@ extern "C" int kcf_xg_status(kcf_xg *x, uint64_t *bytes_out_per_kmer, uint64_t *
     if (!x) return KCF_ERR_ARG;
     kcf_ctx *ctx = x->ctx;
     KCF_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (x->send_stream) KCF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, x->ev_sent, 0));
     uint32_t f = 0;
     unsigned int cur[KCF_XG_MAX_WORLD] = {0};
     KCF_CUDA(ctx, cudaMemcpyAsync(&f, x->dev.flags, 4, cudaMemcpyDeviceToHost, ctx->stream));

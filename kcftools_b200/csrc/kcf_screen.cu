@@ -754,7 +754,7 @@ extern "C" int kcf_measure_random_line_rate(kcf_ctx *ctx, uint64_t n_bytes, uint
 // ---- host side: plans ---------------------------------------------------------------------------
 // bring the device-side sequence table up to date, stream-ordered and without a host synchronisation (a host that
 // uploads one chromosome after the other and screens each as it arrives must not stall on earlier work)
-static int kcf_sync_seqs(kcf_ctx *ctx)
+int kcf_sync_seqs(kcf_ctx *ctx)
 {
     const size_t n = ctx->seqs.size();
     if (ctx->d_seqs_cap < std::max<size_t>(n, 1)) {
@@ -911,8 +911,10 @@ extern "C" int kcf_plan_create(kcf_ctx *ctx, int32_t kmer_length, const kcf_wind
 }
 
 int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t min_count, uint64_t tile_begin, uint64_t tile_end,
-                      int32_t *d_counts, bool extract, uint32_t *d_owned_hit, unsigned long long *d_owned_sum, const KcfXgDev *xsend)
+                      int32_t *d_counts, bool extract, uint32_t *d_owned_hit, unsigned long long *d_owned_sum, const KcfXgDev *xsend,
+                      cudaStream_t on_stream, uint32_t ctas_per_sm_cap)
 {
+    const cudaStream_t stream = on_stream ? on_stream : ctx->stream; // the exchange's send may run beside the answers of the batch before
     const bool owned = d_owned_hit != nullptr;
     if (xsend) extract = true;
     if (!extract && !owned && db->part_world > 1)
@@ -923,7 +925,7 @@ int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t min_coun
     if (rc != KCF_OK) return rc;
     unsigned long long *d_counter = reinterpret_cast<unsigned long long *>(
         reinterpret_cast<uint8_t *>(plan->d_tile_sum) + std::max<uint64_t>(plan->n_tiles, 1) * sizeof(KcfGap));
-    KCF_CUDA(ctx, cudaMemsetAsync(d_counter, 0, 8, ctx->stream));
+    KCF_CUDA(ctx, cudaMemsetAsync(d_counter, 0, 8, stream));
     KcfScreenParams p{};
     p.seqs = ctx->d_seqs;
     p.wins = plan->d_wins;
@@ -973,8 +975,9 @@ int kcf_launch_screen(kcf_ctx *ctx, kcf_db *db, kcf_plan *plan, int32_t min_coun
     int per_sm = 0;
     KCF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * KCF_WPC, smem));
     const uint64_t n = tile_end - tile_begin;
+    if (ctas_per_sm_cap) per_sm = std::min<int>(per_sm, (int)ctas_per_sm_cap); // a persistent grid that leaves room for another kernel
     const unsigned grid = (unsigned)std::min<uint64_t>((n + KCF_WPC - 1) / KCF_WPC, (uint64_t)ctx->sm_count * std::max(per_sm, 1));
-    if (grid) kern<<<grid, 32 * KCF_WPC, smem, ctx->stream>>>(p, db->geom);
+    if (grid) kern<<<grid, 32 * KCF_WPC, smem, stream>>>(p, db->geom);
     KCF_CUDA(ctx, cudaGetLastError());
     return KCF_OK;
 }

@@ -162,6 +162,14 @@ class Exchange:
             blob = b"".join(handles)
             self.ctx._check(self.ctx._lib.kcf_xg_connect(self._h, blob, None))
 
+    def pipeline(self, send_ctas_per_sm: int):
+        """sends of this workspace run on their own stream from now on, on at most that many resident CTAs per SM"""
+        self.ctx._check(self.ctx._lib.kcf_xg_pipeline(self._h, send_ctas_per_sm))
+
+    def join(self):
+        """the context's stream waits for this workspace's last send"""
+        self.ctx._check(self.ctx._lib.kcf_xg_join(self.ctx._h, self._h))
+
     def status(self) -> tuple[int, int, int]:
         """synchronises; raises on a workspace overflow.  Returns (bytes out per run, bytes back per run, runs sent in the last batch)"""
         a, b, n = C.c_uint64(), C.c_uint64(), C.c_uint64()
@@ -174,20 +182,51 @@ class Exchange:
             self._h = C.c_void_p()
 
 
-def _exchange_of(ctx, db, plan, rank, world, batch_tiles, connect):
-    """the workspace is kept on the plan: created and connected once, reused by every later call"""
-    x = getattr(plan, "_exchange", None)
-    if x is None or x.world != world or x.batch_tiles != batch_tiles:
-        if x is not None:
+def _exchange_of(ctx, db, plan, rank, world, batch_tiles, connect, n: int = 1):
+    """the workspaces are kept on the plan: created and connected once, reused by every later call"""
+    xs = getattr(plan, "_exchange", None)
+    if xs is None or len(xs) < n or xs[0].world != world or xs[0].batch_tiles != batch_tiles:
+        for x in xs or []:
             x.close()
-        x = Exchange(ctx, db, rank, world, batch_tiles)
-        connect(x)
-        plan._exchange = x
-    return x
+        xs = []
+        for _ in range(n):
+            x = Exchange(ctx, db, rank, world, batch_tiles)
+            connect(x)
+            xs.append(x)
+        plan._exchange = xs
+    return xs
+
+
+SEND_CTAS = 10  # of the 20 CTAs per SM the screening kernel would take: the other half of the SM answers the batch before
+
+
+def _pipelined(parts, nb, batch_tiles, min_count, barrier):
+    """The batch loop with the send of batch b + 1 beside the answers of batch b.  `parts` = [(ctx, db, plan, (x0, x1)), ...]
+    (one entry per rank this process drives: one under torch.distributed, all of them in the lockstep harness), `barrier()` =
+    every rank's queued sends and answers have landed (queued on the library's stream, or a device synchronisation)."""
+    def send(b, which):
+        for ctx, db, plan, xs in parts:
+            ctx._check(ctx._lib.kcf_xg_send(ctx._h, db._h, plan._h, xs[which]._h, b * batch_tiles, (b + 1) * batch_tiles))
+
+    send(0, 0)
+    for ctx, db, plan, xs in parts:
+        xs[0].join()
+    barrier()
+    for b in range(nb):
+        cur, nxt = b % 2, (b + 1) % 2
+        if b + 1 < nb:
+            send(b + 1, nxt)  # ordered after the fold of batch b - 1, which last read that workspace
+        for ctx, db, plan, xs in parts:
+            ctx._check(ctx._lib.kcf_xg_answer(ctx._h, db._h, xs[cur]._h))
+            if b + 1 < nb:
+                xs[nxt].join()
+        barrier()
+        for ctx, db, plan, xs in parts:
+            ctx._check(ctx._lib.kcf_xg_fold(ctx._h, plan._h, xs[cur]._h, b * batch_tiles, (b + 1) * batch_tiles, min_count))
 
 
 def screen_partitioned(ctx, db, plan, group=None, min_count: int = 1, weights=(0.3, 0.3, 0.4), batch_tiles: int = BATCH_TILES,
-                       phases: dict | None = None) -> np.ndarray:
+                       phases: dict | None = None, pipelined: bool = False) -> np.ndarray:
     """one rank of a torch.distributed job (NCCL, one process per GPU): `db` was opened with placement=1 after
     ctx.set_partition(rank, world), `plan` holds THIS rank's windows.  Returns this rank's rows.
 
@@ -195,7 +234,10 @@ def screen_partitioned(ctx, db, plan, group=None, min_count: int = 1, weights=(0
     11 k-mers — to its owner's inbox over NVLink), a barrier, kcf_xg_answer (owners fetch a run's line once, look its k-mers up,
     store the counts into the requesters' workspaces), a barrier, kcf_xg_fold.  Everything is
     queued on the library's stream — the barriers are one-element all-reduces issued on that same stream — so the host
-    never waits inside the loop.  `phases` (optional dict) accumulates seconds per phase (a device synchronisation is then
+    never waits inside the loop.  `pipelined=True` runs a job of more than one batch over two workspaces (_pipelined: the
+    send of batch b + 1 on half of every SM beside the answers of batch b, one barrier per batch) — measured SLOWER than the
+    plain sequence on 2 x B200 (47.3 against 39.2 ms per 3e9-k-mer job, profiles/r2x): the two kernels compete for the same
+    memory pipeline, they do not fill each other's gaps; kept as an option, off by default.  `phases` (optional dict) accumulates seconds per phase (a device synchronisation is then
     inserted after each) and `_bytes_out` / `_bytes_back`, the bytes this rank put on the wire."""
     import time
     import torch
@@ -212,12 +254,24 @@ def screen_partitioned(ctx, db, plan, group=None, min_count: int = 1, weights=(0
         handles = [None] * world
         dist.all_gather_object(handles, handle, group=group)
         x.connect(handles=handles)
-    x = _exchange_of(ctx, db, plan, me, world, batch_tiles, connect)
+    pipelined = pipelined and phases is None and max_tiles > batch_tiles
+    xs = _exchange_of(ctx, db, plan, me, world, batch_tiles, connect, 2 if pipelined else 1)
+    token = torch.zeros(1, device=dev)
+    if pipelined:  # two workspaces: batch b + 1 is sent while batch b is answered, one barrier per batch
+        for x_ in xs[:2]:
+            x_.pipeline(SEND_CTAS)
+        with torch.cuda.stream(stream):
+            _pipelined([(ctx, db, plan, xs)], (max_tiles + batch_tiles - 1) // batch_tiles, batch_tiles, min_count,
+                       lambda: dist.all_reduce(token, group=group))
+        for x_ in xs[:2]:
+            x_.status()
+        return _finish(ctx, plan, weights)
+    x = xs[0]
+    x.pipeline(0)
     tt = phases if phases is not None else {}
     for k_ in ("send", "barrier_1", "answer", "barrier_2", "fold"):
         tt.setdefault(k_, 0.0)
     tt["_n"] = tt.get("_n", 0) + 1
-    token = torch.zeros(1, device=dev)
 
     def lap(name, t):
         if phases is not None:
@@ -229,6 +283,7 @@ def screen_partitioned(ctx, db, plan, group=None, min_count: int = 1, weights=(0
             t1 = t0 + batch_tiles
             t = time.perf_counter()
             ctx._check(ctx._lib.kcf_xg_send(ctx._h, db._h, plan._h, x._h, t0, t1))
+            x.join()
             t = lap("send", t)
             if phases is not None:  # what crosses NVLink: the runs of this batch that other ranks answer, there and back
                 out_b, back_b, runs = x.status()
@@ -248,35 +303,49 @@ def screen_partitioned(ctx, db, plan, group=None, min_count: int = 1, weights=(0
     return _finish(ctx, plan, weights)
 
 
-def screen_partitioned_local(ranks, min_count: int = 1, weights=(0.3, 0.3, 0.4), batch_tiles: int = BATCH_TILES) -> list[np.ndarray]:
+def screen_partitioned_local(ranks, min_count: int = 1, weights=(0.3, 0.3, 0.4), batch_tiles: int = BATCH_TILES,
+                             pipelined: bool = False) -> list[np.ndarray]:
     """`ranks` = [(ctx, db, plan), ...]: every slice of one database, each with its own window shard, all contexts on GPUs
     of THIS process (typically the same one).  The same library calls as screen_partitioned, the workspaces connected by
     plain device pointers, the barriers replaced by device synchronisations."""
     import torch
     world = len(ranks)
     batch_tiles = int(min(batch_tiles, max(max(r[2].n_tiles for r in ranks), 1)))
-    xs = [Exchange(ctx, db, i, world, batch_tiles) for i, (ctx, db, plan) in enumerate(ranks)]
-    ptrs = [x.export()[1] for x in xs]
-    for x in xs:
-        x.connect(pointers=ptrs)
     n_tiles = max(r[2].n_tiles for r in ranks)
-    try:
-        for t0 in range(0, max(n_tiles, 1), batch_tiles):
-            t1 = t0 + batch_tiles
-            for x, (ctx, db, plan) in zip(xs, ranks):
-                ctx._check(ctx._lib.kcf_xg_send(ctx._h, db._h, plan._h, x._h, t0, t1))
-            torch.cuda.synchronize()
-            for x, (ctx, db, plan) in zip(xs, ranks):
-                ctx._check(ctx._lib.kcf_xg_answer(ctx._h, db._h, x._h))
-            torch.cuda.synchronize()
-            for x, (ctx, db, plan) in zip(xs, ranks):
-                ctx._check(ctx._lib.kcf_xg_fold(ctx._h, plan._h, x._h, t0, t1, min_count))
+    pairs = []
+    for _ in range(2 if pipelined else 1):
+        xs = [Exchange(ctx, db, i, world, batch_tiles) for i, (ctx, db, plan) in enumerate(ranks)]
+        ptrs = [x.export()[1] for x in xs]
         for x in xs:
-            x.status()
+            x.connect(pointers=ptrs)
+        pairs.append(xs)
+    try:
+        if pipelined:
+            for xs in pairs:
+                for x in xs:
+                    x.pipeline(SEND_CTAS)
+            parts = [(ctx, db, plan, (pairs[0][i], pairs[1][i])) for i, (ctx, db, plan) in enumerate(ranks)]
+            _pipelined(parts, (max(n_tiles, 1) + batch_tiles - 1) // batch_tiles, batch_tiles, min_count, torch.cuda.synchronize)
+        else:
+            xs = pairs[0]
+            for t0 in range(0, max(n_tiles, 1), batch_tiles):
+                t1 = t0 + batch_tiles
+                for x, (ctx, db, plan) in zip(xs, ranks):
+                    ctx._check(ctx._lib.kcf_xg_send(ctx._h, db._h, plan._h, x._h, t0, t1))
+                torch.cuda.synchronize()
+                for x, (ctx, db, plan) in zip(xs, ranks):
+                    ctx._check(ctx._lib.kcf_xg_answer(ctx._h, db._h, x._h))
+                torch.cuda.synchronize()
+                for x, (ctx, db, plan) in zip(xs, ranks):
+                    ctx._check(ctx._lib.kcf_xg_fold(ctx._h, plan._h, x._h, t0, t1, min_count))
+        for xs in pairs:
+            for x in xs:
+                x.status()
         return [_finish(ctx, plan, weights) for (ctx, db, plan) in ranks]
     finally:
-        for x in xs:
-            x.close()
+        for xs in pairs:
+            for x in xs:
+                x.close()
 
 
 # ---- scan placement ---------------------------------------------------------------------------------------------------

@@ -289,17 +289,23 @@ def test_empty_inputs(ctx, sc_main):
     db.close()
 
 
-@pytest.mark.parametrize("world,batch_tiles,how", [(1, 1 << 16, "peer"), (2, 1 << 16, "peer"), (3, 7, "peer"), (4, 3, "peer"), (2, 1 << 16, "a2a"), (3, 7, "a2a")])
+@pytest.mark.parametrize("world,batch_tiles,how", [(1, 1 << 16, "peer"), (2, 1 << 16, "peer"), (3, 7, "peer"), (4, 3, "peer"), (2, 1 << 16, "a2a"), (3, 7, "a2a"),
+                                                   (1, 5, "pipelined"), (2, 1 << 16, "pipelined"), (3, 7, "pipelined"), (4, 3, "pipelined")])
 def test_partitioned_database_exchange_path(sc_main, world, batch_tiles, how):
     """placement 1: every rank holds 1/world of the table and a shard of the windows; k-mers travel to their owners and
     the counts come back.  "peer": the exchange over peer memory (kcf_xg_*: the screening kernel appends into the owners'
     inboxes, owners store the counts into the requesters' workspaces); "a2a": the same as all-to-all collectives over
-    caller-owned buffers (kcf_xchg_*).  Here all ranks live on cuda:0 — workspaces connected by plain pointers, the
+    caller-owned buffers (kcf_xchg_*); "pipelined": the peer exchange over two workspaces, the send of batch b + 1 on its own
+    stream beside the answers of batch b (kcf_xg_pipeline / kcf_xg_join).  Here all ranks live on cuda:0 — workspaces connected by plain pointers, the
     all-to-all done by slicing — the library calls are the ones the NCCL job makes."""
     from kcftools_b200 import shard
     from kcftools_b200.api import Context
     from kcftools_b200.partitioned import screen_partitioned_a2a_local, screen_partitioned_local
-    screen_partitioned_local = screen_partitioned_local if how == "peer" else screen_partitioned_a2a_local
+    if how == "a2a":
+        screen_partitioned_local = screen_partitioned_a2a_local
+    elif how == "pipelined":
+        import functools
+        screen_partitioned_local = functools.partial(screen_partitioned_local, pipelined=True)
     sc = sc_main
     wins, segs, *_ = fixed_windows(sc.seq_lens, 20_000, 0, 31)
     rc, want = _oracle_screen(sc, wins, segs, min_count=2, w=(0.2, 0.3, 0.5))

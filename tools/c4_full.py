@@ -87,8 +87,8 @@ def main():
     out["exchange"] = {"value": kmers / (ms * 1e-3), "ms_per_step": ms, "seconds_per_job": ms * 1e-3, "db_load_s": load_s, "table_bytes_per_gpu": int(db.info.table_bytes),
                        "table_bytes_per_record": db.info.table_bytes / max(db.info.resident_kmers, 1), "records_per_gpu": int(db.info.resident_kmers),
                        "job_kmers": kmers, "job_observed_kmers": obs, "stash_kmers": int(db.info.stash_kmers)}
-    if getattr(plan, "_exchange", None) is not None:
-        plan._exchange.close()
+    for x_ in getattr(plan, "_exchange", None) or []:
+        x_.close()
     plan.close()
     db.close()
     # ---- scan placement: 4 slices x (world / 4) window shards
