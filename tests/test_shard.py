@@ -203,3 +203,60 @@ def test_library_cut_equals_python_cut():
             want = shard.partition(shard.window_lengths(wins, segs), n)
             assert got == [r[0] for r in want] + [wins.size]
             assert all(a <= b for a, b in zip(got, got[1:]))
+
+
+def test_pipelined_exchange_schedule_orders_workspaces_and_barriers():
+    """host logic of the pipelined exchange (partitioned._pipelined) against a recording stand-in for the library: batch
+    b + 1 is sent into the OTHER workspace before batch b is answered, the context's stream joins that send before the
+    barrier, every batch is folded after its barrier from the workspace it was sent into, and a workspace is never sent
+    into again before the batch it held has been folded."""
+    from kcftools_b200 import partitioned
+
+    log = []
+
+    class Lib:
+        def kcf_xg_send(self, c, d, p, x, t0, t1):
+            log.append(("send", x, t0, t1))
+            return 0
+
+        def kcf_xg_answer(self, c, d, x):
+            log.append(("answer", x))
+            return 0
+
+        def kcf_xg_fold(self, c, p, x, t0, t1, mc):
+            log.append(("fold", x, t0, t1, mc))
+            return 0
+
+    class Ctx:
+        _lib, _h = Lib(), "ctx"
+
+        def _check(self, rc):
+            assert rc == 0
+
+    class H:
+        def __init__(self, h):
+            self._h = h
+
+    class X(H):
+        def join(self):
+            log.append(("join", self._h))
+
+    for nb in (1, 2, 5):
+        log.clear()
+        partitioned._pipelined([(Ctx(), H("db"), H("plan"), (X("x0"), X("x1")))], nb, 7, 2, lambda: log.append(("barrier",)))
+        sends = [e for e in log if e[0] == "send"]
+        assert [(e[1], e[2], e[3]) for e in sends] == [("x%d" % (b % 2), 7 * b, 7 * b + 7) for b in range(nb)]
+        folds = [e for e in log if e[0] == "fold"]
+        assert [(e[1], e[2], e[3], e[4]) for e in folds] == [("x%d" % (b % 2), 7 * b, 7 * b + 7, 2) for b in range(nb)]
+        assert sum(e[0] == "barrier" for e in log) == nb + 1  # one per batch + the one after the first send
+        for b in range(nb):
+            i_ans = [i for i, e in enumerate(log) if e[0] == "answer"][b]
+            i_fold = log.index(folds[b])
+            assert log[i_ans][1] == "x%d" % (b % 2)
+            assert ("barrier",) in log[i_ans:i_fold]  # the answers of all ranks land before the fold reads them
+            i_send = log.index(sends[b])
+            assert i_send < i_ans and ("join", "x%d" % (b % 2)) in log[i_send:i_ans + 2] and ("barrier",) in log[i_send:i_ans + 3 if b else i_ans]
+            if b + 1 < nb:  # the next batch goes out before this one is answered ...
+                assert log.index(sends[b + 1]) < i_ans
+            if b >= 2:      # ... and never into a workspace whose batch has not been folded
+                assert log.index(folds[b - 2]) < i_send
