@@ -761,7 +761,7 @@ extern "C" int kcf_xg_fold(kcf_ctx *ctx, kcf_plan *plan, kcf_xg *x, uint64_t til
 }
 
 // synchronises the stream; KCF_ERR_NOMEM when a region overflowed in any batch since the last call
-extern "C" int kcf_xg_status(kcf_xg *x, uint64_t *bytes_out_per_kmer, uint64_t *bytes_back_per_kmer, uint64_t *runs_sent_last_batch)
+extern "C" int kcf_xg_status(kcf_xg *x, uint64_t *bytes_out_per_run, uint64_t *bytes_back_per_run, uint64_t *runs_sent_last_batch)
 {
     if (!x) return KCF_ERR_ARG;
     kcf_ctx *ctx = x->ctx;
@@ -776,8 +776,8 @@ extern "C" int kcf_xg_status(kcf_xg *x, uint64_t *bytes_out_per_kmer, uint64_t *
         *runs_sent_last_batch = 0;
         for (int r = 0; r < x->world; ++r) *runs_sent_last_batch += cur[r];
     }
-    if (bytes_out_per_kmer) *bytes_out_per_kmer = 16;                              // per RUN
-    if (bytes_back_per_kmer) *bytes_back_per_kmer = x->cbytes == 1 ? 16 : 48;         // per RUN
+    if (bytes_out_per_run) *bytes_out_per_run = 16;
+    if (bytes_back_per_run) *bytes_back_per_run = x->cbytes == 1 ? 16 : 48;
     if (f) {
         cudaMemsetAsync(x->dev.flags, 0, 4, ctx->stream);
         return kcf_fail(ctx, KCF_ERR_NOMEM, "exchange: an inbox region of %llu entries overflowed; use smaller batches", (unsigned long long)x->cap);
