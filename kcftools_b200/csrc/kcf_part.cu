@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(128) kcf_xg_fold_kernel(KcfXgDev X, uint64_t n
         const uint32_t below = headmask & (0xFFFFFFFFu >> (31u - lane)); // run heads at or before this lane (runs never cross a word)
         const uint32_t hl = below ? 31u - __clz(below) : lane;
         const uint32_t hs = __shfl_sync(0xffffffffu, slot, hl);
-        const bool has = slot != 0xFFFFFFFFu && below != 0u;
+        const bool has = slot != 0xFFFFFFFFu && below != 0u && hs != 0xFFFFFFFFu; // (a head that found its region full has no slot: its run reads as absent)
         if (has) {
             const uint64_t at = ((uint64_t)(hs >> 28) * X.cap + (hs & 0x0FFFFFFFu)) * X.stride + (uint64_t)(lane - hl) * X.cbytes; // lane - hl: place in the run
             c = X.cbytes == 1 ? (uint32_t)X.my_back[at] : *reinterpret_cast<const uint32_t *>(X.my_back + at);
